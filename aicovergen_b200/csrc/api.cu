@@ -1,0 +1,50 @@
+// C ABI glue: error strings, launch counter, tap-GEMM dispatch.
+#include "tapgemm.cuh"
+#include <atomic>
+#include <cstdarg>
+
+namespace b200vc {
+
+static thread_local char g_err[1024] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+}  // namespace b200vc
+
+using namespace b200vc;
+
+extern "C" {
+
+const char* b200vc_version(void) { return "b200vc 0.1 (sm_100a)"; }
+const char* b200vc_last_error(void) { return g_err; }
+int64_t b200vc_launch_count(void) { return (int64_t)g_launches.load(); }
+int64_t b200vc_sizeof_tapgemm_params(void) { return (int64_t)sizeof(b200vc_tapgemm_params); }
+
+int b200vc_tapgemm(const b200vc_tapgemm_params* p, int backend, void* stream) {
+  B200VC_REQUIRE(p != nullptr, "tapgemm: null descriptor");
+  B200VC_REQUIRE(p->A && p->Wt && p->out, "tapgemm: null operand pointer");
+  B200VC_REQUIRE(p->ntaps >= 1 && p->ntaps <= B200VC_MAX_TAPS, "tapgemm: ntaps %d out of range", p->ntaps);
+  B200VC_REQUIRE(p->BW >= 1 && p->BH >= 1 && p->BW * p->BH == TG_TILE_M, "tapgemm: BW*BH must be 128 (got %d x %d)", p->BW, p->BH);
+  B200VC_REQUIRE(p->N >= 1 && p->Kc >= 1, "tapgemm: bad N/Kc %d/%d", p->N, p->Kc);
+  B200VC_REQUIRE(p->OW >= 1 && p->OH >= 1 && p->OB >= 1, "tapgemm: empty output space");
+  B200VC_REQUIRE(p->a_stride[0] == 1, "tapgemm: A must be channels-last (a_stride[0]==1)");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (backend == B200VC_BACKEND_TC_TF32) return tapgemm_tc_launch(*p, s);
+  if (backend == B200VC_BACKEND_SIMT_FP32) return tapgemm_simt_launch(*p, s);
+  set_last_error("tapgemm: unknown backend %d", backend);
+  return kErrInvalidArg;
+}
+
+int b200vc_tapgemm_tc_supported(const b200vc_tapgemm_params* p) {
+  return (p && tapgemm_tc_supported(*p)) ? 1 : 0;
+}
+
+}  // extern "C"

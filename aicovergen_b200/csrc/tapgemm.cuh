@@ -1,0 +1,118 @@
+// "Tap-GEMM": the one implicit-GEMM formulation every conv / linear / batched
+// matmul on the hot path is lowered to.
+//
+//   D[pixel, n] = sum_{tap} sum_{k < Kc}  A[pixel + tap.offset, tap.c_off + k] * W[tap.widx (+batch), n, k]
+//
+// * A is a rank-5 strided view (c, w, h, b, p) of a channels-last fp32 tensor;
+//   out-of-range coordinates read as zero (this is the conv zero padding).
+// * Output pixels are tiled BW x BH (BW*BH == 128 GEMM rows per tile).
+// * The epilogue (bias / activation / residuals / scale / second output) is
+//   shared verbatim by the SIMT fp32 kernel and the tcgen05 TF32 kernel so both
+//   produce the same graph semantics.
+//
+// Reference call sites this replaces (all cuDNN/cuBLAS library calls there):
+//   infer_pack/modules.py:299-312 (ResBlock1 convs), models.py:494-516
+//   (GeneratorNSF), modules.py:188-213 (WN), attentions.py:216-275 (1x1 convs,
+//   QK^T / PV matmuls), rmvpe.py:23-58 (Conv2d 3x3), fairseq HuBERT convs and
+//   linears, mdx.py:77 (the ONNX TFC-TDF net).
+#pragma once
+#include "common.cuh"
+#include "../../include/b200vc.h"
+
+namespace b200vc {
+
+constexpr int TG_MAX_TAPS = B200VC_MAX_TAPS;
+constexpr int TG_TILE_M = 128;
+
+// The descriptor is the public C struct (include/b200vc.h); see there for field docs.
+//   epilogue: v = acc + bias; v = act_pre(v); v += res; v *= scale; v += res2;
+//             v = act_post(v); out = v; out2 = act2(v)
+using TgTap = b200vc_tap;
+using TgParams = b200vc_tapgemm_params;
+
+// One GEMM row's addressing state.
+struct TgRow {
+  long long o_off;   // offset into out/out2/res2 (n added later)
+  long long r_off;   // offset into res
+  int brow;          // index for per-row bias
+  bool valid;
+};
+
+__device__ __forceinline__ TgRow tg_row(const TgParams& p, int b, int h, int w) {
+  TgRow r;
+  const int mh = h * p.osh + p.ooh, mw = w * p.osw + p.oow;
+  r.valid = (h < p.OH) && (w < p.OW) && (b < p.OB) && (mh >= 0) && (mh < p.o_fh) && (mw >= 0) &&
+            (mw < p.o_fw);
+  r.o_off = (long long)b * p.o_sb + (long long)mh * p.o_sh + (long long)mw * p.o_sw;
+  r.r_off = (long long)b * p.r_sb + (long long)h * p.r_sh + (long long)w * p.r_sw;
+  r.brow = h * p.OW + w;
+  return r;
+}
+
+__device__ __forceinline__ float tg_epi1(const TgParams& p, const TgRow& r, int n, float acc) {
+  float v = acc;
+  if (p.bias) v += p.bias_per_row ? __ldg(p.bias + r.brow) : __ldg(p.bias + n);
+  v = apply_act(v, p.act_pre, p.act_pre_p);
+  if (p.res) v += p.res[r.r_off + n];
+  v *= p.scale;
+  if (p.res2) v += p.res2[r.o_off + n];
+  v = apply_act(v, p.act_post, p.act_post_p);
+  return v;
+}
+
+// Scalar store of one element.
+__device__ __forceinline__ void tg_store1(const TgParams& p, const TgRow& r, int n, float acc) {
+  if (!r.valid || n >= p.N) return;
+  float v = tg_epi1(p, r, n, acc);
+  p.out[r.o_off + n] = v;
+  if (p.out2) p.out2[r.o_off + n] = apply_act(v, p.act2, p.act2_p);
+}
+
+// Store 4 consecutive n (n % 4 == 0). Uses float4 when p.vec4 and fully in range.
+__device__ __forceinline__ void tg_store4(const TgParams& p, const TgRow& r, int n, float4 acc) {
+  if (!r.valid || n >= p.N) return;
+  if ((p.vec4 & 2) && n + 3 < p.N) {
+    float v[4] = {acc.x, acc.y, acc.z, acc.w};
+    if (p.bias) {
+      if (p.bias_per_row) {
+        float bb = __ldg(p.bias + r.brow);
+        v[0] += bb; v[1] += bb; v[2] += bb; v[3] += bb;
+      } else {
+        float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+        v[0] += bb.x; v[1] += bb.y; v[2] += bb.z; v[3] += bb.w;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = apply_act(v[i], p.act_pre, p.act_pre_p);
+    if (p.res) {
+      float4 rr = *reinterpret_cast<const float4*>(p.res + r.r_off + n);
+      v[0] += rr.x; v[1] += rr.y; v[2] += rr.z; v[3] += rr.w;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] *= p.scale;
+    if (p.res2) {
+      float4 rr = *reinterpret_cast<const float4*>(p.res2 + r.o_off + n);
+      v[0] += rr.x; v[1] += rr.y; v[2] += rr.z; v[3] += rr.w;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = apply_act(v[i], p.act_post, p.act_post_p);
+    *reinterpret_cast<float4*>(p.out + r.o_off + n) = make_float4(v[0], v[1], v[2], v[3]);
+    if (p.out2) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = apply_act(v[i], p.act2, p.act2_p);
+      *reinterpret_cast<float4*>(p.out2 + r.o_off + n) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+  } else {
+    tg_store1(p, r, n + 0, acc.x);
+    tg_store1(p, r, n + 1, acc.y);
+    tg_store1(p, r, n + 2, acc.z);
+    tg_store1(p, r, n + 3, acc.w);
+  }
+}
+
+// Host-side launchers (tapgemm_simt.cu / tapgemm_tc.cu).
+int tapgemm_simt_launch(const TgParams& p, cudaStream_t stream);
+int tapgemm_tc_launch(const TgParams& p, cudaStream_t stream);
+bool tapgemm_tc_supported(const TgParams& p);
+
+}  // namespace b200vc

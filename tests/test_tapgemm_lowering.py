@@ -1,0 +1,156 @@
+"""Host logic: conv/linear -> tap-GEMM descriptor lowerings, checked on CPU with the
+descriptor emulator (tests/emu.py) against torch.nn.functional."""
+import torch
+import torch.nn.functional as F
+
+from aicovergen_b200 import tapgemm as tg
+from emu import emulate
+
+torch.manual_seed(0)
+
+
+def close(a, b, tol=1e-4):
+    err = (a - b).abs().max().item()
+    ref = b.abs().max().item() + 1e-9
+    assert err / ref < tol, (err, ref)
+
+
+def test_linear_bias_act():
+    x = torch.randn(300, 96)
+    w = torch.randn(40, 96)
+    b = torch.randn(40)
+    out = torch.zeros(300, 40)
+    op = tg.linear(x, w, out, tg.Epi(bias=b, act_pre=tg.ACT_LRELU, act_pre_p=0.1))
+    emulate(op)
+    close(out, F.leaky_relu(F.linear(x, w, b), 0.1))
+
+
+def test_conv1d_dilated_residual_dual():
+    T, Ci, Co, k, d = 257, 24, 24, 7, 3
+    x = torch.randn(T, Ci)
+    w = torch.randn(Co, Ci, k)
+    b = torch.randn(Co)
+    res = torch.randn(T, Co)
+    out = torch.zeros(T, Co)
+    out2 = torch.zeros(T, Co)
+    op = tg.conv1d(x, tg.pack_conv1d(w), out, dilation=d,
+                   epi=tg.Epi(bias=b, res=res, out2=out2, act2=tg.ACT_LRELU, act2_p=0.1))
+    emulate(op)
+    ref = F.conv1d(x.t()[None], w, b, dilation=d, padding=(k * d - d) // 2)[0].t() + res
+    close(out, ref)
+    close(out2, F.leaky_relu(ref, 0.1))
+
+
+def test_conv1d_column_slice_io():
+    # read a channel slice of a wider buffer, write into a slice of another
+    T = 130
+    xbuf = torch.randn(T, 48)
+    obuf = torch.zeros(T, 64)
+    w = torch.randn(16, 32, 3)
+    op = tg.conv1d(xbuf[:, 8:40], tg.pack_conv1d(w), obuf[:, 16:32])
+    emulate(op)
+    ref = F.conv1d(xbuf[:, 8:40].t()[None], w, padding=1)[0].t()
+    close(obuf[:, 16:32], ref)
+    assert obuf[:, :16].abs().max() == 0 and obuf[:, 32:].abs().max() == 0
+
+
+def test_conv1d_strided():
+    for (k, s, pad) in [(3, 2, 0), (2, 2, 0), (10, 5, 0), (4, 2, 1), (8, 4, 2)]:
+        T, Ci, Co = 40 * s, 8, 12
+        x = torch.randn(T, Ci)
+        w = torch.randn(Co, Ci, k)
+        ref = F.conv1d(x.t()[None], w, stride=s, padding=pad)[0].t()
+        out = torch.zeros(ref.shape[0], Co)
+        op = tg.conv1d_strided(x, tg.pack_conv1d(w), out, stride=s, pad=pad)
+        emulate(op)
+        close(out, ref)
+
+
+def test_conv_transpose1d():
+    for (k, s) in [(16, 10), (4, 2), (20, 8), (24, 12), (16, 8), (16, 4)]:
+        T, Ci, Co = 37, 16, 8
+        p = (k - s) // 2
+        x = torch.randn(T, Ci)
+        w = torch.randn(Ci, Co, k)
+        b = torch.randn(Co)
+        ref = F.conv_transpose1d(x.t()[None], w, b, stride=s, padding=p)[0].t()
+        out = torch.full((ref.shape[0], Co), float("nan"))
+        for op in tg.conv_transpose1d(x, tg.pack_convt1d(w), out, s, p, tg.Epi(bias=b)):
+            emulate(op)
+        close(out, ref)
+
+
+def test_conv2d_3x3_batch():
+    B, H, W, Ci, Co = 2, 9, 16, 8, 12
+    x = torch.randn(B, H, W, Ci)
+    w = torch.randn(Co, Ci, 3, 3)
+    b = torch.randn(Co)
+    out = torch.zeros(B, H, W, Co)
+    op = tg.conv2d(x, tg.pack_conv2d(w), out, 3, 3, (1, 1), tg.Epi(bias=b, act_pre=tg.ACT_RELU))
+    emulate(op)
+    ref = F.relu(F.conv2d(x.permute(0, 3, 1, 2), w, b, padding=1)).permute(0, 2, 3, 1)
+    close(out, ref)
+
+
+def test_conv_transpose2d_s2():
+    B, H, W, Ci, Co = 1, 5, 8, 6, 4
+    x = torch.randn(B, H, W, Ci)
+    w = torch.randn(Ci, Co, 3, 3)
+    ref = F.conv_transpose2d(x.permute(0, 3, 1, 2), w, stride=2, padding=1, output_padding=1).permute(0, 2, 3, 1)
+    out = torch.full(ref.shape, float("nan"))
+    for op in tg.conv_transpose2d_s2(x, tg.pack_convt2d(w), out, 3, 1):
+        emulate(op)
+    close(out, ref)
+    # 2x2 stride 2 (MDX up-sampling)
+    w2 = torch.randn(Ci, Co, 2, 2)
+    ref = F.conv_transpose2d(x.permute(0, 3, 1, 2), w2, stride=2).permute(0, 2, 3, 1)
+    out = torch.full(ref.shape, float("nan"))
+    for op in tg.conv_transpose2d_s2(x, tg.pack_convt2d(w2), out, 2, 0):
+        emulate(op)
+    close(out, ref)
+
+
+def test_conv2d_k2s2():
+    B, H, W, Ci, Co = 2, 6, 8, 4, 5
+    x = torch.randn(B, H, W, Ci)
+    w = torch.randn(Co, Ci, 2, 2)
+    out = torch.zeros(B, H // 2, W // 2, Co)
+    op = tg.conv2d_k2s2(x, tg.pack_conv2d(w), out)
+    emulate(op)
+    ref = F.conv2d(x.permute(0, 3, 1, 2), w, stride=2).permute(0, 2, 3, 1)
+    close(out, ref)
+
+
+def test_bmm_nt_heads():
+    T, H, D = 50, 3, 16
+    q = torch.randn(T, H * D)
+    k = torch.randn(T, H * D)
+    # per-head views of [T, H*D] without copies
+    qa = q.view(T, H, D).permute(1, 0, 2)
+    ka = k.view(T, H, D).permute(1, 0, 2)
+    Tp = 52
+    sc = torch.zeros(H, T, Tp)
+    op = tg.bmm_nt(qa, ka, sc[:, :, :T], tg.Epi(scale=0.25))
+    emulate(op)
+    ref = torch.einsum("htd,hsd->hts", qa, ka) * 0.25
+    close(sc[:, :, :T], ref)
+    # P @ V via V^T rows
+    vt = torch.randn(H * D, Tp)
+    vta = vt.view(H, D, Tp)[:, :, :T]
+    o = torch.zeros(T, H * D)
+    oa = o.view(T, H, D).permute(1, 0, 2)
+    op2 = tg.bmm_nt(sc[:, :, :T], vta, oa)
+    emulate(op2)
+    close(oa, torch.einsum("hts,hds->htd", sc[:, :, :T], vta))
+
+
+def test_bias_per_row_role_swap():
+    # V^T = Wv @ X^T + b[:,None]
+    T, Cc = 33, 24
+    x = torch.randn(T, Cc)
+    wv = torch.randn(20, Cc)
+    b = torch.randn(20)
+    out = torch.zeros(20, 36)
+    op = tg.linear(wv, x, out[:, :T], tg.Epi(bias=b, bias_per_row=True))
+    emulate(op)
+    close(out[:, :T], (x @ wv.t() + b).t())

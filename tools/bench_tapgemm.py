@@ -1,0 +1,64 @@
+"""Micro-benchmark of the tap-GEMM kernels on representative hot-path shapes.
+Usage (on the GPU box): python tools/bench_tapgemm.py [--simt]
+Prints one line per shape: backend, ms, TFLOP/s, GB/s (algorithmic in+out bytes)."""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from aicovergen_b200 import tapgemm as tg  # noqa: E402
+
+
+def timeit(fn, warm=3, iters=10):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / iters
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--simt", action="store_true")
+    ap.add_argument("--out", default="gpurun_out/bench_tapgemm.jsonl")
+    args = ap.parse_args()
+    backends = [("tc", tg.BACKEND_TC)] + ([("simt", tg.BACKEND_SIMT)] if args.simt else [])
+    shapes = [
+        # name, T, Cin, Cout, k, dil
+        ("voc.s1 C256 k3", 65980, 256, 256, 3, 1),
+        ("voc.s1 C256 k11", 65980, 256, 256, 11, 5),
+        ("voc.s2 C128 k7", 659800, 128, 128, 7, 3),
+        ("voc.s3 C64 k7", 1319600, 64, 64, 7, 3),
+        ("voc.s4 C32 k11", 2639200, 32, 32, 11, 1),
+        ("hubert.ffn1", 3299, 768, 3072, 1, 1),
+        ("hubert.ffn2", 3299, 3072, 768, 1, 1),
+        ("encp.ffn1 k3", 6598, 192, 768, 3, 1),
+        ("flow.wn k5", 6598, 192, 384, 5, 1),
+    ]
+    os.makedirs(os.path.dirname(args.out), exist_ok=True)
+    with open(args.out, "w") as f:
+        for name, T, Ci, Co, k, d in shapes:
+            x = torch.randn(T, Ci, device="cuda")
+            w = torch.randn(k, Co, Ci, device="cuda") / (Ci * k) ** 0.5
+            b = torch.randn(Co, device="cuda")
+            out = torch.empty(T, Co, device="cuda")
+            for bname, be in backends:
+                op = tg.conv1d(x, w, out, dilation=d, epi=tg.Epi(bias=b, act_pre=tg.ACT_LRELU, act_pre_p=0.1), backend=be)
+                ms = timeit(op)
+                fl = 2.0 * T * Ci * Co * k
+                by = 4.0 * T * (Ci + Co)
+                rec = dict(shape=name, backend=bname, ms=ms, tflops=fl / ms / 1e9, gbs=by / ms / 1e6)
+                print(json.dumps(rec), flush=True)
+                f.write(json.dumps(rec) + "\n")
+
+
+if __name__ == "__main__":
+    main()
