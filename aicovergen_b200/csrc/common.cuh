@@ -77,6 +77,13 @@ __device__ __forceinline__ float apply_act(float v, int act, float p) {
   }
 }
 
+// Round-to-nearest to TF32 precision (10-bit mantissa); the tensor core then sees exact operands.
+__device__ __forceinline__ float round_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

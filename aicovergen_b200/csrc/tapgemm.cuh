@@ -64,8 +64,11 @@ __device__ __forceinline__ float tg_epi1(const TgParams& p, const TgRow& r, int 
 __device__ __forceinline__ void tg_store1(const TgParams& p, const TgRow& r, int n, float acc) {
   if (!r.valid || n >= p.N) return;
   float v = tg_epi1(p, r, n, acc);
-  p.out[r.o_off + n] = v;
-  if (p.out2) p.out2[r.o_off + n] = apply_act(v, p.act2, p.act2_p);
+  p.out[r.o_off + n] = (p.round_tf32 & 1) ? round_tf32(v) : v;
+  if (p.out2) {
+    float v2 = apply_act(v, p.act2, p.act2_p);
+    p.out2[r.o_off + n] = (p.round_tf32 & 2) ? round_tf32(v2) : v2;
+  }
 }
 
 // Store 4 consecutive n (n % 4 == 0). Uses float4 when p.vec4 and fully in range.
@@ -96,10 +99,17 @@ __device__ __forceinline__ void tg_store4(const TgParams& p, const TgRow& r, int
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[i] = apply_act(v[i], p.act_post, p.act_post_p);
-    *reinterpret_cast<float4*>(p.out + r.o_off + n) = make_float4(v[0], v[1], v[2], v[3]);
+    if (p.round_tf32 & 1)
+      *reinterpret_cast<float4*>(p.out + r.o_off + n) =
+          make_float4(round_tf32(v[0]), round_tf32(v[1]), round_tf32(v[2]), round_tf32(v[3]));
+    else
+      *reinterpret_cast<float4*>(p.out + r.o_off + n) = make_float4(v[0], v[1], v[2], v[3]);
     if (p.out2) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) v[i] = apply_act(v[i], p.act2, p.act2_p);
+      for (int i = 0; i < 4; ++i) {
+        v[i] = apply_act(v[i], p.act2, p.act2_p);
+        if (p.round_tf32 & 2) v[i] = round_tf32(v[i]);
+      }
       *reinterpret_cast<float4*>(p.out2 + r.o_off + n) = make_float4(v[0], v[1], v[2], v[3]);
     }
   } else {

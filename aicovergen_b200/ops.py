@@ -1,0 +1,109 @@
+"""Thin torch-tensor wrappers over the non-GEMM C-ABI kernels (include/b200vc.h).
+
+Every function enqueues on the current torch CUDA stream and returns immediately.
+Tensors are passed by data_ptr(); nothing here computes on the host.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _ffi
+
+_P = C.c_void_p
+_i64, _i32, _f32 = C.c_int64, C.c_int, C.c_float
+
+_ffi.declare("b200vc_layernorm", [_P, _P, _P, _P, _P, _i64, _i32, _i64, _i64, _i64, _f32, _i32, _P])
+_ffi.declare("b200vc_softmax_rows", [_P, _i32, _i32, _i32, _i64, _i64, _P, _i32, _P, _i32, _i32, _i32, _P])
+_ffi.declare("b200vc_relpos_value_add", [_P, _i32, _P, _i32, _i64, _i64, _P, _i32, _i32, _i32, _P])
+_ffi.declare("b200vc_gather_rows", [_P, _P, _P, _i64, _i32, _P])
+_ffi.declare("b200vc_gate_tanh_sigmoid", [_P, _P, _i64, _i32, _i32, _P])
+_ffi.declare("b200vc_zp_sample", [_P, _P, _P, _i64, _i32, _f32, _P])
+_ffi.declare("b200vc_axpby", [_P, _P, _P, _i64, _f32, _f32, _P])
+_ffi.declare("b200vc_act", [_P, _P, _i64, _i32, _f32, _i32, _P])
+_ffi.declare("b200vc_nsf_source", [_P, _P, _P, _P, _i32, _i32, _f32, _f32, _f32, _P])
+_ffi.declare("b200vc_conv1d_to1", [_P, _P, _P, _i64, _i32, _i32, _i32, _i32, _P])
+
+
+def _s():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _f32c(t: torch.Tensor):
+    assert t.is_cuda and t.dtype == torch.float32, (t.device, t.dtype)
+    return t
+
+
+def layernorm(x, gamma, beta, out, res=None, eps=1e-5, round_out=False):
+    """out[r,:] = LN(x[r,:] + res[r,:]); x/res/out are [rows, C] with unit channel stride."""
+    rows, Cc = x.shape
+    assert x.stride(1) == 1 and out.stride(1) == 1 and (res is None or res.stride(1) == 1)
+    _ffi.check(_ffi.lib().b200vc_layernorm(_p(_f32c(x)), _p(res), _p(gamma), _p(beta), _p(out), rows, Cc,
+                                           x.stride(0), 0 if res is None else res.stride(0), out.stride(0),
+                                           eps, int(round_out), _s()), "layernorm")
+
+
+def softmax_rows(S, T, q=None, emb_rel_k=None, window=0, round_out=False):
+    """In-place softmax over S[heads, rows, :T]; optional relative-key bias (q [rows, heads*dk], emb_rel_k [2W+1, dk])."""
+    heads, rows, _ = S.shape
+    assert S.stride(2) == 1
+    dk = 0 if emb_rel_k is None else emb_rel_k.shape[-1]
+    _ffi.check(_ffi.lib().b200vc_softmax_rows(_p(_f32c(S)), heads, rows, T, S.stride(1), S.stride(0), _p(q),
+                                              0 if q is None else q.stride(0), _p(emb_rel_k), window, dk,
+                                              int(round_out), _s()), "softmax_rows")
+
+
+def relpos_value_add(out, P, T, emb_rel_v, window, heads):
+    dk = emb_rel_v.shape[-1]
+    _ffi.check(_ffi.lib().b200vc_relpos_value_add(_p(_f32c(out)), out.stride(0), _p(P), T, P.stride(1), P.stride(0),
+                                                  _p(emb_rel_v), window, dk, heads, _s()), "relpos_value_add")
+
+
+def gather_rows(table, idx, out):
+    assert idx.dtype == torch.int64 and idx.is_cuda and table.is_contiguous() and out.is_contiguous()
+    _ffi.check(_ffi.lib().b200vc_gather_rows(_p(_f32c(table)), _p(idx), _p(out), idx.numel(), table.shape[1], _s()),
+               "gather_rows")
+
+
+def gate_tanh_sigmoid(a, out, round_out=False):
+    rows, C2 = a.shape
+    assert a.is_contiguous() and out.is_contiguous()
+    _ffi.check(_ffi.lib().b200vc_gate_tanh_sigmoid(_p(_f32c(a)), _p(out), rows, C2 // 2, int(round_out), _s()), "gate")
+
+
+def zp_sample(stats, noise, z, scale=0.66666):
+    P, C2 = stats.shape
+    assert stats.is_contiguous() and noise.is_contiguous() and z.is_contiguous() and noise.numel() == P * (C2 // 2)
+    _ffi.check(_ffi.lib().b200vc_zp_sample(_p(_f32c(stats)), _p(noise), _p(z), P, C2 // 2, scale, _s()), "zp_sample")
+
+
+def axpby(a, b, out, alpha=1.0, beta=1.0):
+    assert a.is_contiguous() and out.is_contiguous() and (b is None or b.is_contiguous())
+    _ffi.check(_ffi.lib().b200vc_axpby(_p(_f32c(a)), _p(b), _p(out), a.numel(), alpha, beta, _s()), "axpby")
+
+
+def act(x, out, code, p=0.0, round_out=False):
+    assert x.is_contiguous() and out.is_contiguous()
+    _ffi.check(_ffi.lib().b200vc_act(_p(_f32c(x)), _p(out), x.numel(), code, p, int(round_out), _s()), "act")
+
+
+def nsf_source(f0, noise, har, scratch, upp, sr, lin_w, lin_b):
+    """har[:T*upp] = tanh(lin_w * sine_source(f0) + lin_b); f0 [T] f32, noise [T*upp] f32, scratch [T] f64."""
+    T = f0.numel()
+    assert f0.is_contiguous() and noise.is_contiguous() and noise.numel() >= T * upp and scratch.dtype == torch.float64
+    _ffi.check(_ffi.lib().b200vc_nsf_source(_p(_f32c(f0)), _p(noise), _p(har), _p(scratch), T, upp, float(sr),
+                                            float(lin_w), float(lin_b), _s()), "nsf_source")
+
+
+def conv1d_to1(x, w, out, pad, act_code):
+    """out[t] = act(sum_{k,c} w[k,c] x[t+k-pad,c]); x [T,C] contiguous, w [K,C]."""
+    T, Cc = x.shape
+    assert x.is_contiguous() and w.is_contiguous()
+    _ffi.check(_ffi.lib().b200vc_conv1d_to1(_p(_f32c(x)), _p(w), _p(out), T, Cc, w.shape[0], pad, act_code, _s()),
+               "conv1d_to1")

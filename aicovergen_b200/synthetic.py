@@ -1,0 +1,144 @@
+"""Seeded synthetic checkpoints in the reference's on-disk formats.
+
+No model files exist offline, so tests and bench.py run on
+random weights with the exact names/shapes the reference loaders expect:
+  * RVC `.pth`  : {"config": [...18 positional...], "weight": state_dict, "f0": 1, "version": "v2"}
+                  (rvc.py:113-134, infer_pack/models.py:643-664)
+  * rmvpe.pt    : E2E(4, 1, (2, 2)).state_dict()           (rmvpe.py:331-333)
+  * hubert_base : fairseq HubertModel names  (rvc.py:99)
+  * MDX-Net     : restated TFC-TDF net ("ConvTDFNet") parameter dict (mdx.py:74)
+  * IVF index   : centroids / list assignment / vectors     (vc_infer_pipeline.py:505-507)
+Deterministic given the seed on any machine (CPU generator, fp32).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List
+
+import torch
+
+# Reference training configs (src/configs/*.json model blocks) as the positional cpt["config"] list
+# (infer_pack/models.py:643-664): spec_channels, segment_size, inter, hidden, filter, heads, layers,
+# kernel, p_dropout, resblock, rb_kernels, rb_dilations, up_rates, up_init, up_kernels, spk_embed, gin, sr
+RVC_CONFIGS = {
+    "40k": [1025, 32, 192, 192, 768, 2, 6, 3, 0, "1", [3, 7, 11], [[1, 3, 5], [1, 3, 5], [1, 3, 5]],
+            [10, 10, 2, 2], 512, [16, 16, 4, 4], 109, 256, 40000],
+    "32k": [513, 32, 192, 192, 768, 2, 6, 3, 0, "1", [3, 7, 11], [[1, 3, 5], [1, 3, 5], [1, 3, 5]],
+            [10, 4, 2, 2, 2], 512, [16, 16, 4, 4, 4], 109, 256, 32000],
+    "48k": [1025, 32, 192, 192, 768, 2, 6, 3, 0, "1", [3, 7, 11], [[1, 3, 5], [1, 3, 5], [1, 3, 5]],
+            [10, 6, 2, 2, 2], 512, [16, 16, 4, 4, 4], 109, 256, 48000],
+    "32k_v2": [513, 32, 192, 192, 768, 2, 6, 3, 0, "1", [3, 7, 11], [[1, 3, 5], [1, 3, 5], [1, 3, 5]],
+               [10, 8, 2, 2], 512, [20, 16, 4, 4], 109, 256, 32000],
+    "48k_v2": [1025, 32, 192, 192, 768, 2, 6, 3, 0, "1", [3, 7, 11], [[1, 3, 5], [1, 3, 5], [1, 3, 5]],
+               [12, 10, 2, 2], 512, [24, 20, 4, 4], 109, 256, 48000],
+}
+
+
+class _Gen:
+    def __init__(self, seed: int):
+        self.g = torch.Generator().manual_seed(seed)
+
+    def normal(self, shape, std=1.0, mean=0.0):
+        return torch.randn(*shape, generator=self.g) * std + mean
+
+    def uniform(self, shape, lo, hi):
+        return torch.rand(*shape, generator=self.g) * (hi - lo) + lo
+
+    def conv(self, shape, gain=1.0):
+        """weight [out, in, *k] ~ N(0, gain^2 / fan_in)."""
+        fan_in = 1
+        for s in shape[1:]:
+            fan_in *= s
+        return self.normal(shape, gain / math.sqrt(fan_in))
+
+
+def _wn(sd: Dict[str, torch.Tensor], name: str, v: torch.Tensor):
+    """Old-style torch.nn.utils.weight_norm parametrisation (dim=0): weight = g * v / ||v||."""
+    sd[name + ".weight_v"] = v
+    sd[name + ".weight_g"] = v.flatten(1).norm(dim=1).reshape(-1, *([1] * (v.dim() - 1))).clone()
+
+
+def make_rvc_checkpoint(sr_key: str = "40k", version: str = "v2", seed: int = 1234, f0: int = 1) -> dict:
+    """Synthetic RVC voice model in the `.pth` dict format consumed by rvc.get_vc (rvc.py:112-143)."""
+    cfg = [c if not isinstance(c, list) else [list(x) if isinstance(x, list) else x for x in c]
+           for c in RVC_CONFIGS[sr_key]]
+    (_, _, inter, hidden, filt, heads, layers, ksz, _, _, rb_k, rb_d, up_r, up_init, up_k, spk, gin, sr) = cfg
+    in_dim = 768 if version == "v2" else 256
+    g = _Gen(seed)
+    sd: Dict[str, torch.Tensor] = {}
+    # ---- enc_p (models.py:64-108, attentions.py:13-73)
+    sd["enc_p.emb_phone.weight"] = g.conv((hidden, in_dim))
+    sd["enc_p.emb_phone.bias"] = g.normal((hidden,), 0.05)
+    if f0:
+        sd["enc_p.emb_pitch.weight"] = g.normal((256, hidden), 0.3)
+    dk = hidden // heads
+    for i in range(layers):
+        p = f"enc_p.encoder.attn_layers.{i}."
+        sd[p + "emb_rel_k"] = g.normal((1, 21, dk), dk ** -0.5)
+        sd[p + "emb_rel_v"] = g.normal((1, 21, dk), dk ** -0.5)
+        for n in ("q", "k", "v", "o"):
+            sd[p + f"conv_{n}.weight"] = g.conv((hidden, hidden, 1), 1.0 if n in "qk" else 0.7)
+            sd[p + f"conv_{n}.bias"] = g.normal((hidden,), 0.05)
+        sd[f"enc_p.encoder.norm_layers_1.{i}.gamma"] = g.uniform((hidden,), 0.8, 1.2)
+        sd[f"enc_p.encoder.norm_layers_1.{i}.beta"] = g.normal((hidden,), 0.05)
+        p = f"enc_p.encoder.ffn_layers.{i}."
+        sd[p + "conv_1.weight"] = g.conv((filt, hidden, ksz))
+        sd[p + "conv_1.bias"] = g.normal((filt,), 0.05)
+        sd[p + "conv_2.weight"] = g.conv((hidden, filt, ksz), 0.7)
+        sd[p + "conv_2.bias"] = g.normal((hidden,), 0.05)
+        sd[f"enc_p.encoder.norm_layers_2.{i}.gamma"] = g.uniform((hidden,), 0.8, 1.2)
+        sd[f"enc_p.encoder.norm_layers_2.{i}.beta"] = g.normal((hidden,), 0.05)
+    sd["enc_p.proj.weight"] = g.conv((inter * 2, hidden, 1), 0.5)
+    sd["enc_p.proj.bias"] = g.normal((inter * 2,), 0.05)
+    # ---- flow (models.py:111-157, modules.py:136-221, 405-462): 4 coupling layers at even indices
+    half = inter // 2
+    for f in range(4):
+        p = f"flow.flows.{2 * f}."
+        sd[p + "pre.weight"] = g.conv((hidden, half, 1))
+        sd[p + "pre.bias"] = g.normal((hidden,), 0.05)
+        for j in range(3):
+            _wn(sd, p + f"enc.in_layers.{j}", g.conv((2 * hidden, hidden, 5)))
+            sd[p + f"enc.in_layers.{j}.bias"] = g.normal((2 * hidden,), 0.05)
+            rs = 2 * hidden if j < 2 else hidden
+            _wn(sd, p + f"enc.res_skip_layers.{j}", g.conv((rs, hidden, 1), 0.7))
+            sd[p + f"enc.res_skip_layers.{j}.bias"] = g.normal((rs,), 0.05)
+        _wn(sd, p + "enc.cond_layer", g.conv((2 * hidden * 3, gin, 1), 0.5))
+        sd[p + "enc.cond_layer.bias"] = g.normal((2 * hidden * 3,), 0.05)
+        # the reference zero-inits `post` (modules.py:437-438); redrawn so the flow is non-trivial
+        sd[p + "post.weight"] = g.conv((half, hidden, 1), 0.3)
+        sd[p + "post.bias"] = g.normal((half,), 0.02)
+    # ---- dec (models.py:422-522)
+    if f0:
+        sd["dec.m_source.l_linear.weight"] = torch.tensor([[0.9]])
+        sd["dec.m_source.l_linear.bias"] = torch.tensor([0.01])
+    sd["dec.conv_pre.weight"] = g.conv((up_init, inter, 7))
+    sd["dec.conv_pre.bias"] = g.normal((up_init,), 0.05)
+    sd["dec.cond.weight"] = g.conv((up_init, gin, 1), 0.5)
+    sd["dec.cond.bias"] = g.normal((up_init,), 0.05)
+    ch = up_init
+    for i, (u, k) in enumerate(zip(up_r, up_k)):
+        cin, cout = up_init // (2 ** i), up_init // (2 ** (i + 1))
+        # ConvTranspose1d weight [Cin, Cout, k]; each output sums ~k/u taps x Cin inputs
+        v = g.normal((cin, cout, k), 1.0 / math.sqrt(cin * k / u))
+        _wn(sd, f"dec.ups.{i}", v)
+        sd[f"dec.ups.{i}.bias"] = g.normal((cout,), 0.05)
+        if f0:
+            if i + 1 < len(up_r):
+                s = 1
+                for r in up_r[i + 1:]:
+                    s *= r
+                sd[f"dec.noise_convs.{i}.weight"] = g.normal((cout, 1, 2 * s), 1.0 / math.sqrt(2 * s) * 3.0)
+            else:
+                sd[f"dec.noise_convs.{i}.weight"] = g.normal((cout, 1, 1), 3.0)
+            sd[f"dec.noise_convs.{i}.bias"] = g.normal((cout,), 0.05)
+        for j, (kk, dd) in enumerate(zip(rb_k, rb_d)):
+            n = i * len(rb_k) + j
+            for m in range(len(dd)):
+                _wn(sd, f"dec.resblocks.{n}.convs1.{m}", g.conv((cout, cout, kk), 1.0))
+                sd[f"dec.resblocks.{n}.convs1.{m}.bias"] = g.normal((cout,), 0.05)
+                _wn(sd, f"dec.resblocks.{n}.convs2.{m}", g.conv((cout, cout, kk), 0.5))
+                sd[f"dec.resblocks.{n}.convs2.{m}.bias"] = g.normal((cout,), 0.05)
+        ch = cout
+    sd["dec.conv_post.weight"] = g.conv((1, ch, 7), 0.5)
+    sd["emb_g.weight"] = g.normal((spk, gin), 1.0)
+    return {"config": cfg, "weight": sd, "f0": f0, "version": version, "info": "synthetic", "sr": sr_key}

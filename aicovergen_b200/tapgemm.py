@@ -127,6 +127,8 @@ class Epi:
     out2: Optional[torch.Tensor] = None    # same addressing as out
     act2: int = ACT_NONE
     act2_p: float = 0.0
+    round_out: bool = False     # store `out` rounded (RN) to TF32: for tensors only consumed by TF32 GEMMs
+    round_out2: bool = False
 
 
 def _tile_box(OW: int, OH: int) -> Tuple[int, int]:
@@ -198,6 +200,7 @@ class TapGemm:
             p.out2 = epi.out2.data_ptr() + 4 * out.off
             self._keep.append(epi.out2)
         p.act2, p.act2_p = epi.act2, float(epi.act2_p)
+        p.round_tf32 = (1 if epi.round_out else 0) | (2 if epi.round_out2 else 0)
         for i, (c_off, dw, dh, dp, widx) in enumerate(self.taps):
             t = p.taps[i]
             t.c_off, t.dw, t.dh, t.dp, t.widx = int(c_off), int(dw), int(dh), int(dp), int(widx)

@@ -88,6 +88,7 @@ typedef struct b200vc_tapgemm_params {
   int32_t act2;
   float act2_p;
   int32_t vec4;         /* bit0: k-vectorised loads ok, bit1: n-vectorised epilogue ok */
+  int32_t round_tf32;   /* bit0: round `out` to TF32 (RN), bit1: round `out2` — for tensors only consumed by TF32 GEMMs */
   b200vc_tap taps[B200VC_MAX_TAPS];
 } b200vc_tapgemm_params;
 
@@ -103,6 +104,51 @@ int64_t b200vc_sizeof_tapgemm_params(void);
 int b200vc_tapgemm(const b200vc_tapgemm_params* p, int backend, void* stream);
 /* 1 when the descriptor satisfies the TMA alignment rules of the tcgen05 path */
 int b200vc_tapgemm_tc_supported(const b200vc_tapgemm_params* p);
+
+/* ---- row / elementwise kernels (fp32, HBM-bound) ---- */
+
+/* out[r,:] = LayerNorm(x[r,:] + res[r,:]) * gamma + beta over C channels (res may be NULL).
+ * Replaces F.layer_norm at infer_pack/modules.py:29-32 and fairseq's LayerNorm calls. */
+int b200vc_layernorm(const float* x, const float* res, const float* gamma, const float* beta, float* out,
+                     int64_t rows, int C, int64_t ldx, int64_t ldr, int64_t ldo, float eps, int round_out,
+                     void* stream);
+
+/* In-place softmax over the last dim of S[heads][rows_per_head][T] (row pitch ld, head pitch head_stride).
+ * With emb_rel_k != NULL adds the VITS banded relative-key bias q_i . emb_rel_k[j-i+W] first
+ * (infer_pack/attentions.py:238-243,261); q rows are [ldq] wide with head h at column h*dk. */
+int b200vc_softmax_rows(float* S, int heads, int rows_per_head, int T, int64_t ld, int64_t head_stride,
+                        const float* q, int ldq, const float* emb_rel_k, int window, int dk,
+                        int round_out, void* stream);
+
+/* out[i, h*dk+d] += sum_r P[h,i,i+r-W] * emb_rel_v[r,d]   (infer_pack/attentions.py:264-271) */
+int b200vc_relpos_value_add(float* out, int ldo, const float* P, int T, int64_t ld, int64_t head_stride,
+                            const float* emb_rel_v, int window, int dk, int heads, void* stream);
+
+/* out[r,:] = table[idx[r],:]  (nn.Embedding at infer_pack/models.py:97,746) */
+int b200vc_gather_rows(const float* table, const int64_t* idx, float* out, int64_t rows, int C, void* stream);
+
+/* out[t,c] = tanh(a[t,c]) * sigmoid(a[t,C+c])  (infer_pack/commons.py:105-112) */
+int b200vc_gate_tanh_sigmoid(const float* a, float* out, int64_t rows, int C, int round_out, void* stream);
+
+/* z[t,c] = stats[t,c] + exp(stats[t,C+c]) * noise[c*P+t] * scale  (infer_pack/models.py:748; noise is the
+ * caller-supplied randn_like(m_p) draw in the reference's [C,P] layout) */
+int b200vc_zp_sample(const float* stats, const float* noise, float* z, int64_t P, int C, float scale, void* stream);
+
+/* out = alpha*a + beta*b (b may be NULL) */
+int b200vc_axpby(const float* a, const float* b, float* out, int64_t n, float alpha, float beta, void* stream);
+
+/* out = act(x) elementwise */
+int b200vc_act(const float* x, float* out, int64_t n, int act, float p, int round_out, void* stream);
+
+/* NSF harmonic source: har[T*upp] = tanh(lin_w * SineGen(f0, upp, sr; noise) + lin_b)
+ * (infer_pack/models.py:320-370 with harmonic_num=0, :414-419). noise[T*upp] is the caller-supplied
+ * randn_like(sine_waves) draw; scratch_cum holds T doubles. */
+int b200vc_nsf_source(const float* f0, const float* noise, float* har, double* scratch_cum, int T, int upp,
+                      float sr, float lin_w, float lin_b, void* stream);
+
+/* out[t] = act(sum_k sum_c w[k,c] x[t+k-pad,c]) : Conv1d C->1 (conv_post + tanh, infer_pack/models.py:514-515) */
+int b200vc_conv1d_to1(const float* x, const float* w, float* out, int64_t T, int C, int K, int pad, int act,
+                      void* stream);
 
 #ifdef __cplusplus
 }
