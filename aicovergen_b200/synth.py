@@ -200,6 +200,7 @@ class _Plan:
         dev, W, be = m.device, m.W, m.backend
         H, inter, heads, dk = m.hidden, m.inter, m.n_heads, m.hidden // m.n_heads
         f32 = dict(device=dev, dtype=torch.float32)
+        R = be == tg.BACKEND_TC      # round GEMM-only activations to TF32 (RN) when the tensor-core path consumes them
         steps: List = []
         add = steps.append
         in_dim = W["emb_phone.w"].shape[1]
@@ -231,20 +232,20 @@ class _Plan:
         tmp = torch.empty(P, H, **f32)
         hbuf = torch.empty(P, m.filter, **f32)
         for i in range(m.n_layers):
-            add(tg.linear(x, W[f"l{i}.qk.w"], qk, Epi(bias=W[f"l{i}.qk.b"], round_out=True), be, name=f"l{i}.qk"))
+            add(tg.linear(x, W[f"l{i}.qk.w"], qk, Epi(bias=W[f"l{i}.qk.b"], round_out=R), be, name=f"l{i}.qk"))
             # V^T = Wv X^T (+ per-row bias): operand roles swapped so the PV GEMM sees a K-major B operand
-            add(tg.linear(W[f"l{i}.v.w"], x, vT[:, :P], Epi(bias=W[f"l{i}.v.b"], bias_per_row=True, round_out=True),
+            add(tg.linear(W[f"l{i}.v.w"], x, vT[:, :P], Epi(bias=W[f"l{i}.v.b"], bias_per_row=True, round_out=R),
                           be, name=f"l{i}.vT"))
             qh = qk[:, :H].view(P, heads, dk).permute(1, 0, 2)
             kh = qk[:, H:].view(P, heads, dk).permute(1, 0, 2)
             add(tg.bmm_nt(qh, kh, sc[:, :, :P], None, be, name=f"l{i}.qk^T"))
-            add(lambda i=i: ops.softmax_rows(sc, P, q=qk, emb_rel_k=W[f"l{i}.rel_k"], window=m.window, round_out=True))
+            add(lambda i=i: ops.softmax_rows(sc, P, q=qk, emb_rel_k=W[f"l{i}.rel_k"], window=m.window, round_out=R))
             add(tg.bmm_nt(sc[:, :, :P], vT.view(heads, dk, Tp)[:, :, :P], o.view(P, heads, dk).permute(1, 0, 2),
                           None, be, name=f"l{i}.pv"))
             add(lambda i=i: ops.relpos_value_add(o, sc, P, W[f"l{i}.rel_v"], m.window, heads))
             add(tg.linear(o, W[f"l{i}.o.w"], tmp, Epi(bias=W[f"l{i}.o.b"], res=x), be, name=f"l{i}.o"))
             add(lambda i=i: ops.layernorm(tmp, W[f"l{i}.ln1.g"], W[f"l{i}.ln1.b"], x))
-            add(tg.conv1d(x, W[f"l{i}.ffn1.w"], hbuf, epi=Epi(bias=W[f"l{i}.ffn1.b"], act_pre=tg.ACT_RELU, round_out=True),
+            add(tg.conv1d(x, W[f"l{i}.ffn1.w"], hbuf, epi=Epi(bias=W[f"l{i}.ffn1.b"], act_pre=tg.ACT_RELU, round_out=R),
                           backend=be, name=f"l{i}.ffn1"))
             add(tg.conv1d(hbuf, W[f"l{i}.ffn2.w"], tmp, epi=Epi(bias=W[f"l{i}.ffn2.b"], res=x), backend=be, name=f"l{i}.ffn2"))
             add(lambda i=i: ops.layernorm(tmp, W[f"l{i}.ln2.g"], W[f"l{i}.ln2.b"], x))
@@ -273,7 +274,7 @@ class _Plan:
             add(tg.linear(x0, pre_w, h, Epi(bias=W[f"f{f}.pre.b"]), be, name=f"f{f}.pre"))
             for j in range(3):
                 add(tg.conv1d(h, W[f"f{f}.in{j}.w"], a, epi=Epi(bias=self.in_b[(f, j)]), backend=be, name=f"f{f}.in{j}"))
-                add(lambda: ops.gate_tanh_sigmoid(a, acts, round_out=True))
+                add(lambda: ops.gate_tanh_sigmoid(a, acts, round_out=R))
                 if j < 2:
                     add(tg.linear(acts, W[f"f{f}.res{j}.w"], h, Epi(bias=W[f"f{f}.res{j}.b"], res=h), be, name=f"f{f}.res{j}"))
                 add(tg.linear(acts, W[f"f{f}.skip{j}.w"], skip,
@@ -290,7 +291,7 @@ class _Plan:
             Ts.append(Ts[-1] * u)
         Cs = [m.up_init // (2 ** (i + 1)) for i in range(nst)]
         xl0 = torch.empty(P, m.up_init, **f32)
-        add(tg.conv1d(S, W["pre.w"], xl0, epi=Epi(bias=self.pre_b, act_post=tg.ACT_LRELU, act_post_p=LRELU, round_out=True),
+        add(tg.conv1d(S, W["pre.w"], xl0, epi=Epi(bias=self.pre_b, act_post=tg.ACT_LRELU, act_post_p=LRELU, round_out=R),
                       backend=be, name="conv_pre"))
         if m.f0:
             smax = max([int(np.prod(m.up_r[i + 1:])) for i in range(nst)])
@@ -320,10 +321,10 @@ class _Plan:
                 pad = s // 2 if i + 1 < nst else 0
                 av = tg.View(self.harbuf, (kk, T, 1, 1, 1), (1, s, 0, 0, 0), off=self.har_off - pad)
                 add(tg.TapGemm(av, tg.weights(W[f"nc{i}.w"]), [(0, 0, 0, 0, 0)], (T, 1, 1), tg.out_of(xs),
-                               Epi(bias=W[f"nc{i}.b"], res=xs, out2=xsl, act2=tg.ACT_LRELU, act2_p=LRELU, round_out2=True),
+                               Epi(bias=W[f"nc{i}.b"], res=xs, out2=xsl, act2=tg.ACT_LRELU, act2_p=LRELU, round_out2=R),
                                be, name=f"noise_conv{i}"))
             else:
-                add(lambda xs=xs, xsl=xsl: ops.act(xs, xsl, tg.ACT_LRELU, LRELU, True))
+                add(lambda xs=xs, xsl=xsl: ops.act(xs, xsl, tg.ACT_LRELU, LRELU, R))
             last_stage = i == nst - 1
             for j in range(nk):
                 n = i * nk + j
@@ -332,13 +333,13 @@ class _Plan:
                 outs = [(xa, xal), (xb, xbl)]
                 for mm, d in enumerate(dil):
                     add(tg.conv1d(curl, W[f"rb{n}.c1.{mm}.w"], tb, dilation=d,
-                                  epi=Epi(bias=W[f"rb{n}.c1.{mm}.b"], act_pre=tg.ACT_LRELU, act_pre_p=LRELU, round_out=True),
+                                  epi=Epi(bias=W[f"rb{n}.c1.{mm}.b"], act_pre=tg.ACT_LRELU, act_pre_p=LRELU, round_out=R),
                                   backend=be, name=f"rb{n}.c1.{mm}"))
                     if mm < len(dil) - 1:
                         nxt, nxtl = outs[mm % 2]
                         add(tg.conv1d(tb, W[f"rb{n}.c2.{mm}.w"], nxt,
                                       epi=Epi(bias=W[f"rb{n}.c2.{mm}.b"], res=cur, out2=nxtl, act2=tg.ACT_LRELU,
-                                              act2_p=LRELU, round_out2=True), backend=be, name=f"rb{n}.c2.{mm}"))
+                                              act2_p=LRELU, round_out2=R), backend=be, name=f"rb{n}.c2.{mm}"))
                         cur, curl = nxt, nxtl
                     else:
                         final = j == nk - 1
@@ -347,7 +348,7 @@ class _Plan:
                                               res2=Ssum if j > 0 else None,
                                               act_post=tg.ACT_LRELU if final else tg.ACT_NONE,
                                               act_post_p=(0.01 if last_stage else LRELU),
-                                              round_out=final and not last_stage),
+                                              round_out=R and final and not last_stage),
                                       backend=be, name=f"rb{n}.c2.{mm}"))
             prev = Ssum
         self.audio = torch.empty(L, **f32)

@@ -142,3 +142,70 @@ def make_rvc_checkpoint(sr_key: str = "40k", version: str = "v2", seed: int = 12
     sd["dec.conv_post.weight"] = g.conv((1, ch, 7), 0.5)
     sd["emb_g.weight"] = g.normal((spk, gin), 1.0)
     return {"config": cfg, "weight": sd, "f0": f0, "version": version, "info": "synthetic", "sr": sr_key}
+
+
+# ---------------------------------------------------------------------------
+# rmvpe.pt  (E2E(4, 1, (2, 2)).state_dict(), rmvpe.py:221-258, 331-333)
+# ---------------------------------------------------------------------------
+def _bn(sd, g: _Gen, name: str, c: int):
+    """BatchNorm2d eval statistics per SURVEY.md §8(d) weights policy."""
+    sd[name + ".weight"] = g.uniform((c,), 0.5, 1.5)
+    sd[name + ".bias"] = g.normal((c,), 0.1)
+    sd[name + ".running_mean"] = g.normal((c,), 0.1)
+    sd[name + ".running_var"] = g.uniform((c,), 0.5, 1.5)
+    sd[name + ".num_batches_tracked"] = torch.tensor(0, dtype=torch.long)
+
+
+def _conv_block_res(sd, g: _Gen, p: str, cin: int, cout: int):
+    """ConvBlockRes (rmvpe.py:23-58): conv.0 / bn conv.1 / conv.3 / bn conv.4 (+ 1x1 shortcut if cin != cout)."""
+    sd[p + "conv.0.weight"] = g.conv((cout, cin, 3, 3), 1.3)
+    _bn(sd, g, p + "conv.1", cout)
+    sd[p + "conv.3.weight"] = g.conv((cout, cout, 3, 3), 0.45)
+    _bn(sd, g, p + "conv.4", cout)
+    if cin != cout:
+        sd[p + "shortcut.weight"] = g.conv((cout, cin, 1, 1), 0.8)
+        sd[p + "shortcut.bias"] = g.normal((cout,), 0.05)
+
+
+def make_rmvpe_state_dict(seed: int = 4321, n_blocks: int = 4, en_de_layers: int = 5, inter_layers: int = 4,
+                          en_out_channels: int = 16, n_mels: int = 128, n_gru_hidden: int = 256,
+                          n_class: int = 360) -> Dict[str, torch.Tensor]:
+    g = _Gen(seed)
+    sd: Dict[str, torch.Tensor] = {}
+    # input BN over the single mel "channel": keep log-mel roughly standardised
+    sd["unet.encoder.bn.weight"] = torch.tensor([0.35])
+    sd["unet.encoder.bn.bias"] = torch.tensor([0.9])
+    sd["unet.encoder.bn.running_mean"] = torch.tensor([-4.0])
+    sd["unet.encoder.bn.running_var"] = torch.tensor([1.3])
+    sd["unet.encoder.bn.num_batches_tracked"] = torch.tensor(0, dtype=torch.long)
+    cin, cout = 1, en_out_channels
+    for i in range(en_de_layers):
+        for b in range(n_blocks):
+            _conv_block_res(sd, g, f"unet.encoder.layers.{i}.conv.{b}.", cin if b == 0 else cout, cout)
+        cin, cout = cout, cout * 2
+    # intermediate: first 256 -> 512, then 512 -> 512
+    ci, co = cin, cout
+    for i in range(inter_layers):
+        for b in range(n_blocks):
+            _conv_block_res(sd, g, f"unet.intermediate.layers.{i}.conv.{b}.", ci if b == 0 else co, co)
+        ci = co
+    dc = co
+    for i in range(en_de_layers):
+        do = dc // 2
+        # ConvTranspose2d weight [Cin, Cout, 3, 3]; stride 2 -> ~2.25 taps per output
+        sd[f"unet.decoder.layers.{i}.conv1.0.weight"] = g.normal((dc, do, 3, 3), 1.2 / math.sqrt(dc * 2.25))
+        _bn(sd, g, f"unet.decoder.layers.{i}.conv1.1", do)
+        for b in range(n_blocks):
+            _conv_block_res(sd, g, f"unet.decoder.layers.{i}.conv2.{b}.", do * 2 if b == 0 else do, do)
+        dc = do
+    sd["cnn.weight"] = g.conv((3, en_out_channels, 3, 3), 1.0)
+    sd["cnn.bias"] = g.normal((3,), 0.05)
+    Hh = n_gru_hidden
+    for suf in ("", "_reverse"):
+        sd[f"fc.0.gru.weight_ih_l0{suf}"] = g.conv((3 * Hh, 3 * n_mels), 1.0)
+        sd[f"fc.0.gru.weight_hh_l0{suf}"] = g.conv((3 * Hh, Hh), 1.0)
+        sd[f"fc.0.gru.bias_ih_l0{suf}"] = g.normal((3 * Hh,), 0.1)
+        sd[f"fc.0.gru.bias_hh_l0{suf}"] = g.normal((3 * Hh,), 0.1)
+    sd["fc.1.weight"] = g.conv((n_class, 2 * Hh), 1.0)
+    sd["fc.1.bias"] = g.normal((n_class,), 0.3, -1.5)
+    return sd
