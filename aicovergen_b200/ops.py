@@ -25,6 +25,12 @@ _ffi.declare("b200vc_axpby", [_P, _P, _P, _i64, _f32, _f32, _P])
 _ffi.declare("b200vc_act", [_P, _P, _i64, _i32, _f32, _i32, _P])
 _ffi.declare("b200vc_nsf_source", [_P, _P, _P, _P, _i32, _i32, _f32, _f32, _f32, _P])
 _ffi.declare("b200vc_conv1d_to1", [_P, _P, _P, _i64, _i32, _i32, _i32, _i32, _P])
+_ffi.declare("b200vc_reflect_pad_1d", [_P, _P, _i64, _i64, _P])
+_ffi.declare("b200vc_magnitude", [_P, _P, _i64, _i32, _i64, _i64, _P])
+_ffi.declare("b200vc_logmel_affine_reflect", [_P, _P, _i32, _i32, _i32, _f32, _f32, _f32, _P])
+_ffi.declare("b200vc_avgpool2x2", [_P, _P, _i32, _i32, _i32, _i32, _i64, _P])
+_ffi.declare("b200vc_bigru", [_P, _P, _P, _P, _i32, _i32, _P])
+_ffi.declare("b200vc_rmvpe_decode", [_P, _P, _i32, _i32, _i64, _f32, _P])
 
 
 def _s():
@@ -107,3 +113,41 @@ def conv1d_to1(x, w, out, pad, act_code):
     assert x.is_contiguous() and w.is_contiguous()
     _ffi.check(_ffi.lib().b200vc_conv1d_to1(_p(_f32c(x)), _p(w), _p(out), T, Cc, w.shape[0], pad, act_code, _s()),
                "conv1d_to1")
+
+
+def reflect_pad_1d(x, out, pad):
+    N = x.numel()
+    assert x.is_contiguous() and out.numel() >= N + 2 * pad
+    _ffi.check(_ffi.lib().b200vc_reflect_pad_1d(_p(_f32c(x)), _p(out), N, pad, _s()), "reflect_pad_1d")
+
+
+def magnitude(spec, mag, nb):
+    rows = spec.shape[0]
+    _ffi.check(_ffi.lib().b200vc_magnitude(_p(_f32c(spec)), _p(mag), rows, nb, spec.stride(0), mag.stride(0), _s()),
+               "magnitude")
+
+
+def logmel_affine_reflect(x, out, rows, clampv, a, b):
+    rows_total, Cc = out.shape
+    assert x.is_contiguous() and out.is_contiguous()
+    _ffi.check(_ffi.lib().b200vc_logmel_affine_reflect(_p(_f32c(x)), _p(out), rows, rows_total, Cc, clampv, a, b, _s()),
+               "logmel_affine_reflect")
+
+
+def avgpool2x2(x, out):
+    """x [B,H,W,C] (channel slice allowed: stride(-1)==1, pixel pitch x.stride(2)), out [B,H/2,W/2,C] contiguous."""
+    B, H, W, Cc = x.shape
+    assert x.stride(3) == 1 and x.stride(1) == W * x.stride(2) and x.stride(0) == H * x.stride(1) and out.is_contiguous()
+    _ffi.check(_ffi.lib().b200vc_avgpool2x2(_p(_f32c(x)), _p(out), B, H, W, Cc, x.stride(2), _s()), "avgpool2x2")
+
+
+def bigru(xp, whh, bhh, out, hidden):
+    T = xp.shape[0]
+    assert xp.is_contiguous() and whh.is_contiguous() and bhh.is_contiguous() and out.is_contiguous()
+    _ffi.check(_ffi.lib().b200vc_bigru(_p(_f32c(xp)), _p(whh), _p(bhh), _p(out), T, hidden, _s()), "bigru")
+
+
+def rmvpe_decode(sal, f0, T, thred):
+    assert f0.dtype == torch.float64 and sal.stride(1) == 1
+    _ffi.check(_ffi.lib().b200vc_rmvpe_decode(_p(_f32c(sal)), _p(f0), T, sal.shape[1], sal.stride(0), thred, _s()),
+               "rmvpe_decode")

@@ -150,6 +150,29 @@ int b200vc_nsf_source(const float* f0, const float* noise, float* har, double* s
 int b200vc_conv1d_to1(const float* x, const float* w, float* out, int64_t T, int C, int K, int pad, int act,
                       void* stream);
 
+/* ---- RMVPE F0 estimator pieces (rmvpe.py) ---- */
+
+/* out[i] = in[reflect(i - pad)] for i in [0, N+2*pad): torch.stft(center=True) framing (rmvpe.py:305-313, mdx.py:39) */
+int b200vc_reflect_pad_1d(const float* in, float* out, int64_t N, int64_t pad, void* stream);
+
+/* mag[t,k] = |spec[t,k] + i spec[t,nb+k]| with zero-filled row tail up to ldm (rmvpe.py:314) */
+int b200vc_magnitude(const float* spec, float* mag, int64_t rows, int nb, int64_t lds, int64_t ldm, void* stream);
+
+/* out[t,c] = a*log(max(x[t,c],clampv))+b for t<rows, reflect-padded to rows_total rows
+ * (rmvpe.py:324 ; the scalar BatchNorm2d(1) of Encoder.bn, rmvpe.py:74,92 ; F.pad reflect, rmvpe.py:353-355) */
+int b200vc_logmel_affine_reflect(const float* x, float* out, int rows, int rows_total, int C, float clampv,
+                                 float a, float b, void* stream);
+
+/* NHWC 2x2 average pooling; input pixel pitch ldi (nn.AvgPool2d, rmvpe.py:111,117) */
+int b200vc_avgpool2x2(const float* in, float* out, int B, int H, int W, int C, int64_t ldi, void* stream);
+
+/* Bidirectional GRU recurrence (nn.GRU(384,256,bidirectional), rmvpe.py:8-20) as a 2x8-CTA cluster kernel.
+ * xp [T, 2*3H] = x W_ih^T + b_ih (dir d at column d*3H); whh [2,3H,H]; bhh [2,3H]; out [T,2H]. */
+int b200vc_bigru(const float* xp, const float* whh, const float* bhh, float* out, int T, int hidden, void* stream);
+
+/* salience [T,n_bins] -> f0[T] (float64) exactly as RMVPE.decode / to_local_average_cents (rmvpe.py:359-409) */
+int b200vc_rmvpe_decode(const float* salience, double* f0, int T, int n_bins, int64_t ld, float thred, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
