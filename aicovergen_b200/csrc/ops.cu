@@ -262,6 +262,43 @@ __global__ void act_kernel(const float* __restrict__ x, float* __restrict__ out,
   out[e] = round_out ? round_tf32(v) : v;
 }
 
+
+// ---------------------------------------------------------------------------
+// GroupNorm with one channel per group over the time axis (fairseq HuBERT conv layer 0:
+// nn.GroupNorm(512, 512)) + GELU.  Pass 1: per-channel sum / sum-of-squares (fp64 atomics);
+// pass 2: normalise, affine, GELU.
+// ---------------------------------------------------------------------------
+__global__ void colstats_kernel(const float* __restrict__ x, double* __restrict__ stats, long long rows, int C,
+                                int rows_per_block) {
+  const int c = blockIdx.y * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = min(rows, r0 + rows_per_block);
+  double s = 0.0, q = 0.0;
+  for (long long r = r0; r < r1; ++r) {
+    const double v = (double)x[r * C + c];
+    s += v;
+    q += v * v;
+  }
+  atomicAdd(stats + c, s);
+  atomicAdd(stats + C + c, q);
+}
+
+__global__ void groupnorm_apply_kernel(const float* __restrict__ x, const double* __restrict__ stats,
+                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                       float* __restrict__ out, long long rows, int C, float eps, int act,
+                                       int round_out) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= rows * C) return;
+  const int c = (int)(e % C);
+  const double mean = stats[c] / (double)rows;
+  const double var = stats[C + c] / (double)rows - mean * mean;
+  const float rstd = (float)(1.0 / sqrt(fmax(var, 0.0) + (double)eps));
+  float v = ((x[e] - (float)mean) * rstd) * gamma[c] + beta[c];
+  v = apply_act(v, act, 0.f);
+  out[e] = round_out ? round_tf32(v) : v;
+}
+
 inline unsigned blocks_for(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
 }  // namespace
@@ -377,6 +414,20 @@ int b200vc_conv1d_to1(const float* x, const float* w, float* out, int64_t T, int
   B200VC_REQUIRE(x && w && out && T > 0 && C % 4 == 0 && K * C * 4 <= 48 * 1024, "conv1d_to1: bad args");
   conv1d_to1_kernel<<<blocks_for(T, 256), 256, K * C * 4, (cudaStream_t)stream>>>(x, w, out, T, C, K, pad, act);
   count_launch();
+  B200VC_LAUNCH_CHECK();
+  return kOk;
+}
+
+int b200vc_groupnorm_time(const float* x, const float* gamma, const float* beta, float* out, double* stats,
+                          int64_t rows, int C, float eps, int act, int round_out, void* stream) {
+  B200VC_REQUIRE(x && gamma && beta && out && stats && rows > 0 && C > 0, "groupnorm_time: bad args");
+  cudaStream_t s = (cudaStream_t)stream;
+  B200VC_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * C, s));
+  const int rpb = 256;
+  dim3 grid(blocks_for(rows, rpb), blocks_for(C, 128));
+  colstats_kernel<<<grid, 128, 0, s>>>(x, stats, rows, C, rpb);
+  groupnorm_apply_kernel<<<blocks_for(rows * C, 256), 256, 0, s>>>(x, stats, gamma, beta, out, rows, C, eps, act, round_out);
+  count_launch(2);
   B200VC_LAUNCH_CHECK();
   return kOk;
 }

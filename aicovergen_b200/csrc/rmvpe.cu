@@ -170,7 +170,8 @@ bigru_kernel(const float* __restrict__ xp, const float* __restrict__ whh /*[2][3
 // numpy is float64, and numpy's pairwise summation order for the 9-element reductions:
 //   sum9(a) = (((a0+a1)+(a2+a3)) + ((a4+a5)+(a6+a7))) + a8
 // ---------------------------------------------------------------------------
-__global__ void rmvpe_decode_kernel(const float* __restrict__ sal, double* __restrict__ f0, int T, int NB,
+__global__ void rmvpe_decode_kernel(const float* __restrict__ sal, double* __restrict__ f0,
+                                    double* __restrict__ cents_out, int T, int NB,
                                     long long ld, float thred) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -205,6 +206,7 @@ __global__ void rmvpe_decode_kernel(const float* __restrict__ sal, double* __res
                                            __fadd_rn(__fadd_rn(sv[4], sv[5]), __fadd_rn(sv[6], sv[7]))), sv[8]);
     double cents = psum / (double)wsum;
     if (best <= thred) cents = 0.0;
+    if (cents_out) cents_out[warp] = cents;
     double f = 10.0 * exp2(cents / 1200.0);
     if (f == 10.0) f = 0.0;
     f0[warp] = f;
@@ -263,10 +265,11 @@ int b200vc_bigru(const float* xp, const float* whh, const float* bhh, float* out
   return kOk;
 }
 
-int b200vc_rmvpe_decode(const float* salience, double* f0, int T, int n_bins, int64_t ld, float thred, void* stream) {
+int b200vc_rmvpe_decode(const float* salience, double* f0, double* cents, int T, int n_bins, int64_t ld, float thred,
+                        void* stream) {
   B200VC_REQUIRE(salience && f0 && T > 0 && n_bins > 0, "rmvpe_decode: bad args");
-  rmvpe_decode_kernel<<<blocks_for((long long)T * 32, 256), 256, 0, (cudaStream_t)stream>>>(salience, f0, T, n_bins,
-                                                                                           ld, thred);
+  rmvpe_decode_kernel<<<blocks_for((long long)T * 32, 256), 256, 0, (cudaStream_t)stream>>>(salience, f0, cents, T,
+                                                                                           n_bins, ld, thred);
   count_launch();
   B200VC_LAUNCH_CHECK();
   return kOk;

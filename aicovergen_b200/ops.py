@@ -30,7 +30,8 @@ _ffi.declare("b200vc_magnitude", [_P, _P, _i64, _i32, _i64, _i64, _P])
 _ffi.declare("b200vc_logmel_affine_reflect", [_P, _P, _i32, _i32, _i32, _f32, _f32, _f32, _P])
 _ffi.declare("b200vc_avgpool2x2", [_P, _P, _i32, _i32, _i32, _i32, _i64, _P])
 _ffi.declare("b200vc_bigru", [_P, _P, _P, _P, _i32, _i32, _P])
-_ffi.declare("b200vc_rmvpe_decode", [_P, _P, _i32, _i32, _i64, _f32, _P])
+_ffi.declare("b200vc_rmvpe_decode", [_P, _P, _P, _i32, _i32, _i64, _f32, _P])
+_ffi.declare("b200vc_groupnorm_time", [_P, _P, _P, _P, _P, _i64, _i32, _f32, _i32, _i32, _P])
 
 
 def _s():
@@ -147,7 +148,15 @@ def bigru(xp, whh, bhh, out, hidden):
     _ffi.check(_ffi.lib().b200vc_bigru(_p(_f32c(xp)), _p(whh), _p(bhh), _p(out), T, hidden, _s()), "bigru")
 
 
-def rmvpe_decode(sal, f0, T, thred):
-    assert f0.dtype == torch.float64 and sal.stride(1) == 1
-    _ffi.check(_ffi.lib().b200vc_rmvpe_decode(_p(_f32c(sal)), _p(f0), T, sal.shape[1], sal.stride(0), thred, _s()),
-               "rmvpe_decode")
+def rmvpe_decode(sal, f0, T, thred, cents=None):
+    assert f0.dtype == torch.float64 and sal.stride(1) == 1 and (cents is None or cents.dtype == torch.float64)
+    _ffi.check(_ffi.lib().b200vc_rmvpe_decode(_p(_f32c(sal)), _p(f0), _p(cents), T, sal.shape[1], sal.stride(0), thred,
+                                              _s()), "rmvpe_decode")
+
+
+def groupnorm_time(x, gamma, beta, out, stats, eps=1e-5, act_code=0, round_out=False):
+    """Per-channel normalisation over rows of x [rows, C] + activation; stats: [2*C] float64 scratch."""
+    rows, Cc = x.shape
+    assert x.is_contiguous() and out.is_contiguous() and stats.dtype == torch.float64 and stats.numel() >= 2 * Cc
+    _ffi.check(_ffi.lib().b200vc_groupnorm_time(_p(_f32c(x)), _p(gamma), _p(beta), _p(out), _p(stats), rows, Cc, eps,
+                                                act_code, int(round_out), _s()), "groupnorm_time")

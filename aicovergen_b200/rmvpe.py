@@ -149,7 +149,14 @@ class RMVPEB200:
     def infer_from_audio(self, audio: np.ndarray, thred: float = 0.03) -> np.ndarray:
         """Reference signature (rmvpe.py:366-383): np.ndarray[N] -> np.ndarray[1 + N//160] (float64 Hz, 0 = unvoiced)."""
         a = torch.from_numpy(np.ascontiguousarray(audio)).float().to(self.device)
-        return self.infer_from_audio_device(a, thred).cpu().numpy()
+        pl = self._plan(int(a.numel()))
+        pl.run(a)
+        ops.rmvpe_decode(pl.sal, pl.f0, pl.n_frames, thred, cents=pl.cents)
+        cents_pred = pl.cents.cpu().numpy()
+        # the reference's own last two numpy lines (rmvpe.py:361-362), on the host so f0 is bit-identical
+        f0 = 10 * (2 ** (cents_pred / 1200))
+        f0[f0 == 10] = 0
+        return f0
 
 
 class _RmvpePlan:
@@ -233,6 +240,7 @@ class _RmvpePlan:
         self.sal = torch.empty(T, N_CLASS, **f32)
         add(tg.linear(hseq, W["fc.w"], self.sal, Epi(bias=W["fc.b"], act_pre=tg.ACT_SIGMOID), be, name="fc"))
         self.f0 = torch.empty(nf, device=dev, dtype=torch.float64)
+        self.cents = torch.empty(nf, device=dev, dtype=torch.float64)
         self.steps = steps
 
     def run(self, audio: torch.Tensor):

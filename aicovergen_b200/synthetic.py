@@ -209,3 +209,49 @@ def make_rmvpe_state_dict(seed: int = 4321, n_blocks: int = 4, en_de_layers: int
     sd["fc.1.weight"] = g.conv((n_class, 2 * Hh), 1.0)
     sd["fc.1.bias"] = g.normal((n_class,), 0.3, -1.5)
     return sd
+
+
+# ---------------------------------------------------------------------------
+# hubert_base.pt — fairseq 0.12.2 HubertModel state-dict names (rvc.py:98-109)
+# ---------------------------------------------------------------------------
+HUBERT_CONV = [(512, 10, 5)] + [(512, 3, 2)] * 4 + [(512, 2, 2)] * 2
+
+
+def make_hubert_state_dict(seed: int = 777, layers: int = 12, dim: int = 768, ffn: int = 3072,
+                           conv=HUBERT_CONV, pos_k: int = 128, pos_groups: int = 16) -> Dict[str, torch.Tensor]:
+    g = _Gen(seed)
+    sd: Dict[str, torch.Tensor] = {}
+    cin = 1
+    for i, (c, k, s) in enumerate(conv):
+        sd[f"feature_extractor.conv_layers.{i}.0.weight"] = g.conv((c, cin, k), 1.6)
+        cin = c
+    sd["feature_extractor.conv_layers.0.2.weight"] = g.uniform((conv[0][0],), 0.7, 1.3)
+    sd["feature_extractor.conv_layers.0.2.bias"] = g.normal((conv[0][0],), 0.1)
+    sd["layer_norm.weight"] = g.uniform((cin,), 0.8, 1.2)
+    sd["layer_norm.bias"] = g.normal((cin,), 0.05)
+    sd["post_extract_proj.weight"] = g.conv((dim, cin), 1.0)
+    sd["post_extract_proj.bias"] = g.normal((dim,), 0.05)
+    v = g.conv((dim, dim // pos_groups, pos_k), 1.0)
+    sd["encoder.pos_conv.0.weight_v"] = v
+    sd["encoder.pos_conv.0.weight_g"] = v.pow(2).sum(dim=(0, 1), keepdim=True).sqrt().clone()   # weight_norm dim=2
+    sd["encoder.pos_conv.0.bias"] = g.normal((dim,), 0.05)
+    sd["encoder.layer_norm.weight"] = g.uniform((dim,), 0.8, 1.2)
+    sd["encoder.layer_norm.bias"] = g.normal((dim,), 0.05)
+    for i in range(layers):
+        p = f"encoder.layers.{i}."
+        for n in ("q", "k", "v", "out"):
+            sd[p + f"self_attn.{n}_proj.weight"] = g.conv((dim, dim), 1.0 if n in ("q", "k") else 0.7)
+            sd[p + f"self_attn.{n}_proj.bias"] = g.normal((dim,), 0.05)
+        sd[p + "self_attn_layer_norm.weight"] = g.uniform((dim,), 0.8, 1.2)
+        sd[p + "self_attn_layer_norm.bias"] = g.normal((dim,), 0.05)
+        sd[p + "fc1.weight"] = g.conv((ffn, dim), 1.0)
+        sd[p + "fc1.bias"] = g.normal((ffn,), 0.05)
+        sd[p + "fc2.weight"] = g.conv((dim, ffn), 0.7)
+        sd[p + "fc2.bias"] = g.normal((dim,), 0.05)
+        sd[p + "final_layer_norm.weight"] = g.uniform((dim,), 0.8, 1.2)
+        sd[p + "final_layer_norm.bias"] = g.normal((dim,), 0.05)
+    sd["final_proj.weight"] = g.conv((256, dim), 1.0)
+    sd["final_proj.bias"] = g.normal((256,), 0.05)
+    sd["mask_emb"] = g.uniform((dim,), 0.0, 1.0)
+    sd["label_embs_concat"] = g.normal((504, 256), 1.0)
+    return sd

@@ -170,8 +170,15 @@ int b200vc_avgpool2x2(const float* in, float* out, int B, int H, int W, int C, i
  * xp [T, 2*3H] = x W_ih^T + b_ih (dir d at column d*3H); whh [2,3H,H]; bhh [2,3H]; out [T,2H]. */
 int b200vc_bigru(const float* xp, const float* whh, const float* bhh, float* out, int T, int hidden, void* stream);
 
-/* salience [T,n_bins] -> f0[T] (float64) exactly as RMVPE.decode / to_local_average_cents (rmvpe.py:359-409) */
-int b200vc_rmvpe_decode(const float* salience, double* f0, int T, int n_bins, int64_t ld, float thred, void* stream);
+/* salience [T,n_bins] -> cents[T] and f0[T] = 10*2^(cents/1200) (float64) with numpy's summation order, as
+ * RMVPE.to_local_average_cents / decode (rmvpe.py:359-409). cents may be NULL. */
+int b200vc_rmvpe_decode(const float* salience, double* f0, double* cents, int T, int n_bins, int64_t ld, float thred,
+                        void* stream);
+
+/* Per-channel normalisation over the time axis of x[rows,C] (nn.GroupNorm(C, C) on [1,C,T]) followed by `act`:
+ * fairseq ConvFeatureExtractionModel layer 0 (called through vc_infer_pipeline.py:405). stats: 2*C doubles scratch. */
+int b200vc_groupnorm_time(const float* x, const float* gamma, const float* beta, float* out, double* stats,
+                          int64_t rows, int C, float eps, int act, int round_out, void* stream);
 
 #ifdef __cplusplus
 }

