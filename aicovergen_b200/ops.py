@@ -32,6 +32,10 @@ _ffi.declare("b200vc_avgpool2x2", [_P, _P, _i32, _i32, _i32, _i32, _i64, _P])
 _ffi.declare("b200vc_bigru", [_P, _P, _P, _P, _i32, _i32, _P])
 _ffi.declare("b200vc_rmvpe_decode", [_P, _P, _P, _i32, _i32, _i64, _f32, _P])
 _ffi.declare("b200vc_groupnorm_time", [_P, _P, _P, _P, _P, _i64, _i32, _f32, _i32, _i32, _P])
+_ffi.declare("b200vc_argmin_rows", [_P, _P, _i32, _i32, _i64, _P])
+_ffi.declare("b200vc_ivf_scan_blend", [_P, _i64, _P, _P, _P, _P, _P, _i64, _i32, _i32, _f32, _P, _P, _P])
+_ffi.declare("b200vc_upsample2_protect", [_P, _P, _P, _P, _i64, _i32, _f32, _i32, _P])
+_ffi.declare("b200vc_boxsum_f64", [_P, _P, _i64, _i32, _P])
 
 
 def _s():
@@ -160,3 +164,30 @@ def groupnorm_time(x, gamma, beta, out, stats, eps=1e-5, act_code=0, round_out=F
     assert x.is_contiguous() and out.is_contiguous() and stats.dtype == torch.float64 and stats.numel() >= 2 * Cc
     _ffi.check(_ffi.lib().b200vc_groupnorm_time(_p(_f32c(x)), _p(gamma), _p(beta), _p(out), _p(stats), rows, Cc, eps,
                                                 act_code, int(round_out), _s()), "groupnorm_time")
+
+
+def argmin_rows(S, out):
+    rows, n = S.shape
+    assert S.stride(1) == 1 and out.dtype == torch.int32
+    _ffi.check(_ffi.lib().b200vc_argmin_rows(_p(_f32c(S)), _p(out), rows, n, S.stride(0), _s()), "argmin_rows")
+
+
+def ivf_scan_blend(q, assign, offsets, ids, vecs, out, rate, out_score=None, out_ids=None):
+    T, d = q.shape
+    assert q.stride(1) == 1 and out.stride(1) == 1 and vecs.is_contiguous()
+    assert assign.dtype == torch.int32 and offsets.dtype == torch.int32 and ids.dtype == torch.int64
+    _ffi.check(_ffi.lib().b200vc_ivf_scan_blend(_p(_f32c(q)), q.stride(0), _p(assign), _p(offsets), _p(ids), _p(vecs),
+                                                _p(out), out.stride(0), T, d, float(rate), _p(out_score), _p(out_ids),
+                                                _s()), "ivf_scan_blend")
+
+
+def upsample2_protect(feats, feats0, pitchf, out, protect, do_protect):
+    P, Cc = out.shape
+    assert feats.is_contiguous() and out.is_contiguous()
+    _ffi.check(_ffi.lib().b200vc_upsample2_protect(_p(_f32c(feats)), _p(feats0), _p(pitchf), _p(out), P, Cc,
+                                                   float(protect), int(do_protect), _s()), "upsample2_protect")
+
+
+def boxsum_f64(x, out, n, window):
+    assert x.dtype == torch.float64 and out.dtype == torch.float64 and x.numel() >= n + window - 1
+    _ffi.check(_ffi.lib().b200vc_boxsum_f64(_p(x), _p(out), n, window, _s()), "boxsum_f64")

@@ -255,3 +255,29 @@ def make_hubert_state_dict(seed: int = 777, layers: int = 12, dim: int = 768, ff
     sd["mask_emb"] = g.uniform((dim,), 0.0, 1.0)
     sd["label_embs_concat"] = g.normal((504, 256), 1.0)
     return sd
+
+
+# ---------------------------------------------------------------------------
+# IVF-Flat index contents (faiss `added_IVF{nlist}_Flat_nprobe_1_*.index`, vc_infer_pipeline.py:505-507)
+# ---------------------------------------------------------------------------
+def make_ivf_index_data(base_feats: torch.Tensor, n_total: int = 87243, nlist: int = 2237, seed: int = 99,
+                        jitter: float = 0.05):
+    """Database = rows of `base_feats` (HuBERT features of a seeded clip) cycled to n_total + N(0, jitter);
+    centroids = one k-means iteration from a seeded sample (SURVEY.md §8(d) cfg 3). Returns (centroids, vectors)."""
+    g = torch.Generator().manual_seed(seed)
+    base = base_feats.float().cpu()
+    reps = (n_total + base.shape[0] - 1) // base.shape[0]
+    vecs = base.repeat(reps, 1)[:n_total].clone()
+    vecs += torch.randn(vecs.shape, generator=g) * jitter
+    perm = torch.randperm(n_total, generator=g)[:nlist]
+    cent = vecs[perm].clone()
+    # one Lloyd iteration
+    c2 = (cent.double() ** 2).sum(1)
+    assign = torch.empty(n_total, dtype=torch.long)
+    for s in range(0, n_total, 8192):
+        d = c2[None, :] - 2.0 * vecs[s:s + 8192].double() @ cent.double().t()
+        assign[s:s + 8192] = d.argmin(1)
+    sums = torch.zeros_like(cent, dtype=torch.float64).index_add_(0, assign, vecs.double())
+    cnt = torch.bincount(assign, minlength=nlist).clamp(min=1)[:, None]
+    cent = (sums / cnt).float()
+    return cent.numpy(), vecs.numpy()

@@ -1,0 +1,251 @@
+"""Host mirror of the reference's RVC inference driver (src/vc_infer_pipeline.py) over the B200 operators.
+
+Same class, method names, argument order and return types as the reference (`VC(tgt_sr, config)`,
+`VC.pipeline(model, net_g, sid, audio, input_audio_path, times, f0_up_key, f0_method, file_index,
+index_rate, if_f0, filter_radius, tgt_sr, resample_sr, rms_mix_rate, version, protect,
+crepe_hop_length, f0_file=None) -> np.int16[...]`, vc_infer_pipeline.py:474-653), so `rvc.rvc_infer`
+and `main.song_cover_pipeline` keep working unchanged.  What differs is where the arithmetic runs:
+HuBERT / index lookup / synthesizer / rmvpe are the libb200vc.so operators and segment audio stays in
+HBM between them (the reference hops D2H/H2D around faiss and after every segment).
+
+Extension (not in the reference): `vc.set_noise_seed(seed)` makes the synthesizer's random draws replay
+the CPU stream `torch.manual_seed(seed)` would give the reference, for parity tests.
+"""
+from __future__ import annotations
+
+import os
+import traceback
+from time import time as ttime
+from typing import Optional
+
+import numpy as np
+import torch
+from scipy import signal
+
+from . import ops
+from .index import IvfIndexB200, read_index
+
+# 5th-order Butterworth high-pass at 48 Hz for 16 kHz input (vc_infer_pipeline.py:22)
+bh, ah = signal.butter(N=5, Wn=48, btype="high", fs=16000)
+
+
+def _frame_rms(y: np.ndarray, frame_length: int, hop_length: int) -> np.ndarray:
+    """librosa.feature.rms(y=..., frame_length, hop_length) of librosa 0.9.1 (center=True, reflect padding) -> [1, n]."""
+    pad = frame_length // 2
+    yp = np.pad(y, (pad, pad), mode="reflect")
+    n = 1 + (len(yp) - frame_length) // hop_length
+    sq = np.abs(yp) ** 2
+    csum = np.concatenate(([0.0], np.cumsum(sq, dtype=np.float64)))
+    starts = hop_length * np.arange(n)
+    power = (csum[starts + frame_length] - csum[starts]) / frame_length
+    return np.sqrt(np.maximum(power, 0.0)).astype(y.dtype if y.dtype in (np.float32, np.float64) else np.float64)[None, :]
+
+
+def change_rms(data1, sr1, data2, sr2, rate):
+    """Match the output loudness envelope to the input's (vc_infer_pipeline.py:41-60). data2 is scaled in place."""
+    import torch.nn.functional as F
+
+    rms1 = _frame_rms(data1, sr1 // 2 * 2, sr1 // 2)
+    rms2 = _frame_rms(data2, sr2 // 2 * 2, sr2 // 2)
+    rms1 = F.interpolate(torch.from_numpy(rms1).unsqueeze(0), size=data2.shape[0], mode="linear").squeeze()
+    rms2 = F.interpolate(torch.from_numpy(rms2).unsqueeze(0), size=data2.shape[0], mode="linear").squeeze()
+    rms2 = torch.max(rms2, torch.zeros_like(rms2) + 1e-6)
+    data2 *= (torch.pow(rms1, torch.tensor(1 - rate)) * torch.pow(rms2, torch.tensor(rate - 1))).numpy()
+    return data2
+
+
+class VC(object):
+    def __init__(self, tgt_sr, config):
+        self.x_pad, self.x_query, self.x_center, self.x_max, self.is_half = (
+            config.x_pad, config.x_query, config.x_center, config.x_max, config.is_half)
+        self.sr = 16000                              # HuBERT input rate
+        self.window = 160                            # samples per F0 frame
+        self.t_pad = self.sr * self.x_pad            # reflect context each side of a segment
+        self.t_pad_tgt = tgt_sr * self.x_pad
+        self.t_pad2 = self.t_pad * 2
+        self.t_query = self.sr * self.x_query        # +- search range around each nominal cut
+        self.t_center = self.sr * self.x_center      # nominal cut spacing
+        self.t_max = self.sr * self.x_max            # below this no cutting
+        self.device = config.device
+        self._noise_gen: Optional[torch.Generator] = None
+
+    # ------------------------------------------------------------------ extension for parity tests
+    def set_noise_seed(self, seed: Optional[int]):
+        self._noise_gen = None if seed is None else torch.Generator().manual_seed(int(seed))
+
+    def _draw_noise(self, net_g, P):
+        """Replays the reference's draw order inside net_g.infer (models.py:748, :337, :368)."""
+        if self._noise_gen is None:
+            return None, None
+        g = self._noise_gen
+        nz = torch.randn(1, net_g.inter, P, generator=g)
+        _ = torch.rand(1, 1, generator=g)
+        ns = torch.randn(1, P * net_g.upp, 1, generator=g) if net_g.f0 else None
+        dev = self.device
+        return nz.to(dev), (None if ns is None else ns.to(dev))
+
+    # ------------------------------------------------------------------ F0
+    def get_f0(self, input_audio_path, x, p_len, f0_up_key, f0_method, filter_radius, crepe_hop_length, inp_f0=None):
+        """rmvpe branch of the reference (vc_infer_pipeline.py:262-278, 322-329, 346-370)."""
+        f0_min, f0_max = 50, 1100
+        f0_mel_min = 1127 * np.log(1 + f0_min / 700)
+        f0_mel_max = 1127 * np.log(1 + f0_max / 700)
+        if f0_method == "rmvpe":
+            if not hasattr(self, "model_rmvpe"):
+                from .rmvpe import RMVPEB200
+                from .rvc import BASE_DIR
+                self.model_rmvpe = RMVPEB200(os.path.join(BASE_DIR, "rvc_models", "rmvpe.pt"), is_half=self.is_half,
+                                             device=self.device)
+            f0 = self.model_rmvpe.infer_from_audio(x, thred=0.03)
+        else:
+            raise NotImplementedError(
+                f"f0_method={f0_method!r}: only 'rmvpe' runs on the B200 path (crepe is SURVEY.md §8(f) next-row; "
+                "pm/harvest/dio are CPU libraries outside the hot path)")
+        f0 *= pow(2, f0_up_key / 12)
+        tf0 = self.sr // self.window
+        if inp_f0 is not None:
+            delta_t = np.round((inp_f0[:, 0].max() - inp_f0[:, 0].min()) * tf0 + 1).astype("int16")
+            replace_f0 = np.interp(list(range(delta_t)), inp_f0[:, 0] * 100, inp_f0[:, 1])
+            shape = f0[self.x_pad * tf0: self.x_pad * tf0 + len(replace_f0)].shape[0]
+            f0[self.x_pad * tf0: self.x_pad * tf0 + len(replace_f0)] = replace_f0[:shape]
+        f0bak = f0.copy()
+        f0_mel = 1127 * np.log(1 + f0 / 700)
+        f0_mel[f0_mel > 0] = (f0_mel[f0_mel > 0] - f0_mel_min) * 254 / (f0_mel_max - f0_mel_min) + 1
+        f0_mel[f0_mel <= 1] = 1
+        f0_mel[f0_mel > 255] = 255
+        f0_coarse = np.rint(f0_mel).astype(int)
+        return f0_coarse, f0bak
+
+    # ------------------------------------------------------------------ one segment
+    def vc(self, model, net_g, sid, audio0, pitch, pitchf, times, index, big_npy, index_rate, version, protect):
+        """Returns the converted segment as a float32 DEVICE tensor (the reference returns numpy; pipeline()
+        keeps segments in HBM until the final concat)."""
+        dev = self.device
+        feats = torch.from_numpy(np.ascontiguousarray(audio0)).float() if isinstance(audio0, np.ndarray) else audio0.float()
+        if feats.dim() == 2:
+            feats = feats.mean(-1)
+        assert feats.dim() == 1, feats.dim()
+        n_in = feats.shape[0]
+        feats = feats.view(1, -1).to(dev)
+        padding_mask = torch.zeros(feats.shape, dtype=torch.bool, device=dev)
+        t0 = ttime()
+        logits = model.extract_features(source=feats, padding_mask=padding_mask, output_layer=9 if version == "v1" else 12)
+        feats = model.final_proj(logits[0]) if version == "v1" else logits[0]
+        f2d = feats[0]                                             # [T, C]
+        has_f0 = pitch is not None and pitchf is not None
+        do_protect = protect < 0.5 and has_f0
+        feats0 = f2d.clone() if do_protect else None
+        if index is not None and big_npy is not None and index_rate != 0:
+            f2d = index.search_blend(f2d, index_rate)
+        t1 = ttime()
+        p_len = n_in // self.window
+        if 2 * f2d.shape[0] < p_len:
+            p_len = 2 * f2d.shape[0]
+        if has_f0:
+            pitch = pitch[:, :p_len]
+            pitchf = pitchf[:, :p_len]
+        up = torch.empty(p_len, f2d.shape[1], device=dev)
+        ops.upsample2_protect(f2d.contiguous(), feats0, pitchf.reshape(-1).contiguous() if has_f0 else None, up,
+                              protect, do_protect)
+        p_len_t = torch.tensor([p_len], device=dev).long()
+        nz, ns = self._draw_noise(net_g, p_len)
+        if has_f0:
+            audio1 = net_g.infer(up.unsqueeze(0), p_len_t, pitch, pitchf, sid, noise_z=nz, noise_src=ns)[0][0, 0]
+        else:
+            audio1 = net_g.infer(up.unsqueeze(0), p_len_t, sid, noise_z=nz)[0][0, 0]
+        t2 = ttime()
+        times[0] += t1 - t0
+        times[2] += t2 - t1
+        return audio1
+
+    # ------------------------------------------------------------------ whole utterance
+    def _cut_points(self, audio: np.ndarray):
+        """Quiet-point search (vc_infer_pipeline.py:514-528): 160-tap box sum of the reflect-padded signal,
+        then argmin |sum| within +-t_query of every t_center multiple. The box sum runs on the device in fp64
+        with the reference's accumulation order, the window scan on the host."""
+        audio_pad = np.pad(audio, (self.window // 2, self.window // 2), mode="reflect")
+        opt_ts = []
+        if audio_pad.shape[0] > self.t_max:
+            n = audio.shape[0]
+            xd = torch.from_numpy(np.ascontiguousarray(audio_pad, dtype=np.float64)).to(self.device)
+            sd = torch.empty(n, dtype=torch.float64, device=self.device)
+            ops.boxsum_f64(xd, sd, n, self.window)
+            audio_sum = sd.cpu().numpy()
+            for t in range(self.t_center, audio.shape[0], self.t_center):
+                seg = np.abs(audio_sum[t - self.t_query: t + self.t_query])
+                opt_ts.append(t - self.t_query + np.where(seg == seg.min())[0][0])
+        return opt_ts
+
+    def pipeline(self, model, net_g, sid, audio, input_audio_path, times, f0_up_key, f0_method, file_index,
+                 index_rate, if_f0, filter_radius, tgt_sr, resample_sr, rms_mix_rate, version, protect,
+                 crepe_hop_length, f0_file=None):
+        if file_index != "" and os.path.exists(file_index) and index_rate != 0:
+            try:
+                index = read_index(file_index, self.device)
+                big_npy = index.reconstruct_n(0, index.ntotal)
+            except Exception:
+                traceback.print_exc()
+                index = big_npy = None
+        else:
+            index = big_npy = None
+        audio = signal.filtfilt(bh, ah, audio)
+        opt_ts = self._cut_points(audio)
+        s = 0
+        audio_opt = []
+        t = None
+        t1 = ttime()
+        audio_pad = np.pad(audio, (self.t_pad, self.t_pad), mode="reflect")
+        p_len = audio_pad.shape[0] // self.window
+        inp_f0 = None
+        if hasattr(f0_file, "name"):
+            try:
+                with open(f0_file.name, "r") as f:
+                    lines = f.read().strip("\n").split("\n")
+                inp_f0 = np.array([[float(i) for i in line.split(",")] for line in lines], dtype="float32")
+            except Exception:
+                traceback.print_exc()
+        sid = torch.tensor(sid, device=self.device).unsqueeze(0).long()
+        pitch, pitchf = None, None
+        if if_f0 == 1:
+            pitch, pitchf = self.get_f0(input_audio_path, audio_pad, p_len, f0_up_key, f0_method, filter_radius,
+                                        crepe_hop_length, inp_f0)
+            pitch = pitch[:p_len]
+            pitchf = pitchf[:p_len]
+            pitch = torch.tensor(pitch, device=self.device).unsqueeze(0).long()
+            pitchf = torch.tensor(pitchf, device=self.device).unsqueeze(0).float()
+        t2 = ttime()
+        times[1] += t2 - t1
+        # the padded utterance goes to HBM once; segments are device slices of it
+        pad_dev = torch.from_numpy(np.ascontiguousarray(audio_pad)).to(self.device).float()
+        w = self.window
+        for t in opt_ts:
+            t = t // w * w
+            seg = pad_dev[s: t + self.t_pad2 + w]
+            if if_f0 == 1:
+                out = self.vc(model, net_g, sid, seg, pitch[:, s // w: (t + self.t_pad2) // w],
+                              pitchf[:, s // w: (t + self.t_pad2) // w], times, index, big_npy, index_rate, version, protect)
+            else:
+                out = self.vc(model, net_g, sid, seg, None, None, times, index, big_npy, index_rate, version, protect)
+            audio_opt.append(out[self.t_pad_tgt: -self.t_pad_tgt].clone())
+            s = t
+        seg = pad_dev[t:] if t is not None else pad_dev
+        if if_f0 == 1:
+            out = self.vc(model, net_g, sid, seg, pitch[:, t // w:] if t is not None else pitch,
+                          pitchf[:, t // w:] if t is not None else pitchf, times, index, big_npy, index_rate, version, protect)
+        else:
+            out = self.vc(model, net_g, sid, seg, None, None, times, index, big_npy, index_rate, version, protect)
+        audio_opt.append(out[self.t_pad_tgt: -self.t_pad_tgt].clone())
+        audio_opt = torch.cat(audio_opt).cpu().numpy()          # the single D2H of the converted utterance
+        self.last_float_output = audio_opt.copy()                # pre-RMS-mix float waveform (parity tests)
+        if rms_mix_rate != 1:
+            audio_opt = change_rms(audio, 16000, audio_opt, tgt_sr, rms_mix_rate)
+        if resample_sr >= 16000 and tgt_sr != resample_sr:
+            raise NotImplementedError("resample_sr != 0 needs librosa.resample; rvc_infer always passes 0 (rvc.py:150)")
+        audio_max = np.abs(audio_opt).max() / 0.99
+        max_int16 = 32768
+        if audio_max > 1:
+            max_int16 /= audio_max
+        self.last_float_mixed = audio_opt
+        audio_opt = (audio_opt * max_int16).astype(np.int16)
+        del pitch, pitchf, sid
+        return audio_opt

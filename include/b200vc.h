@@ -180,6 +180,27 @@ int b200vc_rmvpe_decode(const float* salience, double* f0, double* cents, int T,
 int b200vc_groupnorm_time(const float* x, const float* gamma, const float* beta, float* out, double* stats,
                           int64_t rows, int C, float eps, int act, int round_out, void* stream);
 
+/* ---- VC.pipeline glue (vc_infer_pipeline.py) ---- */
+
+/* out[r] = index of the first minimum of S[r, 0..n) */
+int b200vc_argmin_rows(const float* S, int* out, int rows, int n, int64_t ld, void* stream);
+
+/* faiss IndexIVFFlat(nprobe=1) search(k=8) + the weighting/blend of vc_infer_pipeline.py:421-431 in one kernel:
+ * for query t scan inverted list assign[t] (vectors vecs[offsets[l]..offsets[l+1]), list order), take the 8 smallest
+ * squared-L2, w=(1/d)^2 normalised, out = rate * sum w_k v_k + (1-rate) * q.  out_score/out_ids ([T,8]) optional. */
+int b200vc_ivf_scan_blend(const float* q, int64_t ldq, const int* assign, const int* offsets, const int64_t* ids,
+                          const float* vecs, float* out, int64_t ldo, int T, int d, float rate, float* out_score,
+                          int64_t* out_ids, void* stream);
+
+/* F.interpolate(scale_factor=2) (nearest) of feats/feats0 [T,C] -> [P,C] fused with the `protect` blend
+ * (vc_infer_pipeline.py:433-452); do_protect=0 only upsamples. */
+int b200vc_upsample2_protect(const float* feats, const float* feats0, const float* pitchf, float* out, int64_t P,
+                             int C, float protect, int do_protect, void* stream);
+
+/* out[i] = sum_{j<window} x[i+j] in fp64, accumulated in index order exactly like the 160-pass numpy loop at
+ * vc_infer_pipeline.py:517-519 (x has n+window-1 valid elements). */
+int b200vc_boxsum_f64(const double* x, double* out, int64_t n, int window, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
