@@ -57,7 +57,9 @@ class TapGemmParams(C.Structure):
         ("bias_per_row", C.c_int32),
         ("act_pre", C.c_int32),
         ("act_pre_p", C.c_float),
+        ("row_scale", C.c_void_p),
         ("res", C.c_void_p),
+        ("res_op", C.c_int32),
         ("scale", C.c_float),
         ("res2", C.c_void_p),
         ("act_post", C.c_int32),

@@ -199,9 +199,10 @@ __global__ void rmvpe_decode_kernel(const float* __restrict__ sal, double* __res
       const bool in = (k >= 0 && k < NB);
       sv[i] = in ? s[k] : 0.f;
       const double cents = in ? (20.0 * (double)k + 1997.3794084376191) : 0.0;
-      pv[i] = (double)sv[i] * cents;
+      pv[i] = __dmul_rn((double)sv[i], cents);   // no FMA contraction: numpy rounds the product first
     }
-    const double psum = (((pv[0] + pv[1]) + (pv[2] + pv[3])) + ((pv[4] + pv[5]) + (pv[6] + pv[7]))) + pv[8];
+    const double psum = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(pv[0], pv[1]), __dadd_rn(pv[2], pv[3])),
+                                            __dadd_rn(__dadd_rn(pv[4], pv[5]), __dadd_rn(pv[6], pv[7]))), pv[8]);
     const float wsum = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(sv[0], sv[1]), __fadd_rn(sv[2], sv[3])),
                                            __fadd_rn(__fadd_rn(sv[4], sv[5]), __fadd_rn(sv[6], sv[7]))), sv[8]);
     double cents = psum / (double)wsum;

@@ -53,7 +53,8 @@ __device__ __forceinline__ float tg_epi1(const TgParams& p, const TgRow& r, int 
   float v = acc;
   if (p.bias) v += p.bias_per_row ? __ldg(p.bias + r.brow) : __ldg(p.bias + n);
   v = apply_act(v, p.act_pre, p.act_pre_p);
-  if (p.res) v += p.res[r.r_off + n];
+  if (p.row_scale) v *= __ldg(p.row_scale + r.brow);
+  if (p.res) { const float rr = p.res[r.r_off + n]; v = p.res_op ? v * rr : v + rr; }
   v *= p.scale;
   if (p.res2) v += p.res2[r.o_off + n];
   v = apply_act(v, p.act_post, p.act_post_p);
@@ -87,9 +88,14 @@ __device__ __forceinline__ void tg_store4(const TgParams& p, const TgRow& r, int
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[i] = apply_act(v[i], p.act_pre, p.act_pre_p);
+    if (p.row_scale) {
+      const float rs = __ldg(p.row_scale + r.brow);
+      v[0] *= rs; v[1] *= rs; v[2] *= rs; v[3] *= rs;
+    }
     if (p.res) {
       float4 rr = *reinterpret_cast<const float4*>(p.res + r.r_off + n);
-      v[0] += rr.x; v[1] += rr.y; v[2] += rr.z; v[3] += rr.w;
+      if (p.res_op) { v[0] *= rr.x; v[1] *= rr.y; v[2] *= rr.z; v[3] *= rr.w; }
+      else { v[0] += rr.x; v[1] += rr.y; v[2] += rr.z; v[3] += rr.w; }
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[i] *= p.scale;

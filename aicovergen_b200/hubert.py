@@ -145,7 +145,7 @@ class _HubertPlan:
         rows_even = lambda t: t + (t % 2)
         cur = torch.zeros(rows_even(T0), 512, **f32)
         gstats = torch.zeros(2 * 512, device=dev, dtype=torch.float64)
-        add(lambda: ops.groupnorm_time(c0, W["gn.g"], W["gn.b"], cur[:T0], gstats, 1e-5, tg.ACT_GELU, R))
+        add(lambda cur=cur: ops.groupnorm_time(c0, W["gn.g"], W["gn.b"], cur[:T0], gstats, 1e-5, tg.ACT_GELU, R))
         # ---- conv1..6 (stride 2) through the [T/2, 2C] view
         for i in range(1, len(CONV)):
             To = lens[i]

@@ -36,6 +36,11 @@ _ffi.declare("b200vc_argmin_rows", [_P, _P, _i32, _i32, _i64, _P])
 _ffi.declare("b200vc_ivf_scan_blend", [_P, _i64, _P, _P, _P, _P, _P, _i64, _i32, _i32, _f32, _P, _P, _P])
 _ffi.declare("b200vc_upsample2_protect", [_P, _P, _P, _P, _i64, _i32, _f32, _i32, _P])
 _ffi.declare("b200vc_boxsum_f64", [_P, _P, _i64, _i32, _P])
+_ffi.declare("b200vc_mdx_gather_chunks", [_P, _i64, _P, _P, _P, _P, _i32, _i32, _i32, _f32, _i32, _P])
+_ffi.declare("b200vc_nhwc_to_nhcw", [_P, _P, _P, _i64, _i32, _i32, _i32, _P])
+_ffi.declare("b200vc_nhcw_to_nhwc_add", [_P, _P, _P, _i64, _i32, _i32, _i32, _P])
+_ffi.declare("b200vc_mdx_ola_store", [_P, _P, _P, _P, _P, _P, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _i32, _P])
+_ffi.declare("b200vc_mdx_finalize", [_P, _P, _P, _i64, _f32, _f32, _P])
 
 
 def _s():
@@ -191,3 +196,42 @@ def upsample2_protect(feats, feats0, pitchf, out, protect, do_protect):
 def boxsum_f64(x, out, n, window):
     assert x.dtype == torch.float64 and out.dtype == torch.float64 and x.numel() >= n + window - 1
     _ffi.check(_ffi.lib().b200vc_boxsum_f64(_p(x), _p(out), n, window, _s()), "boxsum_f64")
+
+
+def mdx_gather_chunks(wave, src_start, lo, hi, out, chunk, half, sign, round_out):
+    """wave [2, n_song] contiguous; src_start/lo/hi int64 [B]; out [B, 2, chunk + 2*half]."""
+    B = src_start.numel()
+    assert wave.is_contiguous() and out.is_contiguous() and src_start.dtype == torch.int64
+    _ffi.check(_ffi.lib().b200vc_mdx_gather_chunks(_p(_f32c(wave)), wave.shape[1], _p(src_start), _p(lo), _p(hi), _p(out),
+                                                   B, chunk, half, float(sign), int(round_out), _s()), "mdx_gather_chunks")
+
+
+def nhwc_to_nhcw(x, scale, out, round_out=False):
+    """x [..., W, C] contiguous -> out [..., C, W] (* scale[c])."""
+    W, Cc = x.shape[-2], x.shape[-1]
+    R = x.numel() // (W * Cc)
+    assert x.is_contiguous() and out.is_contiguous()
+    _ffi.check(_ffi.lib().b200vc_nhwc_to_nhcw(_p(_f32c(x)), _p(scale), _p(out), R, W, Cc, int(round_out), _s()), "nhwc_to_nhcw")
+
+
+def nhcw_to_nhwc_add(t, x, out, round_out=False):
+    """out[..., w, c] = x[..., w, c] + t[..., c, w]."""
+    W, Cc = x.shape[-2], x.shape[-1]
+    R = x.numel() // (W * Cc)
+    assert x.is_contiguous() and out.is_contiguous() and t.is_contiguous()
+    _ffi.check(_ffi.lib().b200vc_nhcw_to_nhwc_add(_p(_f32c(t)), _p(x), _p(out), R, W, Cc, int(round_out), _s()),
+               "nhcw_to_nhwc_add")
+
+
+def mdx_ola_store(frames, env, dst_start, keep_lo, keep_hi, song, T, n_fft, hop, chunk, trim, coef, accumulate):
+    B = dst_start.numel()
+    assert frames.is_contiguous() and song.is_contiguous() and env.numel() >= chunk + n_fft
+    _ffi.check(_ffi.lib().b200vc_mdx_ola_store(_p(_f32c(frames)), _p(env), _p(dst_start), _p(keep_lo), _p(keep_hi), _p(song),
+                                               song.shape[1], B, T, n_fft, hop, chunk, trim, float(coef), int(accumulate),
+                                               _s()), "mdx_ola_store")
+
+
+def mdx_finalize(proc, wave_norm, inverse, peak, compensation):
+    assert proc.is_contiguous()
+    _ffi.check(_ffi.lib().b200vc_mdx_finalize(_p(_f32c(proc)), _p(wave_norm), _p(inverse), proc.numel(), float(peak),
+                                              float(compensation), _s()), "mdx_finalize")

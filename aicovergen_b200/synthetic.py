@@ -281,3 +281,51 @@ def make_ivf_index_data(base_feats: torch.Tensor, n_total: int = 87243, nlist: i
     cnt = torch.bincount(assign, minlength=nlist).clamp(min=1)[:, None]
     cent = (sums / cnt).float()
     return cent.numpy(), vecs.numpy()
+
+
+# ---------------------------------------------------------------------------
+# MDX-Net TFC-TDF U-Net ("ConvTDFNet") — the architecture inside the UVR-MDX-NET ONNX files (mdx.py:74).
+# The .onnx graphs are not in the reference repo: names follow the public KUIELab/UVR module layout.
+# ---------------------------------------------------------------------------
+def make_mdx_state_dict(dim_f: int = 3072, dim_t: int = 256, g: int = 48, l: int = 3, n: int = 5, bn: int = 8,
+                        k: int = 3, dim_c: int = 4, seed: int = 2024) -> Dict[str, torch.Tensor]:
+    gen = _Gen(seed)
+    sd: Dict[str, torch.Tensor] = {}
+
+    def bnorm(name, c):
+        sd[name + ".weight"] = gen.uniform((c,), 0.7, 1.3)
+        sd[name + ".bias"] = gen.normal((c,), 0.1)
+        sd[name + ".running_mean"] = gen.normal((c,), 0.1)
+        sd[name + ".running_var"] = gen.uniform((c,), 0.6, 1.4)
+
+    def tfc_tdf(p, c, f):
+        for j in range(l):
+            sd[f"{p}.tfc.H.{j}.0.weight"] = gen.conv((c, c, k, k), 1.3)
+            sd[f"{p}.tfc.H.{j}.0.bias"] = gen.normal((c,), 0.05)
+            bnorm(f"{p}.tfc.H.{j}.1", c)
+        sd[f"{p}.tdf.0.weight"] = gen.conv((f // bn, f), 1.0)
+        bnorm(f"{p}.tdf.1", c)
+        sd[f"{p}.tdf.3.weight"] = gen.conv((f, f // bn), 1.0)
+        bnorm(f"{p}.tdf.4", c)
+
+    sd["first_conv.0.weight"] = gen.conv((g, dim_c, 1, 1), 1.5)
+    sd["first_conv.0.bias"] = gen.normal((g,), 0.05)
+    bnorm("first_conv.1", g)
+    f, c = dim_f, g
+    for i in range(n):
+        tfc_tdf(f"encoding_blocks.{i}", c, f)
+        sd[f"ds.{i}.0.weight"] = gen.conv((c + g, c, 2, 2), 1.3)
+        sd[f"ds.{i}.0.bias"] = gen.normal((c + g,), 0.05)
+        bnorm(f"ds.{i}.1", c + g)
+        f, c = f // 2, c + g
+    tfc_tdf("bottleneck_block", c, f)
+    for i in range(n):
+        sd[f"us.{i}.0.weight"] = gen.normal((c, c - g, 2, 2), 1.3 / math.sqrt(c))     # ConvTranspose2d [Cin, Cout, 2, 2]
+        sd[f"us.{i}.0.bias"] = gen.normal((c - g,), 0.05)
+        bnorm(f"us.{i}.1", c - g)
+        f, c = f * 2, c - g
+        tfc_tdf(f"decoding_blocks.{i}", c, f)
+    sd["final_conv.0.weight"] = gen.conv((dim_c, c, 1, 1), 0.1)
+    sd["final_conv.0.bias"] = gen.normal((dim_c,), 0.02)
+    sd["_meta"] = torch.tensor([dim_f, dim_t, g, l, n, bn, k, dim_c])
+    return sd

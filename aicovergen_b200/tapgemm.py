@@ -119,7 +119,9 @@ class Epi:
     bias_per_row: bool = False
     act_pre: int = ACT_NONE
     act_pre_p: float = 0.0
+    row_scale: Optional[torch.Tensor] = None   # [OH*OW] per-output-row multiplier applied after act_pre
     res: Optional[torch.Tensor] = None     # channels-last tensor over the output pixel space
+    res_mul: bool = False                  # v *= res instead of v += res
     scale: float = 1.0
     res2: Optional[torch.Tensor] = None    # same addressing as out
     act_post: int = ACT_NONE
@@ -178,6 +180,10 @@ class TapGemm:
             self._keep.append(epi.bias)
         p.bias_per_row = int(epi.bias_per_row)
         p.act_pre, p.act_pre_p = epi.act_pre, float(epi.act_pre_p)
+        if epi.row_scale is not None:
+            assert epi.row_scale.dtype == torch.float32 and epi.row_scale.is_contiguous()
+            p.row_scale = epi.row_scale.data_ptr()
+            self._keep.append(epi.row_scale)
         p.r_sb = p.r_sh = p.r_sw = 0
         if epi.res is not None:
             r = epi.res
@@ -187,6 +193,7 @@ class TapGemm:
                 st.insert(0, 0)
             p.r_sb, p.r_sh, p.r_sw = int(st[0]), int(st[1]), int(st[2])
             p.res = r.data_ptr()
+            p.res_op = 1 if epi.res_mul else 0
             self._keep.append(r)
         p.scale = float(epi.scale)
         if epi.res2 is not None:

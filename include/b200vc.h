@@ -78,7 +78,9 @@ typedef struct b200vc_tapgemm_params {
   int32_t bias_per_row;
   int32_t act_pre;
   float act_pre_p;
+  const float* row_scale; /* optional: v *= row_scale[h*OW + w] after act_pre (per-output-row scale)   */
   const float* res;
+  int32_t res_op;       /* 0: v += res ; 1: v *= res (MDX-Net multiplicative skip) */
   float scale;
   const float* res2;
   int32_t act_post;
@@ -200,6 +202,34 @@ int b200vc_upsample2_protect(const float* feats, const float* feats0, const floa
 /* out[i] = sum_{j<window} x[i+j] in fp64, accumulated in index order exactly like the 160-pass numpy loop at
  * vc_infer_pipeline.py:517-519 (x has n+window-1 valid elements). */
 int b200vc_boxsum_f64(const double* x, double* out, int64_t n, int window, void* stream);
+
+/* ---- MDX-Net pass (src/mdx.py) ---- */
+
+/* Build the reflect-padded STFT input of B chunks straight from the song: out[b,ch,j], j in [0, chunk+2*half),
+ * = sign * wave[ch, src_start[b] + reflect(j-half)] when that song index is inside [lo[b],hi[b]) else 0
+ * (MDX.pad_wave zero regions, mdx.py:156-171, + torch.stft(center=True) reflect padding, mdx.py:39). */
+int b200vc_mdx_gather_chunks(const float* wave, int64_t n_song, const int64_t* src_start, const int64_t* lo,
+                             const int64_t* hi, float* out, int B, int chunk, int half, float sign, int round_out,
+                             void* stream);
+
+/* x [R,W,C] -> out [R,C,W] * scale[c] and back with a fused residual add: the layout change around the
+ * frequency-axis Linear layers (TDF) of the MDX-Net graph executed at mdx.py:77. */
+int b200vc_nhwc_to_nhcw(const float* x, const float* scale, float* out, int64_t R, int W, int C, int round_out,
+                        void* stream);
+int b200vc_nhcw_to_nhwc_add(const float* t, const float* x, float* out, int64_t R, int W, int C, int round_out,
+                            void* stream);
+
+/* torch.istft tail (mdx.py:53) fused with the trim / concat / [:-pad] / margin logic of mdx.py:195-197,107-117:
+ * frames [B,2,T,n_fft] = irfft(X)*window; overlap-add, divide by the window envelope env[chunk+n_fft], keep
+ * s in [trim, chunk-trim) and write song[ch, dst_start[b]+s-trim] (if inside [keep_lo[b],keep_hi[b])) with
+ * song = (accumulate ? song : 0) + coef*y. */
+int b200vc_mdx_ola_store(const float* frames, const float* env, const int64_t* dst_start, const int64_t* keep_lo,
+                         const int64_t* keep_hi, float* song, int64_t n_song, int B, int T, int n_fft, int hop,
+                         int chunk, int trim, float coef, int accumulate, void* stream);
+
+/* proc *= peak; inverse = -proc*compensation + wave_norm   (mdx.py:267, 280) */
+int b200vc_mdx_finalize(float* proc, const float* wave_norm, float* inverse, int64_t n, float peak,
+                        float compensation, void* stream);
 
 #ifdef __cplusplus
 }

@@ -78,6 +78,8 @@ def emulate(op) -> None:
         else:
             v = v + bias[None, :N]
     v = _act(v, epi.act_pre, epi.act_pre_p)
+    if epi.row_scale is not None:
+        v = v * epi.row_scale.double()[(hh * OW + ww)][:, None]
     n_idx = torch.arange(N)
     if epi.res is not None:
         r = epi.res
@@ -86,7 +88,8 @@ def emulate(op) -> None:
             st.insert(0, 0)
         rf = _flat(r).double()
         ridx = r.storage_offset() + bb * st[0] + hh * st[1] + ww * st[2]
-        v = v + rf[ridx[:, None] + n_idx[None, :]]
+        rv = rf[ridx[:, None] + n_idx[None, :]]
+        v = v * rv if epi.res_mul else v + rv
     v = v * epi.scale
     mh, mw = hh * out.osh + out.ooh, ww * out.osw + out.oow
     valid = (mh >= 0) & (mh < out.fh) & (mw >= 0) & (mw < out.fw)

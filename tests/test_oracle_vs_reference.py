@@ -119,3 +119,42 @@ def test_pipeline_oracle_matches_reference(with_index):
     # which the random-weight synthesizer amplifies to ~1e-4 on the waveform)
     assert diff.max() <= 12, diff.max()
     assert np.sqrt((diff.astype(np.float64) ** 2).mean()) < 1.5
+
+
+def test_mdx_oracle_matches_reference():
+    """mdx.py's own MDXModel.stft/istft and MDX.process_wave (2 threads, margins, padding) with a fake ORT
+    session running the restated net, vs oracle/mdx.py."""
+    from aicovergen_b200.synthetic import make_mdx_state_dict
+    from oracle import mdx as om
+    from oracle import ref_import
+
+    ref = ref_import.module("mdx")
+    dim_f, dim_t, n_fft = 256, 16, 2048         # small geometry: chunk = 1024*15 samples, trim 1024
+    sd = make_mdx_state_dict(dim_f=dim_f, dim_t=dim_t, g=8, n=3)
+    net = lambda spec: om.convtdfnet(sd, spec)
+
+    class FakeSession:
+        def __init__(self, path, providers=None):
+            pass
+
+        def run(self, _, feed):
+            return [net(torch.from_numpy(feed["input"])).numpy()]
+
+    sys.modules["onnxruntime"].InferenceSession = FakeSession
+    ref.ort.InferenceSession = FakeSession
+    model = ref.MDXModel(torch.device("cpu"), dim_f=dim_f, dim_t=dim_t, n_fft=n_fft, stem_name="Vocals", compensation=1.035)
+    sess = ref.MDX("fake.onnx", model, processor=-1)
+    mp = om.MdxParams(dim_f, dim_t, n_fft, stem_name="Vocals", compensation=1.035)
+    rng = np.random.default_rng(0)
+    N = 44100 * 3 + 1234
+    wave = (rng.standard_normal((2, N)) * 0.2).astype(np.float32)
+    # stft / istft
+    x = torch.from_numpy(wave[:, :mp.chunk_size].copy())[None]
+    assert torch.equal(model.stft(x), mp.stft(x))
+    spec = mp.stft(x)
+    assert torch.allclose(model.istft(spec), mp.istft(spec), atol=0, rtol=0)
+    # full process_wave
+    ref_out = sess.process_wave(wave.copy(), 2)
+    got = om.process_wave(wave.copy(), mp, net, 2)
+    assert ref_out.shape == got.shape == wave.shape
+    assert np.abs(ref_out - got).max() < 1e-6
