@@ -44,7 +44,9 @@ __device__ __forceinline__ TgRow tg_row(const TgParams& p, int b, int h, int w) 
   r.valid = (h < p.OH) && (w < p.OW) && (b < p.OB) && (mh >= 0) && (mh < p.o_fh) && (mw >= 0) &&
             (mw < p.o_fw);
   r.o_off = (long long)b * p.o_sb + (long long)mh * p.o_sh + (long long)mw * p.o_sw;
-  r.r_off = (long long)b * p.r_sb + (long long)h * p.r_sh + (long long)w * p.r_sw;
+  // residual #1 is addressed by the GEMM pixel, or by the mapped output pixel when res_op bit1 is set
+  if (p.res_op & 2) r.r_off = (long long)b * p.r_sb + (long long)mh * p.r_sh + (long long)mw * p.r_sw;
+  else r.r_off = (long long)b * p.r_sb + (long long)h * p.r_sh + (long long)w * p.r_sw;
   r.brow = h * p.OW + w;
   return r;
 }
@@ -54,7 +56,7 @@ __device__ __forceinline__ float tg_epi1(const TgParams& p, const TgRow& r, int 
   if (p.bias) v += p.bias_per_row ? __ldg(p.bias + r.brow) : __ldg(p.bias + n);
   v = apply_act(v, p.act_pre, p.act_pre_p);
   if (p.row_scale) v *= __ldg(p.row_scale + r.brow);
-  if (p.res) { const float rr = p.res[r.r_off + n]; v = p.res_op ? v * rr : v + rr; }
+  if (p.res) { const float rr = p.res[r.r_off + n]; v = (p.res_op & 1) ? v * rr : v + rr; }
   v *= p.scale;
   if (p.res2) v += p.res2[r.o_off + n];
   v = apply_act(v, p.act_post, p.act_post_p);
@@ -94,7 +96,7 @@ __device__ __forceinline__ void tg_store4(const TgParams& p, const TgRow& r, int
     }
     if (p.res) {
       float4 rr = *reinterpret_cast<const float4*>(p.res + r.r_off + n);
-      if (p.res_op) { v[0] *= rr.x; v[1] *= rr.y; v[2] *= rr.z; v[3] *= rr.w; }
+      if (p.res_op & 1) { v[0] *= rr.x; v[1] *= rr.y; v[2] *= rr.z; v[3] *= rr.w; }
       else { v[0] += rr.x; v[1] += rr.y; v[2] += rr.z; v[3] += rr.w; }
     }
 #pragma unroll

@@ -122,6 +122,7 @@ class Epi:
     row_scale: Optional[torch.Tensor] = None   # [OH*OW] per-output-row multiplier applied after act_pre
     res: Optional[torch.Tensor] = None     # channels-last tensor over the output pixel space
     res_mul: bool = False                  # v *= res instead of v += res
+    res_mapped: bool = False               # address res by the mapped output pixel (conv-transpose phases)
     scale: float = 1.0
     res2: Optional[torch.Tensor] = None    # same addressing as out
     act_post: int = ACT_NONE
@@ -193,7 +194,7 @@ class TapGemm:
                 st.insert(0, 0)
             p.r_sb, p.r_sh, p.r_sw = int(st[0]), int(st[1]), int(st[2])
             p.res = r.data_ptr()
-            p.res_op = 1 if epi.res_mul else 0
+            p.res_op = (1 if epi.res_mul else 0) | (2 if epi.res_mapped else 0)
             self._keep.append(r)
         p.scale = float(epi.scale)
         if epi.res2 is not None:

@@ -80,7 +80,8 @@ typedef struct b200vc_tapgemm_params {
   float act_pre_p;
   const float* row_scale; /* optional: v *= row_scale[h*OW + w] after act_pre (per-output-row scale)   */
   const float* res;
-  int32_t res_op;       /* 0: v += res ; 1: v *= res (MDX-Net multiplicative skip) */
+  int32_t res_op;       /* bit0: v *= res instead of v += res (MDX-Net multiplicative skip); bit1: address res by the
+                           mapped output pixel (h*osh+ooh, w*osw+oow) instead of the GEMM pixel */
   float scale;
   const float* res2;
   int32_t act_post;

@@ -87,7 +87,10 @@ def emulate(op) -> None:
         while len(st) < 4:
             st.insert(0, 0)
         rf = _flat(r).double()
-        ridx = r.storage_offset() + bb * st[0] + hh * st[1] + ww * st[2]
+        if epi.res_mapped:
+            ridx = r.storage_offset() + bb * st[0] + (hh * out.osh + out.ooh).clamp(0, out.fh - 1) * st[1] + (ww * out.osw + out.oow).clamp(0, out.fw - 1) * st[2]
+        else:
+            ridx = r.storage_offset() + bb * st[0] + hh * st[1] + ww * st[2]
         rv = rf[ridx[:, None] + n_idx[None, :]]
         v = v * rv if epi.res_mul else v + rv
     v = v * epi.scale
