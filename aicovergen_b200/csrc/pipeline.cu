@@ -161,6 +161,48 @@ __global__ void boxsum_f64_kernel(const double* __restrict__ x, double* __restri
   out[i] = s;
 }
 
+
+// Mono down-mix + band-limited resampling (Hann-windowed sinc, `zc` zero crossings each side), rate_in -> rate_out.
+// Stand-in for the ffmpeg "-ac 1 -ar 16000" decode at my_utils.py:13-17 (ingest is SURVEY.md 8(f) rank 2).
+__global__ void resample_sinc_mono_kernel(const float* __restrict__ x, long long n_in, int channels,
+                                          float* __restrict__ out, long long n_out, double ratio /*in/out*/, int zc) {
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= n_out) return;
+  const double scale = ratio > 1.0 ? 1.0 / ratio : 1.0;        // cutoff relative to the input Nyquist
+  const double center = (double)m * ratio;
+  const double halfw = (double)zc / scale;
+  long long k0 = (long long)ceil(center - halfw), k1 = (long long)floor(center + halfw);
+  float acc = 0.f;
+  for (long long k = k0; k <= k1; ++k) {
+    if (k < 0 || k >= n_in) continue;
+    const float d = (float)((double)k - center);
+    const float a = d * (float)scale;
+    const float sinc = fabsf(a) < 1e-6f ? 1.f : sinf(3.14159265358979f * a) / (3.14159265358979f * a);
+    const float win = 0.5f + 0.5f * cosf(3.14159265358979f * d / (float)halfw);
+    float v = 0.f;
+    for (int c = 0; c < channels; ++c) v += x[(long long)c * n_in + k];
+    acc += (v / channels) * sinc * win * (float)scale;
+  }
+  out[m] = acc;
+}
+
+// out[ch,n] = ga * lerp(a_mono, n * ra) + gb * b[ch,n] + gc * c[ch,n]  — gain-and-sum stand-in for the pydub overlay
+// at main.py:229-233 (a = converted vocals at its own rate, b = backup vocals, c = instrumental)
+__global__ void mix3_kernel(const float* __restrict__ a, long long n_a, double ra, const float* __restrict__ b,
+                            const float* __restrict__ c, float* __restrict__ out, long long n, float ga, float gb,
+                            float gc) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= 2 * n) return;
+  const long long i = e % n;
+  const double pos = (double)i * ra;
+  const long long i0 = (long long)pos;
+  const float fr = (float)(pos - (double)i0);
+  float av = 0.f;
+  if (i0 + 1 < n_a) av = a[i0] * (1.f - fr) + a[i0 + 1] * fr;
+  else if (i0 < n_a) av = a[i0];
+  out[e] = ga * av + gb * b[e] + gc * c[e];
+}
+
 }  // namespace
 }  // namespace b200vc
 
@@ -202,6 +244,25 @@ int b200vc_upsample2_protect(const float* feats, const float* feats0, const floa
 int b200vc_boxsum_f64(const double* x, double* out, int64_t n, int window, void* stream) {
   B200VC_REQUIRE(x && out && n > 0 && window > 0, "boxsum_f64: bad args");
   boxsum_f64_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, out, n, window);
+  count_launch();
+  B200VC_LAUNCH_CHECK();
+  return kOk;
+}
+
+int b200vc_resample_sinc_mono(const float* x, int64_t n_in, int channels, float* out, int64_t n_out, double ratio,
+                              int zero_crossings, void* stream) {
+  B200VC_REQUIRE(x && out && n_in > 0 && n_out > 0 && channels > 0 && ratio > 0, "resample_sinc_mono: bad args");
+  resample_sinc_mono_kernel<<<blocks_for(n_out, 256), 256, 0, (cudaStream_t)stream>>>(x, n_in, channels, out, n_out, ratio,
+                                                                                    zero_crossings);
+  count_launch();
+  B200VC_LAUNCH_CHECK();
+  return kOk;
+}
+
+int b200vc_mix3(const float* a_mono, int64_t n_a, double ratio_a, const float* b, const float* c, float* out, int64_t n,
+                float ga, float gb, float gc, void* stream) {
+  B200VC_REQUIRE(a_mono && b && c && out && n > 0 && n_a > 0, "mix3: bad args");
+  mix3_kernel<<<blocks_for(2 * n, 256), 256, 0, (cudaStream_t)stream>>>(a_mono, n_a, ratio_a, b, c, out, n, ga, gb, gc);
   count_launch();
   B200VC_LAUNCH_CHECK();
   return kOk;

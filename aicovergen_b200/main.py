@@ -1,0 +1,294 @@
+"""Host mirror of the reference orchestrator (src/main.py): `song_cover_pipeline` with the reference's 21-argument
+signature, plus `CoverEngine`, the array-level form of the same stage graph that keeps every intermediate stem in
+HBM (the reference passes WAV files between stages, main.py:166-203).
+
+Stage graph (main.py:166-190, 193-203, 229-233):
+    song --MDX(Voc_FT, denoise)--> vocals, instrumental
+    vocals --MDX(KARA_2, denoise)--> backup vocals (main stem), main vocals (inverse stem)
+    main vocals --MDX(Reverb_HQ, denoise, exclude_main)--> de-reverbed main vocals (inverse stem)
+    de-reverbed vocals --mono 16 kHz--> RVC VC.pipeline --> converted vocals @ tgt_sr
+    converted + backup + instrumental --gains -4/-6/-7 dB, overlay--> cover
+
+Out of scope here: YouTube download, ffmpeg/sox, pedalboard effects (HPF +
+compressor + reverb) and pydub's mp3 export — the effects stage is a pass-through and the mix is a plain
+gain-and-sum (documented substitution, also used by the CPU arm of bench.py).
+"""
+from __future__ import annotations
+
+import gc
+import hashlib
+import json
+import os
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+from scipy.io import wavfile
+
+from . import ops
+from .mdx import MDX, MDXModel, run_mdx, run_mdx_arrays, run_mdx_device, _read_wav_44k, _write_wav_pcm16
+from .rvc import Config, get_vc, load_hubert, rvc_infer
+
+BASE_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+mdxnet_models_dir = os.path.join(BASE_DIR, "mdxnet_models")
+rvc_models_dir = os.path.join(BASE_DIR, "rvc_models")
+output_dir = os.path.join(BASE_DIR, "song_output")
+
+# the three separation models of preprocess_song with their model_data.json parameter sets
+# (mdxnet_models/model_data.json: Voc_FT-class :282-288, KARA_2-class :212-218, Reverb_HQ-class :247-253)
+MDX_STAGES = (
+    dict(name="UVR-MDX-NET-Voc_FT", dim_f=3072, dim_t=256, n_fft=7680, stem="Vocals", compensate=1.021),
+    dict(name="UVR_MDXNET_KARA_2", dim_f=2048, dim_t=256, n_fft=5120, stem="Instrumental", compensate=1.035),
+    dict(name="Reverb_HQ_By_FoxJoy", dim_f=3072, dim_t=512, n_fft=6144, stem="Other", compensate=1.035),
+)
+
+
+def db_gain(db: float) -> float:
+    return float(10.0 ** (db / 20.0))
+
+
+class CoverEngine:
+    """All models of one cover job resident on one GPU; `cover(song)` runs the whole stage graph on device arrays."""
+
+    def __init__(self, mdx_weights, hubert_sd, rmvpe_sd, rvc_cpt, index=None, device="cuda:0", mdx_stages=MDX_STAGES):
+        from .hubert import HubertB200
+        from .rmvpe import RMVPEB200
+        from .synth import SynthesizerB200
+        from .vc_infer_pipeline import VC
+
+        self.device = device
+        self.stages = mdx_stages
+        self.mdx = []
+        for st, w in zip(mdx_stages, mdx_weights):
+            model = MDXModel(device, st["dim_f"], st["dim_t"], st["n_fft"], stem_name=st["stem"], compensation=st["compensate"])
+            self.mdx.append(MDX(w, model, int(str(device).split(":")[-1])))
+        self.config = Config(device, True)
+        self.hubert = HubertB200(hubert_sd, device)
+        self.net_g = SynthesizerB200(rvc_cpt, device)
+        self.cpt = rvc_cpt
+        self.tgt_sr = rvc_cpt["config"][-1]
+        self.vc = VC(self.tgt_sr, self.config)
+        self.vc.model_rmvpe = RMVPEB200(rmvpe_sd, device=device)
+        self.index_path = index or ""
+
+    @torch.no_grad()
+    def separate(self, song_dev: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """The three MDX passes of preprocess_song on a device tensor [2,N] float32 @44.1k -> stems (device tensors)."""
+        vocals, instrumental = run_mdx_device(self.mdx[0], song_dev, denoise=True)
+        backup, main_vocals = run_mdx_device(self.mdx[1], vocals, denoise=True)
+        _, dereverb = run_mdx_device(self.mdx[2], main_vocals, denoise=True)
+        return dict(vocals=vocals, instrumental=instrumental, backup=backup, main=main_vocals, dereverb=dereverb)
+
+    @torch.no_grad()
+    def convert(self, vocals_44k: torch.Tensor, pitch_change=0, index_rate=0.5, filter_radius=3, rms_mix_rate=0.25,
+                protect=0.33, f0_method="rmvpe") -> np.ndarray:
+        """load_audio (mono 16 kHz, on device) + VC.pipeline. Returns int16 @ tgt_sr (host, like the reference)."""
+        n16 = int(vocals_44k.shape[1] * 16000 // 44100)
+        mono = torch.empty(n16, device=self.device)
+        ops.resample_sinc_mono(vocals_44k.contiguous(), mono, 44100, 16000)
+        audio = mono.cpu().numpy()
+        times = [0, 0, 0]
+        return self.vc.pipeline(self.hubert, self.net_g, 0, audio, "array", times, pitch_change, f0_method, self.index_path,
+                                index_rate, self.cpt.get("f0", 1), filter_radius, self.tgt_sr, 0, rms_mix_rate,
+                                self.cpt.get("version", "v1"), protect, 128)
+
+    @torch.no_grad()
+    def mix(self, ai_vocals_i16: np.ndarray, backup: torch.Tensor, instrumental: torch.Tensor, main_gain=0, backup_gain=0,
+            inst_gain=0) -> torch.Tensor:
+        a = torch.from_numpy(ai_vocals_i16.astype(np.float32) / 32768.0).to(self.device)
+        out = torch.empty_like(backup)
+        ops.mix3(a, self.tgt_sr, backup.contiguous(), instrumental.contiguous(), out, 44100, db_gain(-4 + main_gain),
+                 db_gain(-6 + backup_gain), db_gain(-7 + inst_gain))
+        return out
+
+    def cover_device(self, song_dev: torch.Tensor, **kw) -> torch.Tensor:
+        """song already in HBM -> cover in HBM."""
+        stems = self.separate(song_dev)
+        ai = self.convert(stems["dereverb"], **kw)
+        return self.mix(ai, stems["backup"], stems["instrumental"])
+
+    def cover(self, song: np.ndarray, **kw) -> np.ndarray:
+        """Host array in, host array out (H2D of the song and D2H of the cover included)."""
+        dev = torch.from_numpy(np.ascontiguousarray(song, dtype=np.float32)).to(self.device, non_blocking=True)
+        return self.cover_device(dev, **kw).cpu().numpy()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# file-level mirror of the reference functions
+# ---------------------------------------------------------------------------------------------------------------
+def raise_exception(error_msg, is_webui):
+    raise Exception(error_msg)      # gr.Error in the WebUI build of the reference (main.py:81-85)
+
+
+def display_progress(message, percent, is_webui, progress=None):
+    if is_webui and progress is not None:
+        progress(percent, desc=message)
+    else:
+        print(message)
+
+
+def get_hash(filepath):
+    h = hashlib.blake2b()
+    with open(filepath, "rb") as f:
+        while chunk := f.read(8192):
+            h.update(chunk)
+    return h.hexdigest()[:11]
+
+
+def get_rvc_model(voice_model, is_webui):
+    model_dir = os.path.join(rvc_models_dir, voice_model)
+    pth = idx = None
+    for file in os.listdir(model_dir):
+        ext = os.path.splitext(file)[1]
+        if ext == ".pth":
+            pth = file
+        if ext in (".index", ".npz"):
+            idx = file
+    if pth is None:
+        raise_exception(f"No model file exists in {model_dir}.", is_webui)
+    return os.path.join(model_dir, pth), os.path.join(model_dir, idx) if idx else ""
+
+
+def get_audio_paths(song_dir):
+    orig = inst = dereverb = backup = None
+    for file in os.listdir(song_dir):
+        if file.endswith("_Instrumental.wav"):
+            inst = os.path.join(song_dir, file)
+            orig = inst.replace("_Instrumental", "")
+        elif file.endswith("_Vocals_Main_DeReverb.wav"):
+            dereverb = os.path.join(song_dir, file)
+        elif file.endswith("_Vocals_Backup.wav"):
+            backup = os.path.join(song_dir, file)
+    return orig, inst, dereverb, backup
+
+
+def convert_to_stereo(audio_path):
+    """main.py:125-135 (ffmpeg -ac 2): mono WAVs are duplicated to two channels."""
+    sr, data = wavfile.read(audio_path)
+    if data.ndim == 1:
+        stereo_path = f"{os.path.splitext(audio_path)[0]}_stereo.wav"
+        wavfile.write(stereo_path, sr, np.stack([data, data], 1))
+        return stereo_path
+    return audio_path
+
+
+def _mdx_model_path(name):
+    for ext in (".onnx", ".pt", ".pth"):
+        p = os.path.join(mdxnet_models_dir, name + ext)
+        if os.path.exists(p):
+            return p
+    return os.path.join(mdxnet_models_dir, name + ".onnx")
+
+
+def preprocess_song(song_input, mdx_model_params, song_id, is_webui, input_type, progress=None):
+    if input_type == "yt":
+        raise_exception("YouTube download is out of scope for the B200 build (no network stack); pass a local file.", is_webui)
+    orig_song_path, keep_orig = song_input, True
+    song_output_dir = os.path.join(output_dir, song_id)
+    orig_song_path = convert_to_stereo(orig_song_path)
+    display_progress("[~] Separating Vocals from Instrumental...", 0.1, is_webui, progress)
+    vocals_path, instrumentals_path = run_mdx(mdx_model_params, song_output_dir, _mdx_model_path("UVR-MDX-NET-Voc_FT"),
+                                              orig_song_path, denoise=True, keep_orig=keep_orig)
+    display_progress("[~] Separating Main Vocals from Backup Vocals...", 0.2, is_webui, progress)
+    backup_vocals_path, main_vocals_path = run_mdx(mdx_model_params, song_output_dir, _mdx_model_path("UVR_MDXNET_KARA_2"),
+                                                   vocals_path, suffix="Backup", invert_suffix="Main", denoise=True)
+    display_progress("[~] Applying DeReverb to Vocals...", 0.3, is_webui, progress)
+    _, main_vocals_dereverb_path = run_mdx(mdx_model_params, song_output_dir, _mdx_model_path("Reverb_HQ_By_FoxJoy"),
+                                           main_vocals_path, invert_suffix="DeReverb", exclude_main=True, denoise=True)
+    return orig_song_path, vocals_path, instrumentals_path, main_vocals_path, backup_vocals_path, main_vocals_dereverb_path
+
+
+def voice_change(voice_model, vocals_path, output_path, pitch_change, f0_method, index_rate, filter_radius, rms_mix_rate,
+                 protect, crepe_hop_length, is_webui):
+    rvc_model_path, rvc_index_path = get_rvc_model(voice_model, is_webui)
+    device = "cuda:0"
+    config = Config(device, True)
+    hubert_model = load_hubert(device, config.is_half, os.path.join(rvc_models_dir, "hubert_base.pt"))
+    cpt, version, net_g, tgt_sr, vc = get_vc(device, config.is_half, config, rvc_model_path)
+    rvc_infer(rvc_index_path, index_rate, vocals_path, output_path, pitch_change, f0_method, cpt, version, net_g,
+              filter_radius, tgt_sr, rms_mix_rate, protect, crepe_hop_length, vc, hubert_model)
+    del hubert_model, cpt
+    gc.collect()
+
+
+def add_audio_effects(audio_path, reverb_rm_size, reverb_wet, reverb_dry, reverb_damping):
+    """main.py:206-226 applies pedalboard HPF + compressor + reverb; pass-through here."""
+    output_path = f"{os.path.splitext(audio_path)[0]}_mixed.wav"
+    sr, data = wavfile.read(audio_path)
+    wavfile.write(output_path, sr, data)
+    return output_path
+
+
+def combine_audio(audio_paths, output_path, main_gain, backup_gain, inst_gain, output_format):
+    """Gain-and-sum stand-in for the pydub overlay/export (main.py:229-233); always writes 16-bit WAV."""
+    sr_a, a = wavfile.read(audio_paths[0])
+    sr_b, b = wavfile.read(audio_paths[1])
+    sr_c, c = wavfile.read(audio_paths[2])
+    dev = "cuda:0"
+    to_f = lambda x: x.astype(np.float32) / 32768.0 if x.dtype == np.int16 else x.astype(np.float32)
+    a = to_f(a if a.ndim == 1 else a.mean(1))
+    b, c = to_f(b), to_f(c)
+    n = min(len(b), len(c))
+    bt = torch.from_numpy(np.ascontiguousarray(b[:n].T)).to(dev)
+    ct = torch.from_numpy(np.ascontiguousarray(c[:n].T)).to(dev)
+    out = torch.empty_like(bt)
+    ops.mix3(torch.from_numpy(a).to(dev), sr_a, bt, ct, out, sr_b, db_gain(-4 + main_gain), db_gain(-6 + backup_gain),
+             db_gain(-7 + inst_gain))
+    _write_wav_pcm16(output_path, out.cpu().numpy().T, sr_b)
+
+
+def song_cover_pipeline(song_input, voice_model, pitch_change, keep_files, is_webui=0, main_gain=0, backup_gain=0,
+                        inst_gain=0, index_rate=0.5, filter_radius=3, rms_mix_rate=0.25, f0_method="rmvpe",
+                        crepe_hop_length=128, protect=0.33, pitch_change_all=0, reverb_rm_size=0.15, reverb_wet=0.2,
+                        reverb_dry=0.8, reverb_damping=0.7, output_format="mp3", progress=None):
+    """Same positional contract as main.song_cover_pipeline (main.py:236-240); returns the cover's path."""
+    try:
+        if not song_input or not voice_model:
+            raise_exception("Ensure that the song input field and voice model field is filled.", is_webui)
+        display_progress("[~] Starting AI Cover Generation Pipeline...", 0, is_webui, progress)
+        with open(os.path.join(mdxnet_models_dir, "model_data.json")) as infile:
+            mdx_model_params = json.load(infile)
+        if str(song_input).startswith("https://"):
+            raise_exception("YouTube input is out of scope for the B200 build; pass a local file.", is_webui)
+        input_type = "local"
+        song_input = song_input.strip('"')
+        if not os.path.exists(song_input):
+            raise_exception(f"{song_input} does not exist.", is_webui)
+        song_id = get_hash(song_input)
+        song_dir = os.path.join(output_dir, song_id)
+        if not os.path.exists(song_dir):
+            os.makedirs(song_dir)
+            (orig_song_path, vocals_path, instrumentals_path, main_vocals_path, backup_vocals_path,
+             main_vocals_dereverb_path) = preprocess_song(song_input, mdx_model_params, song_id, is_webui, input_type, progress)
+        else:
+            vocals_path, main_vocals_path = None, None
+            paths = get_audio_paths(song_dir)
+            if any(p is None for p in paths) or keep_files:
+                (orig_song_path, vocals_path, instrumentals_path, main_vocals_path, backup_vocals_path,
+                 main_vocals_dereverb_path) = preprocess_song(song_input, mdx_model_params, song_id, is_webui, input_type, progress)
+            else:
+                orig_song_path, instrumentals_path, main_vocals_dereverb_path, backup_vocals_path = paths
+        pitch_change = pitch_change * 12 + pitch_change_all
+        stem = os.path.splitext(os.path.basename(orig_song_path))[0]
+        ai_vocals_path = os.path.join(song_dir, f"{stem}_{voice_model}_p{pitch_change}_i{index_rate}_fr{filter_radius}_rms{rms_mix_rate}_pro{protect}_{f0_method}.wav")
+        if output_format != "wav":
+            display_progress("[!] mp3 export needs ffmpeg; writing WAV instead.", 0.0, is_webui, progress)
+        ai_cover_path = os.path.join(song_dir, f"{stem} ({voice_model} Ver).wav")
+        if not os.path.exists(ai_vocals_path):
+            display_progress("[~] Converting voice using RVC...", 0.5, is_webui, progress)
+            voice_change(voice_model, main_vocals_dereverb_path, ai_vocals_path, pitch_change, f0_method, index_rate,
+                         filter_radius, rms_mix_rate, protect, crepe_hop_length, is_webui)
+        display_progress("[~] Applying audio effects to Vocals...", 0.8, is_webui, progress)
+        ai_vocals_mixed_path = add_audio_effects(ai_vocals_path, reverb_rm_size, reverb_wet, reverb_dry, reverb_damping)
+        if pitch_change_all != 0:
+            raise_exception("pitch_change_all needs sox (out of scope for the B200 build).", is_webui)
+        display_progress("[~] Combining AI Vocals and Instrumentals...", 0.9, is_webui, progress)
+        combine_audio([ai_vocals_mixed_path, backup_vocals_path, instrumentals_path], ai_cover_path, main_gain, backup_gain,
+                      inst_gain, output_format)
+        if not keep_files:
+            for file in (vocals_path, main_vocals_path, ai_vocals_mixed_path):
+                if file and os.path.exists(file):
+                    os.remove(file)
+        return ai_cover_path
+    except Exception as e:
+        raise_exception(str(e), is_webui)

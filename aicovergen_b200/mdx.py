@@ -228,13 +228,13 @@ class _NetPlan:
             ot = buf(3, B, Hh, c, Ww)
             add(tg.linear(h, W[key + ".w2"], ot.view(rows, Ww), Epi(bias=b2, bias_per_row=True, act_pre=tg.ACT_RELU), be,
                           name=f"{key}.tdf2"))
-            add(lambda ot=ot, t=t, out=out: ops.nhcw_to_nhwc_add(ot, t, out, False))
+            add(lambda ot=ot, t=t, out=out: ops.nhcw_to_nhwc_add(ot, t, out, R))
 
         # ---- first conv (1x1, 4 -> g) reading [B, ch, T, F, ri]: one tap per stereo channel, K = (re, im)
         x = torch.empty(B, T, F, g, **f32)
         a = tg.View(self.spec_in, (2, F, T, B, 2), (1, 2, 2 * F, 2 * T * 2 * F, T * 2 * F))
         add(tg.TapGemm(a, tg.Weights(W["first.w"], 2, g, 2, 2 * g), [(0, 0, 0, 0, 0), (0, 0, 0, 1, 1)], (F, T, B),
-                       tg.out_of(x), Epi(bias=W["first.b"], act_pre=tg.ACT_RELU), tg.BACKEND_SIMT, name="first_conv"))
+                       tg.out_of(x), Epi(bias=W["first.b"], act_pre=tg.ACT_RELU, round_out=R), tg.BACKEND_SIMT, name="first_conv"))
         Hh, Ww, c = T, F, g
         skips = []
         for i in range(n):
@@ -242,7 +242,7 @@ class _NetPlan:
             tfc_tdf(x, f"enc{i}", Hh, Ww, c, y)
             skips.append((y, Hh, Ww, c))
             x = torch.empty(B, Hh // 2, Ww // 2, c + g, **f32)
-            add(tg.conv2d_k2s2(y, W[f"ds{i}.w"], x, Epi(bias=W[f"ds{i}.b"], act_pre=tg.ACT_RELU), be, name=f"ds{i}"))
+            add(tg.conv2d_k2s2(y, W[f"ds{i}.w"], x, Epi(bias=W[f"ds{i}.b"], act_pre=tg.ACT_RELU, round_out=R), be, name=f"ds{i}"))
             Hh, Ww, c = Hh // 2, Ww // 2, c + g
         y = torch.empty(B, Hh, Ww, c, **f32)
         tfc_tdf(x, "mid", Hh, Ww, c, y)
@@ -251,7 +251,7 @@ class _NetPlan:
             sk, Hs, Ws, cs = skips[-1 - i]
             u = torch.empty(B, Hs, Ws, cs, **f32)
             for op in tg.conv_transpose2d_s2(x, W[f"us{i}.w"], u, 2, 0,
-                                             Epi(bias=W[f"us{i}.b"], act_pre=tg.ACT_RELU, res=sk, res_mul=True, res_mapped=True),
+                                             Epi(bias=W[f"us{i}.b"], act_pre=tg.ACT_RELU, res=sk, res_mul=True, res_mapped=True, round_out=R),
                                              be, name=f"us{i}"):
                 add(op)
             Hh, Ww, c = Hs, Ws, cs
@@ -434,13 +434,12 @@ def _write_wav_pcm16(path, data_T, sr):
     wavfile.write(path, sr, np.rint(x * 32767.0).astype(np.int16))
 
 
-def run_mdx_arrays(mdx_sess: MDX, wave: np.ndarray, denoise=False, m_threads=2):
-    """Device version of the arithmetic in run_mdx (mdx.py:257-280): returns (main [2,N], inverse [2,N]) float32."""
-    dev = mdx_sess.device
+def run_mdx_device(mdx_sess: MDX, wave_dev: torch.Tensor, denoise=False, m_threads=2):
+    """The arithmetic of run_mdx (mdx.py:257-280) on a device tensor [2,N]: returns (main, inverse) device tensors.
+    NB the reference normalises `wave` in place by its peak and reuses the normalised array for the inverse stem."""
     model = mdx_sess.model
-    peak = max(np.max(wave), abs(np.min(wave)))
-    w = torch.from_numpy(np.ascontiguousarray(wave, dtype=np.float32)).to(dev)
-    w = (w / float(peak)).contiguous()              # the reference normalises in place and reuses it for the inverse stem
+    peak = float(torch.maximum(wave_dev.max(), wave_dev.min().abs()).item())       # max(np.max(w), abs(np.min(w)))
+    w = (wave_dev / peak).contiguous()
     proc = torch.zeros_like(w)
     if denoise:
         mdx_sess._process_device(w, proc, -1.0, -0.5, False, m_threads)      # -(P(-w)) * 0.5
@@ -449,6 +448,13 @@ def run_mdx_arrays(mdx_sess: MDX, wave: np.ndarray, denoise=False, m_threads=2):
         mdx_sess._process_device(w, proc, 1.0, 1.0, False, m_threads)
     inverse = torch.empty_like(w)
     ops.mdx_finalize(proc, w, inverse, peak, model.compensation)
+    return proc, inverse
+
+
+def run_mdx_arrays(mdx_sess: MDX, wave: np.ndarray, denoise=False, m_threads=2):
+    """Host-array wrapper of run_mdx_device: returns (main [2,N], inverse [2,N]) float32."""
+    w = torch.from_numpy(np.ascontiguousarray(wave, dtype=np.float32)).to(mdx_sess.device)
+    proc, inverse = run_mdx_device(mdx_sess, w, denoise, m_threads)
     return proc.cpu().numpy(), inverse.cpu().numpy()
 
 

@@ -261,7 +261,7 @@ def make_hubert_state_dict(seed: int = 777, layers: int = 12, dim: int = 768, ff
 # IVF-Flat index contents (faiss `added_IVF{nlist}_Flat_nprobe_1_*.index`, vc_infer_pipeline.py:505-507)
 # ---------------------------------------------------------------------------
 def make_ivf_index_data(base_feats: torch.Tensor, n_total: int = 87243, nlist: int = 2237, seed: int = 99,
-                        jitter: float = 0.05):
+                        jitter: float = 0.05, lloyd: bool = True):
     """Database = rows of `base_feats` (HuBERT features of a seeded clip) cycled to n_total + N(0, jitter);
     centroids = one k-means iteration from a seeded sample (SURVEY.md §8(d) cfg 3). Returns (centroids, vectors)."""
     g = torch.Generator().manual_seed(seed)
@@ -271,6 +271,8 @@ def make_ivf_index_data(base_feats: torch.Tensor, n_total: int = 87243, nlist: i
     vecs += torch.randn(vecs.shape, generator=g) * jitter
     perm = torch.randperm(n_total, generator=g)[:nlist]
     cent = vecs[perm].clone()
+    if not lloyd:
+        return cent.numpy(), vecs.numpy()
     # one Lloyd iteration
     c2 = (cent.double() ** 2).sum(1)
     assign = torch.empty(n_total, dtype=torch.long)

@@ -232,6 +232,17 @@ int b200vc_mdx_ola_store(const float* frames, const float* env, const int64_t* d
 int b200vc_mdx_finalize(float* proc, const float* wave_norm, float* inverse, int64_t n, float peak,
                         float compensation, void* stream);
 
+/* ---- ingest / mix stand-ins (SURVEY.md 8(f) "next" rows; not parity-claimed against ffmpeg/pydub) ---- */
+
+/* out[m] = band-limited (Hann-windowed sinc) resample of the channel mean of x[channels, n_in]; ratio = rate_in/rate_out.
+ * Stands where my_utils.load_audio's ffmpeg "-ac 1 -ar 16000" stands (my_utils.py:13-17). */
+int b200vc_resample_sinc_mono(const float* x, int64_t n_in, int channels, float* out, int64_t n_out, double ratio,
+                              int zero_crossings, void* stream);
+
+/* out[2,n] = ga*lerp(a_mono at ratio_a) + gb*b + gc*c : gain-and-sum stand-in for main.combine_audio (main.py:229-233) */
+int b200vc_mix3(const float* a_mono, int64_t n_a, double ratio_a, const float* b, const float* c, float* out, int64_t n,
+                float ga, float gb, float gc, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
