@@ -270,6 +270,53 @@ class _NetPlan:
             st()
 
 
+def shard_range(n_items: int, rank: int, world: int):
+    """Contiguous share of `n_items` chunk inferences for `rank` of `world` (remainder to the low ranks)."""
+    base, rem = divmod(n_items, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def segment_bounds(n, chunk_size, margin_size):
+    """Start/end of the overlapping segments MDX.segment(combine=False) cuts (mdx.py:119-141)."""
+    if chunk_size <= 0 or chunk_size > n:
+        chunk_size = n
+    if margin_size > chunk_size:
+        margin_size = chunk_size
+    bounds = []
+    for count, skip in enumerate(range(0, n, chunk_size)):
+        margin = 0 if count == 0 else margin_size
+        end = min(skip + chunk_size + margin_size, n)
+        bounds.append((skip - margin, end))
+        if end == n:
+            break
+    return bounds
+
+
+def chunk_descriptors(n, n_fft, chunk_size, mt_threads, margin=44100):
+    """Flattens segment + pad_wave + trim + [:-pad] + segment(combine) (mdx.py:119-171, 195-197, 107-117) into one
+    record per chunk inference: (src_start, lo, hi, dst_start, keep_lo, keep_hi), all in song sample coordinates.
+    Chunk b reads song[src_start + s] for s in [0, chunk) where the index is inside [lo, hi) (zeros elsewhere) and its
+    kept output sample k in [0, gen) lands at dst_start + k when that is inside [keep_lo, keep_hi)."""
+    trim = n_fft // 2
+    gen = chunk_size - 2 * trim
+    bounds = segment_bounds(n, n // mt_threads, margin)
+    src, lo, hi, dst, klo, khi = [], [], [], [], [], []
+    for k, (a, b) in enumerate(bounds):
+        nh = b - a
+        pad = gen - nh % gen
+        keep_lo = a + (0 if k == 0 else margin)                     # segment(combine=True) uses the default margin
+        keep_hi = b - (0 if (k == len(bounds) - 1 or margin == 0) else margin)
+        for i in range((nh + pad) // gen):
+            src.append(a + i * gen - trim)
+            lo.append(a)
+            hi.append(b)
+            dst.append(a + i * gen)
+            klo.append(keep_lo)
+            khi.append(keep_hi)
+    return [np.asarray(v, dtype=np.int64) for v in (src, lo, hi, dst, klo, khi)]
+
+
 class MDX:
     DEFAULT_SR = 44100
     DEFAULT_CHUNK_SIZE = 0 * DEFAULT_SR
@@ -319,49 +366,25 @@ class MDX:
 
     @staticmethod
     def _segment_bounds(n, chunk_size, margin_size):
-        if chunk_size <= 0 or chunk_size > n:
-            chunk_size = n
-        if margin_size > chunk_size:
-            margin_size = chunk_size
-        bounds = []
-        for count, skip in enumerate(range(0, n, chunk_size)):
-            margin = 0 if count == 0 else margin_size
-            end = min(skip + chunk_size + margin_size, n)
-            bounds.append((skip - margin, end))
-            if end == n:
-                break
-        return bounds
+        return segment_bounds(n, chunk_size, margin_size)
 
     def _descriptors(self, n, mt_threads):
-        """Per chunk: where its input comes from, which song range it may read, where its kept output lands."""
         m = self.model
-        trim = m.n_fft // 2
-        gen = m.chunk_size - 2 * trim
-        margin = self.DEFAULT_MARGIN_SIZE
-        bounds = self._segment_bounds(n, n // mt_threads, margin)
-        eff_margin = margin        # MDX.segment(combine=True) is called with the default margin (mdx.py:235)
-        src, lo, hi, dst, klo, khi = [], [], [], [], [], []
-        for k, (a, b) in enumerate(bounds):
-            nh = b - a
-            pad = gen - nh % gen
-            keep_lo = a + (0 if k == 0 else eff_margin)
-            keep_hi = b - (0 if (k == len(bounds) - 1 or eff_margin == 0) else eff_margin)
-            for i in range((nh + pad) // gen):
-                src.append(a + i * gen - trim)
-                lo.append(a)
-                hi.append(b)
-                dst.append(a + i * gen)
-                klo.append(keep_lo)
-                khi.append(keep_hi)
-        return [np.asarray(v, dtype=np.int64) for v in (src, lo, hi, dst, klo, khi)]
+        return chunk_descriptors(n, m.n_fft, m.chunk_size, mt_threads, self.DEFAULT_MARGIN_SIZE)
 
     def _process_device(self, wave_dev: torch.Tensor, out_dev: torch.Tensor, sign: float, coef: float, accumulate: bool,
-                        mt_threads: int):
-        """Run every chunk of `sign * wave` through STFT -> net -> iSTFT and add coef * result into out_dev."""
+                        mt_threads: int, shard=(0, 1)):
+        """Run this rank's share of the chunks of `sign * wave` through STFT -> net -> iSTFT and add coef * result into
+        out_dev.  With shard=(rank, world) the flattened chunk list is split into contiguous ranges (chunks are
+        independent, mdx.py:190-196); the caller sums the per-rank outputs (each sample is written by exactly one chunk)."""
         m, dev = self.model, self.device
         n = wave_dev.shape[1]
         src, lo, hi, dst, klo, khi = self._descriptors(n, mt_threads)
+        c_lo, c_hi = shard_range(len(src), shard[0], shard[1])
+        src, lo, hi, dst, klo, khi = (v[c_lo:c_hi] for v in (src, lo, hi, dst, klo, khi))
         nchunks = len(src)
+        if nchunks == 0:
+            return
         B = min(self.BATCH, nchunks)
         R = self.backend == tg.BACKEND_TC
         fwd, inv, env = m.dft(R)
@@ -434,18 +457,26 @@ def _write_wav_pcm16(path, data_T, sr):
     wavfile.write(path, sr, np.rint(x * 32767.0).astype(np.int16))
 
 
-def run_mdx_device(mdx_sess: MDX, wave_dev: torch.Tensor, denoise=False, m_threads=2):
+def run_mdx_device(mdx_sess: MDX, wave_dev: torch.Tensor, denoise=False, m_threads=2, group=None):
     """The arithmetic of run_mdx (mdx.py:257-280) on a device tensor [2,N]: returns (main, inverse) device tensors.
     NB the reference normalises `wave` in place by its peak and reuses the normalised array for the inverse stem."""
     model = mdx_sess.model
     peak = float(torch.maximum(wave_dev.max(), wave_dev.min().abs()).item())       # max(np.max(w), abs(np.min(w)))
     w = (wave_dev / peak).contiguous()
     proc = torch.zeros_like(w)
+    shard = (0, 1)
+    if group is not None:
+        import torch.distributed as dist
+        shard = (dist.get_rank(group), dist.get_world_size(group))
     if denoise:
-        mdx_sess._process_device(w, proc, -1.0, -0.5, False, m_threads)      # -(P(-w)) * 0.5
-        mdx_sess._process_device(w, proc, 1.0, 0.5, True, m_threads)         # + P(w) * 0.5
+        mdx_sess._process_device(w, proc, -1.0, -0.5, False, m_threads, shard)      # -(P(-w)) * 0.5
+        mdx_sess._process_device(w, proc, 1.0, 0.5, True, m_threads, shard)         # + P(w) * 0.5
     else:
-        mdx_sess._process_device(w, proc, 1.0, 1.0, False, m_threads)
+        mdx_sess._process_device(w, proc, 1.0, 1.0, False, m_threads, shard)
+    if shard[1] > 1:
+        # the only collective on the path: every rank holds a disjoint set of output samples (zeros elsewhere),
+        # so one NCCL sum over NVLink reassembles the stem on all ranks
+        dist.all_reduce(proc, group=group)
     inverse = torch.empty_like(w)
     ops.mdx_finalize(proc, w, inverse, peak, model.compensation)
     return proc, inverse

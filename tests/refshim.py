@@ -49,17 +49,4 @@ def ref_vc(tgt_sr, x_pad=3, x_query=10, x_center=60, x_max=65):
     return v, v.VC(tgt_sr, cfg)
 
 
-def vocal_like(seconds, sr=16000, seed=7):
-    """SURVEY.md §8(d) cfg-3 style synthetic vocal: harmonic stack with vibrato, unvoiced bursts, noise floor."""
-    rng = np.random.default_rng(seed)
-    n = int(seconds * sr)
-    t = np.arange(n) / sr
-    f0 = 220.0 * 2 ** (0.5 * np.sin(2 * np.pi * 0.2 * t)) * 2 ** (30 / 1200 * np.sin(2 * np.pi * 5.5 * t))
-    phase = 2 * np.pi * np.cumsum(f0) / sr
-    x = sum(np.sin(k * phase) / k for k in range(1, 9))
-    burst = ((t % 3.0) > 2.6)
-    x = np.where(burst, rng.standard_normal(n) * 0.7, x)
-    x = x + 0.1 * rng.standard_normal(n)
-    # a short near-silent gap every ~1.7 s gives the cut-point search something to find
-    x = x * np.where((t % 1.7) > 1.62, 0.02, 1.0)
-    return (0.5 * x / np.abs(x).max()).astype(np.float32)
+from siggen import vocal_like  # noqa: E402,F401

@@ -1,0 +1,54 @@
+"""The C-ABI library builds for sm_100a, loads on a CPU-only box, and exports every symbol include/b200vc.h declares."""
+import ctypes
+import os
+import re
+
+from aicovergen_b200 import _ffi, build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    txt = open(os.path.join(ROOT, "include", "b200vc.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200vc_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    lib_path = build.build()
+    assert lib_path.exists()
+    lib = ctypes.CDLL(str(lib_path))
+    names = _declared()
+    assert len(names) >= 25, names
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_ctypes_struct_mirror_matches_compiled_struct():
+    lib = _ffi.lib()          # raises on ABI size mismatch
+    assert lib.b200vc_version().startswith(b"b200vc")
+    assert lib.b200vc_sizeof_tapgemm_params() == ctypes.sizeof(_ffi.TapGemmParams)
+
+
+def test_error_reporting_without_gpu():
+    """Argument validation happens before any CUDA call, so it is testable here: bad descriptor -> rc<0 + message."""
+    lib = _ffi.lib()
+    p = _ffi.TapGemmParams()
+    rc = lib.b200vc_tapgemm(ctypes.byref(p), 0, None)
+    assert rc < 0
+    assert b"tapgemm" in lib.b200vc_last_error()
+
+
+def test_sass_contains_blackwell_tensor_and_tma_instructions():
+    """tcgen05.mma / TMA must survive to SASS (UTC*MMA, UTMALDG, LDTM) — /opt/skills/guides/B200_PROFILING.md."""
+    import shutil
+    import subprocess
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        import pytest
+        pytest.skip("cuobjdump not available")
+    obj = build.OUT_DIR / "tapgemm_tc.o"
+    sass = subprocess.run([cuobjdump, "-sass", str(obj)], capture_output=True, text=True).stdout
+    for mnem in ("UTCHMMA", "UTMALDG", "LDTM"):
+        assert mnem in sass, mnem

@@ -1,0 +1,76 @@
+"""Multi-GPU host logic on CPU: the MDX chunk list is partitioned across ranks with no overlap / no gap, and the
+per-rank partial outputs summed by the collective equal the single-rank result (gloo, world_size 2 and 3)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from aicovergen_b200.mdx import chunk_descriptors, shard_range
+
+
+def fake_process(n, n_fft, chunk, rank, world):
+    """Stand-in for STFT -> net -> iSTFT: each kept output sample gets the value f(song index); exactly the
+    addressing of b200vc_mdx_ola_store."""
+    src, lo, hi, dst, klo, khi = chunk_descriptors(n, n_fft, chunk, 2)
+    gen = chunk - n_fft
+    out = np.zeros(n, dtype=np.float64)
+    cnt = np.zeros(n, dtype=np.int64)
+    a, b = shard_range(len(src), rank, world)
+    for i in range(a, b):
+        k = np.arange(gen)
+        d = dst[i] + k
+        ok = (d >= klo[i]) & (d < khi[i]) & (d >= 0) & (d < n)
+        out[d[ok]] += np.sin(d[ok] * 0.001) + 2.0
+        cnt[d[ok]] += 1
+    return out, cnt
+
+
+def test_descriptors_cover_every_sample_exactly_once():
+    for n in (44100 * 7 + 13, 10584000, 253440 * 4, 100000):
+        for (n_fft, dim_t) in ((7680, 256), (5120, 256), (6144, 512)):
+            chunk = 1024 * (dim_t - 1)
+            out, cnt = fake_process(n, n_fft, chunk, 0, 1)
+            assert (cnt == 1).all(), (n, n_fft, cnt.min(), cnt.max())
+    # reference geometry: 4-min song, Kim_Vocal_2 class -> 22 + 22 chunk inferences per sweep
+    assert len(chunk_descriptors(10584000, 7680, 261120, 2)[0]) == 44
+
+
+def test_shard_range_partitions():
+    for n in (1, 7, 44, 88):
+        for w in (1, 2, 3, 8):
+            spans = [shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+
+
+def _worker(rank, world, port, n, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    out, _ = fake_process(n, 7680, 261120, rank, world)
+    t = torch.from_numpy(out)
+    dist.all_reduce(t)
+    if rank == 0:
+        q.put(t.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_sum_equals_single_rank(world):
+    n = 44100 * 40 + 321
+    ref, cnt = fake_process(n, 7680, 261120, 0, 1)
+    assert (cnt == 1).all()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000 + world
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert np.array_equal(got, ref)
