@@ -130,7 +130,8 @@ __device__ __forceinline__ void tg_store4(const TgParams& p, const TgRow& r, int
 
 // Host-side launchers (tapgemm_simt.cu / tapgemm_tc.cu).
 int tapgemm_simt_launch(const TgParams& p, cudaStream_t stream);
-int tapgemm_tc_launch(const TgParams& p, cudaStream_t stream);
+int tapgemm_tc_launch(const TgParams& p, cudaStream_t stream);    // v1: one tile per CTA
+int tapgemm_tc2_launch(const TgParams& p, cudaStream_t stream);   // v2: persistent, double-buffered TMEM, coalesced epilogue
 bool tapgemm_tc_supported(const TgParams& p);
 
 }  // namespace b200vc

@@ -305,6 +305,11 @@ int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmW, const TgParams& p
 
 }  // namespace
 
+int encode_map_f32(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims,
+                   const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+  return encode_map(tm, base, rank, dims, strides_bytes, box);
+}
+
 // Whether a problem can go through the TMA/tcgen05 path (alignment rules of
 // cuTensorMapEncodeTiled); otherwise callers use the SIMT kernel.
 bool tapgemm_tc_supported(const TgParams& p) {

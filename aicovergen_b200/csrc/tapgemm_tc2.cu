@@ -1,0 +1,367 @@
+// tcgen05 tap-GEMM v2: PERSISTENT, double-buffered TMEM accumulators, coalesced epilogue.
+//
+//   grid  = min(#tiles, #SMs) CTAs, each loops over output tiles (n-tile fastest so neighbouring CTAs share the A box in L2)
+//   warp 0 : TMA producer — the shared-memory ring keeps filling across tile boundaries
+//   warp 1 : TMEM allocator (2 x BN columns) + single-thread tcgen05.mma issuer; tcgen05.commit -> smem-empty / tmem-full
+//   warps 2-5 : epilogue — tcgen05.ld of accumulator stage `it & 1` while the MMA warp already fills the other stage;
+//               the 32x32 fp32 block of each warp is transposed through padded shared memory so every global
+//               store / residual load is a full 128-byte line (the v1 kernel wrote 16 B per row per instruction)
+//
+// Same descriptor, same epilogue semantics as tapgemm.cuh (scalar form tg_epi1).
+#include "tapgemm.cuh"
+#include <cuda.h>
+
+namespace b200vc {
+
+int encode_map_f32(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims,
+                   const cuuint64_t* strides_bytes, const cuuint32_t* box);   // tapgemm_tc.cu
+
+namespace {
+
+constexpr int KCHUNK = 32;
+constexpr int A_STAGE_BYTES = TG_TILE_M * 128;
+constexpr int NUM_THREADS = 192;
+constexpr int EPI_WARPS = 4;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct RowInfo {
+  long long o_off;
+  long long r_off;
+  int brow;
+  int valid;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                   const __grid_constant__ TgParams p, int ntiles_n, int total_tiles) {
+  constexpr int B_STAGE_BYTES = BN * 128;
+  constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  constexpr uint32_t TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;     // power of two for BN in {32,64,128,256}
+  constexpr uint32_t IDESC = make_idesc_tf32(128, BN);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  auto a_stage = [&](int s) { return smem_base + s * STAGE_BYTES; };
+  auto b_stage = [&](int s) { return smem_base + s * STAGE_BYTES + A_STAGE_BYTES; };
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  // epilogue staging (generic pointers): per warp a 32 x 33 fp32 transpose tile + 32 row records
+  float* stage_f = reinterpret_cast<float*>(smem_gen + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 6));
+  RowInfo* rows_s = reinterpret_cast<RowInfo*>(stage_f + EPI_WARPS * 32 * 33);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntw = (p.OW + p.BW - 1) / p.BW;
+  const int nth = (p.OH + p.BH - 1) / p.BH;
+  const int kchunks = (p.Kc + KCHUNK - 1) / KCHUNK;
+  const int nchunks = p.ntaps * kchunks;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  auto tile_coords = [&](int tile, int& w0, int& h0, int& tb, int& n0) {
+    const int nt = tile % ntiles_n;
+    int mt = tile / ntiles_n;
+    const int tw = mt % ntw; mt /= ntw;
+    const int th = mt % nth; mt /= nth;
+    tb = mt;
+    w0 = tw * p.BW;
+    h0 = th * p.BH;
+    n0 = nt * BN;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int it_chunk = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int w0, h0, tb, n0;
+        tile_coords(tile, w0, h0, tb, n0);
+        for (int chunk = 0; chunk < nchunks; ++chunk, ++it_chunk) {
+          const int s = it_chunk % STAGES;
+          const uint32_t ph = (it_chunk / STAGES) & 1;
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          const int tap_i = chunk / kchunks;
+          const int kc0 = (chunk - tap_i * kchunks) * KCHUNK;
+          const TgTap tap = p.taps[tap_i];
+          mbar_expect_tx(full_bar(s), STAGE_BYTES);
+          tma_load_5d(a_stage(s), &tmA, full_bar(s), tap.c_off + kc0, w0 + tap.dw, h0 + tap.dh, tb, tap.dp);
+          tma_load_3d(b_stage(s), &tmW, full_bar(s), kc0, n0, tap.widx + tb * p.w_batch_step);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int it_chunk = 0, it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t use = (uint32_t)(it >> 1);
+        mbar_wait(tempty_bar(acc), (use & 1u) ^ 1u);      // epilogue has drained this accumulator stage
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int chunk = 0; chunk < nchunks; ++chunk, ++it_chunk) {
+          const int s = it_chunk % STAGES;
+          const uint32_t ph = (it_chunk / STAGES) & 1;
+          mbar_wait(full_bar(s), ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t adesc = make_smem_desc(a_stage(s));
+          const uint64_t bdesc = make_smem_desc(b_stage(s));
+#pragma unroll
+          for (int k = 0; k < KCHUNK / 8; ++k)
+            umma_tf32(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, (chunk > 0 || k > 0) ? 1u : 0u);
+          umma_commit(empty_bar(s));
+        }
+        umma_commit(tfull_bar(acc));
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;
+    const int ew = warp - 2;                       // staging slot
+    float* st = stage_f + ew * 32 * 33;
+    RowInfo* ri = rows_s + ew * 32;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      int w0, h0, tb, n0;
+      tile_coords(tile, w0, h0, tb, n0);
+      {
+        const int m = q * 32 + lane;
+        const TgRow r = tg_row(p, tb, h0 + m / p.BW, w0 + m % p.BW);
+        ri[lane].o_off = r.o_off;
+        ri[lane].r_off = r.r_off;
+        ri[lane].brow = r.brow;
+        ri[lane].valid = r.valid ? 1 : 0;
+      }
+      const int acc = it & 1;
+      const uint32_t use = (uint32_t)(it >> 1);
+      mbar_wait(tfull_bar(acc), use & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      __syncwarp();
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        if (n0 + c0 >= p.N) break;                 // warp-uniform
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) st[lane * 33 + j] = __uint_as_float(v[j]);
+        __syncwarp();
+        const int n = n0 + c0 + lane;
+        const bool n_ok = n < p.N;
+        const float bias_n = (p.bias && !p.bias_per_row && n_ok) ? __ldg(p.bias + n) : 0.f;
+#pragma unroll 4
+        for (int r = 0; r < 32; ++r) {
+          const RowInfo info = ri[r];
+          if (!info.valid || !n_ok) continue;
+          float x = st[r * 33 + lane];
+          if (p.bias) x += p.bias_per_row ? __ldg(p.bias + info.brow) : bias_n;
+          x = apply_act(x, p.act_pre, p.act_pre_p);
+          if (p.row_scale) x *= __ldg(p.row_scale + info.brow);
+          if (p.res) {
+            const float rr = p.res[info.r_off + n];
+            x = (p.res_op & 1) ? x * rr : x + rr;
+          }
+          x *= p.scale;
+          if (p.res2) x += p.res2[info.o_off + n];
+          x = apply_act(x, p.act_post, p.act_post_p);
+          p.out[info.o_off + n] = (p.round_tf32 & 1) ? round_tf32(x) : x;
+          if (p.out2) {
+            const float x2 = apply_act(x, p.act2, p.act2_p);
+            p.out2[info.o_off + n] = (p.round_tf32 & 2) ? round_tf32(x2) : x2;
+          }
+        }
+        __syncwarp();
+      }
+      // all TMEM reads of this accumulator stage are complete (tcgen05.wait::ld inside tmem_ld32)
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+template <int BN, int STAGES>
+int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmW, const TgParams& p, int ntiles_n, int total_tiles,
+               int grid, cudaStream_t stream) {
+  constexpr int smem = STAGES * (A_STAGE_BYTES + BN * 128) + 8 * (2 * STAGES + 6) + EPI_WARPS * 32 * 33 * 4 +
+                       EPI_WARPS * 32 * (int)sizeof(RowInfo) + 1024;
+  static_assert(smem <= 227 * 1024, "shared memory budget");
+  static bool configured = false;
+  if (!configured) {
+    B200VC_CHECK_CUDA(cudaFuncSetAttribute(tapgemm_tc2_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  tapgemm_tc2_kernel<BN, STAGES><<<grid, NUM_THREADS, smem, stream>>>(tmA, tmW, p, ntiles_n, total_tiles);
+  return kOk;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+}  // namespace
+
+int tapgemm_tc2_launch(const TgParams& p, cudaStream_t stream) {
+  B200VC_REQUIRE(tapgemm_tc_supported(p), "tapgemm_tc: operand alignment not TMA-compatible");
+  const int ntw = ceil_div(p.OW, p.BW), nth = ceil_div(p.OH, p.BH);
+  const long long mtiles = (long long)ntw * nth * p.OB;
+  const int BN = p.N > 128 ? 256 : (p.N > 64 ? 128 : (p.N > 32 ? 64 : 32));
+  const int ntiles_n = ceil_div(p.N, BN);
+  const long long total = mtiles * ntiles_n;
+  B200VC_REQUIRE(total > 0 && total < (1ll << 31), "tapgemm_tc: bad tile count %lld", total);
+
+  CUtensorMap tmA, tmW;
+  {
+    cuuint64_t dims[5], strides[4];
+    cuuint32_t box[5] = {KCHUNK, (cuuint32_t)p.BW, (cuuint32_t)p.BH, 1, 1};
+    long long span = 1;
+    for (int i = 0; i < 5; ++i) {
+      dims[i] = (cuuint64_t)(p.a_dim[i] > 0 ? p.a_dim[i] : 1);
+      if (i > 0) {
+        long long st = p.a_stride[i];
+        if (p.a_dim[i] <= 1) st = ((span + 3) / 4) * 4;
+        strides[i - 1] = (cuuint64_t)st * 4ull;
+        span = st * (long long)dims[i];
+      } else {
+        span = (long long)dims[0];
+      }
+    }
+    int rc = encode_map_f32(&tmA, p.A, 5, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    int max_widx = 0;
+    for (int i = 0; i < p.ntaps; ++i) max_widx = p.taps[i].widx > max_widx ? p.taps[i].widx : max_widx;
+    const int nw = max_widx + 1 + (p.OB - 1) * p.w_batch_step;
+    cuuint64_t dims[3] = {(cuuint64_t)p.Kc, (cuuint64_t)p.N, (cuuint64_t)nw};
+    long long wst = p.wstride;
+    if (nw <= 1) wst = ((p.ldw * p.N + 3) / 4) * 4;
+    cuuint64_t strides[2] = {(cuuint64_t)p.ldw * 4ull, (cuuint64_t)wst * 4ull};
+    cuuint32_t box[3] = {KCHUNK, (cuuint32_t)BN, 1};
+    int rc = encode_map_f32(&tmW, p.Wt, 3, dims, strides, box);
+    if (rc) return rc;
+  }
+  const int grid = (int)(total < num_sms() ? total : num_sms());
+  int rc;
+  switch (BN) {
+    case 256: rc = launch_cfg<256, 4>(tmA, tmW, p, ntiles_n, (int)total, grid, stream); break;
+    case 128: rc = launch_cfg<128, 6>(tmA, tmW, p, ntiles_n, (int)total, grid, stream); break;
+    case 64:  rc = launch_cfg<64, 8>(tmA, tmW, p, ntiles_n, (int)total, grid, stream); break;
+    default:  rc = launch_cfg<32, 8>(tmA, tmW, p, ntiles_n, (int)total, grid, stream); break;
+  }
+  if (rc) return rc;
+  count_launch();
+  B200VC_LAUNCH_CHECK();
+  return kOk;
+}
+
+}  // namespace b200vc

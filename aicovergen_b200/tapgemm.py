@@ -19,7 +19,7 @@ import torch
 
 from . import _ffi
 from ._ffi import (ACT_EXP, ACT_GELU, ACT_LRELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH,
-                   BACKEND_SIMT, BACKEND_TC, MAX_TAPS, TapGemmParams)
+                   BACKEND_SIMT, BACKEND_TC, BACKEND_TC_V1, MAX_TAPS, TapGemmParams)
 
 __all__ = [
     "View", "Weights", "Out", "Epi", "TapGemm", "view", "out_of",
@@ -27,7 +27,7 @@ __all__ = [
     "conv2d_k2s2", "bmm_nt",
     "pack_conv1d", "pack_convt1d", "pack_conv2d", "pack_convt2d",
     "ACT_NONE", "ACT_RELU", "ACT_LRELU", "ACT_GELU", "ACT_TANH", "ACT_SIGMOID", "ACT_EXP",
-    "BACKEND_SIMT", "BACKEND_TC",
+    "BACKEND_SIMT", "BACKEND_TC", "BACKEND_TC_V1",
 ]
 
 
@@ -240,7 +240,7 @@ class TapGemm:
 
     def __call__(self, stream: Optional[int] = None, backend: Optional[int] = None):
         be = self.backend if backend is None else backend
-        if be == BACKEND_TC and not self.tc_supported():
+        if be in (BACKEND_TC, BACKEND_TC_V1) and not self.tc_supported():
             be = BACKEND_SIMT   # operand not TMA-addressable (e.g. C==1); still CUDA, still fp32-exact
         if stream is None:
             stream = torch.cuda.current_stream().cuda_stream

@@ -42,7 +42,8 @@ enum {
 /* which kernel family executes a tap-GEMM */
 enum {
   B200VC_BACKEND_SIMT_FP32 = 0, /* exact fp32 FMA kernel                      */
-  B200VC_BACKEND_TC_TF32 = 1    /* tcgen05.mma kind::tf32, TMA-fed, TMEM accum */
+  B200VC_BACKEND_TC_TF32 = 1,   /* tcgen05.mma kind::tf32, TMA-fed, TMEM accum: persistent kernel (tapgemm_tc2.cu) */
+  B200VC_BACKEND_TC_TF32_V1 = 2 /* same math, one-tile-per-CTA kernel (tapgemm_tc.cu), kept as a cross-check       */
 };
 
 typedef struct b200vc_tap {

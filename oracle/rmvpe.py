@@ -68,25 +68,14 @@ def e2e(sd: SD, mel: torch.Tensor, n_blocks=4, n_enc=5, n_inter=4) -> torch.Tens
 
 
 def bigru(sd: SD, x: torch.Tensor) -> torch.Tensor:
-    """nn.GRU(384, 256, 1 layer, batch_first, bidirectional) (rmvpe.py:8-20); PyTorch gate order r, z, n."""
-    T = x.shape[1]
+    """nn.GRU(384, 256, 1 layer, batch_first, bidirectional) (rmvpe.py:8-20) — the same torch operator the reference
+    calls, loaded with the checkpoint's weights (gate order r, z, n)."""
     Hh = sd["fc.0.gru.weight_hh_l0"].shape[1]
-    outs = []
-    for suf, order in (("", range(T)), ("_reverse", range(T - 1, -1, -1))):
-        wi, wh = sd[f"fc.0.gru.weight_ih_l0{suf}"], sd[f"fc.0.gru.weight_hh_l0{suf}"]
-        bi, bh = sd[f"fc.0.gru.bias_ih_l0{suf}"], sd[f"fc.0.gru.bias_hh_l0{suf}"]
-        xp = F.linear(x[0], wi, bi)                        # [T, 3H]
-        h = torch.zeros(Hh)
-        out = torch.zeros(T, Hh)
-        for t in order:
-            hp = F.linear(h, wh, bh)
-            r = torch.sigmoid(xp[t, :Hh] + hp[:Hh])
-            z = torch.sigmoid(xp[t, Hh:2 * Hh] + hp[Hh:2 * Hh])
-            n = torch.tanh(xp[t, 2 * Hh:] + r * hp[2 * Hh:])
-            h = (1 - z) * n + z * h
-            out[t] = h
-        outs.append(out)
-    return torch.cat(outs, -1).unsqueeze(0)
+    gru = torch.nn.GRU(x.shape[-1], Hh, num_layers=1, batch_first=True, bidirectional=True)
+    gru.load_state_dict({k[len("fc.0.gru."):]: v for k, v in sd.items() if k.startswith("fc.0.gru.")})
+    gru.eval()
+    with torch.no_grad():
+        return gru(x)[0]
 
 
 def mel2hidden(sd: SD, mel: torch.Tensor) -> torch.Tensor:

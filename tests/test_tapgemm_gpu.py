@@ -8,7 +8,7 @@ from aicovergen_b200 import tapgemm as tg
 
 pytestmark = pytest.mark.gpu
 
-BACKENDS = [("simt", tg.BACKEND_SIMT, 2e-5), ("tc", tg.BACKEND_TC, 2e-3)]
+BACKENDS = [("simt", tg.BACKEND_SIMT, 2e-5), ("tc", tg.BACKEND_TC, 2e-3), ("tc1", tg.BACKEND_TC_V1, 2e-3)]
 
 
 def rel_rms(a, b):

@@ -30,7 +30,7 @@ def main():
     ap.add_argument("--simt", action="store_true")
     ap.add_argument("--out", default="gpurun_out/bench_tapgemm.jsonl")
     args = ap.parse_args()
-    backends = [("tc", tg.BACKEND_TC)] + ([("simt", tg.BACKEND_SIMT)] if args.simt else [])
+    backends = [("tc2", tg.BACKEND_TC), ("tc1", tg.BACKEND_TC_V1)] + ([("simt", tg.BACKEND_SIMT)] if args.simt else [])
     shapes = [
         # name, T, Cin, Cout, k, dil
         ("voc.s1 C256 k3", 65980, 256, 256, 3, 1),
@@ -42,6 +42,8 @@ def main():
         ("hubert.ffn2", 3299, 3072, 768, 1, 1),
         ("encp.ffn1 k3", 6598, 192, 768, 3, 1),
         ("flow.wn k5", 6598, 192, 384, 5, 1),
+        ("mdx.l0 c48 k3 (as 1d)", 786432, 48, 48, 9, 1),
+        ("mdx.l2 c144 k3 (as 1d)", 49152, 144, 144, 9, 1),
     ]
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     with open(args.out, "w") as f:
