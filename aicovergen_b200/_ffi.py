@@ -11,7 +11,7 @@ from pathlib import Path
 MAX_TAPS = 128
 
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_GELU, ACT_TANH, ACT_SIGMOID, ACT_EXP = range(7)
-BACKEND_SIMT, BACKEND_TC, BACKEND_TC_V1 = 0, 1, 2
+BACKEND_SIMT, BACKEND_TC, BACKEND_TC_V1 = 0, 1, 2   # BACKEND_TC_V1 now selects the experimental persistent kernel
 
 
 class Tap(C.Structure):

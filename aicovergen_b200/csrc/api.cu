@@ -37,8 +37,8 @@ int b200vc_tapgemm(const b200vc_tapgemm_params* p, int backend, void* stream) {
   B200VC_REQUIRE(p->OW >= 1 && p->OH >= 1 && p->OB >= 1, "tapgemm: empty output space");
   B200VC_REQUIRE(p->a_stride[0] == 1, "tapgemm: A must be channels-last (a_stride[0]==1)");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (backend == B200VC_BACKEND_TC_TF32) return tapgemm_tc2_launch(*p, s);
-  if (backend == B200VC_BACKEND_TC_TF32_V1) return tapgemm_tc_launch(*p, s);
+  if (backend == B200VC_BACKEND_TC_TF32) return tapgemm_tc_launch(*p, s);
+  if (backend == B200VC_BACKEND_TC_TF32_PERSISTENT) return tapgemm_tc2_launch(*p, s);
   if (backend == B200VC_BACKEND_SIMT_FP32) return tapgemm_simt_launch(*p, s);
   set_last_error("tapgemm: unknown backend %d", backend);
   return kErrInvalidArg;

@@ -269,3 +269,230 @@ int b200vc_mix3(const float* a_mono, int64_t n_a, double ratio_a, const float* b
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------
+// change_rms + peak guard + int16 conversion on the device (vc_infer_pipeline.py:41-60, 645-649)
+// ---------------------------------------------------------------------------------------------------------
+namespace b200vc {
+namespace {
+
+// librosa.feature.rms(center=True, reflect): one block per frame, fp64 accumulation
+template <typename T>
+__global__ void frame_rms_kernel(const T* __restrict__ y, long long n, int frame, int hop, double* __restrict__ rms) {
+  const long long f = blockIdx.x;
+  const long long start = f * hop - frame / 2;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < frame; i += blockDim.x) {
+    long long j = start + i;
+    if (j < 0) j = -j;
+    if (j >= n) j = 2 * (n - 1) - j;
+    const double v = (j >= 0 && j < n) ? (double)y[j] : 0.0;
+    acc += v * v;
+  }
+  __shared__ double red[32];
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) t += red[w];
+    rms[f] = sqrt(t / frame);
+  }
+}
+
+__device__ __forceinline__ double lerp_frames(const double* __restrict__ r, int nf, long long i, double scale) {
+  // F.interpolate(mode="linear", align_corners=False)
+  double src = ((double)i + 0.5) * scale - 0.5;
+  if (src < 0.0) src = 0.0;
+  int i0 = (int)src;
+  if (i0 > nf - 1) i0 = nf - 1;
+  const int i1 = i0 + (i0 < nf - 1 ? 1 : 0);
+  const double l1 = src - (double)i0;
+  return (1.0 - l1) * r[i0] + l1 * r[i1];
+}
+
+// data2[i] *= rms1(i)^(1-rate) * max(rms2(i),1e-6)^(rate-1)
+__global__ void rms_mix_kernel(float* __restrict__ data2, long long n2, const double* __restrict__ rms1, int nf1,
+                               const double* __restrict__ rms2, int nf2, double rate) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n2) return;
+  const double r1 = lerp_frames(rms1, nf1, i, (double)nf1 / (double)n2);
+  float r2 = (float)lerp_frames(rms2, nf2, i, (double)nf2 / (double)n2);
+  r2 = fmaxf(r2, 1e-6f);
+  const double f = pow(r1, 1.0 - rate) * (double)powf(r2, (float)(rate - 1.0));
+  data2[i] = (float)((double)data2[i] * f);
+}
+
+__global__ void absmax_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
+  float m = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(x[i]));
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));   // m >= 0: int order == float order
+}
+
+// out = (int16)(x * (abs_max/0.99 > 1 ? 32768/(abs_max/0.99) : 32768))  with C truncation toward zero
+__global__ void to_int16_kernel(const float* __restrict__ x, long long n, const float* __restrict__ absmax,
+                                short* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float audio_max = absmax[0] / 0.99f;
+  double max_int16 = 32768.0;
+  if (audio_max > 1.f) max_int16 /= (double)audio_max;
+  out[i] = (short)(int)((double)x[i] * max_int16);
+}
+
+}  // namespace
+}  // namespace b200vc
+
+extern "C" {
+
+int b200vc_change_rms(const double* data1, int64_t n1, int sr1, float* data2, int64_t n2, int sr2, double rate,
+                      double* scratch, void* stream) {
+  B200VC_REQUIRE(data1 && data2 && scratch && n1 > 0 && n2 > 0 && sr1 > 1 && sr2 > 1, "change_rms: bad args");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int frame1 = sr1 / 2 * 2, hop1 = sr1 / 2, frame2 = sr2 / 2 * 2, hop2 = sr2 / 2;
+  const int nf1 = 1 + (int)(n1 / hop1), nf2 = 1 + (int)(n2 / hop2);
+  double* rms1 = scratch;
+  double* rms2 = scratch + nf1;
+  b200vc::frame_rms_kernel<double><<<nf1, 256, 0, s>>>(data1, n1, frame1, hop1, rms1);
+  b200vc::frame_rms_kernel<float><<<nf2, 256, 0, s>>>(data2, n2, frame2, hop2, rms2);
+  b200vc::rms_mix_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, s>>>(data2, n2, rms1, nf1, rms2, nf2, rate);
+  b200vc::count_launch(3);
+  B200VC_LAUNCH_CHECK();
+  return b200vc::kOk;
+}
+
+int b200vc_to_int16_peak_guard(const float* x, int64_t n, float* scratch_absmax, int16_t* out, void* stream) {
+  B200VC_REQUIRE(x && scratch_absmax && out && n > 0, "to_int16_peak_guard: bad args");
+  cudaStream_t s = (cudaStream_t)stream;
+  B200VC_CHECK_CUDA(cudaMemsetAsync(scratch_absmax, 0, sizeof(float), s));
+  b200vc::absmax_kernel<<<592, 256, 0, s>>>(x, n, scratch_absmax);
+  b200vc::to_int16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, n, scratch_absmax, out);
+  b200vc::count_launch(2);
+  B200VC_LAUNCH_CHECK();
+  return b200vc::kOk;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------
+// Zero-phase IIR in fp64, block-parallel, as a cascade of second-order sections (scipy.signal.sosfiltfilt semantics:
+// odd extension, sosfilt_zi initial conditions).  Per section and direction:
+//   pass 1: every thread runs the DF2T recurrence over its own block of L samples from a zero state
+//   pass 2: one thread chains the block-end states:  s_{k+1} = zs_end_k + M_L s_k
+//   pass 3: y[n] += h_{n mod L} . s_k   (response of the section to the carried-in state)
+// Replaces `signal.filtfilt(bh, ah, audio)` (vc_infer_pipeline.py:22, 513; 5th-order Butterworth high-pass).  The
+// reference's transfer-function form is itself only accurate to ~7e-7 here (scipy's filtfilt and sosfiltfilt of the same
+// filter differ by that much); this cascade matches scipy.sosfiltfilt to ~4e-13.
+// ---------------------------------------------------------------------------------------------------------
+namespace b200vc {
+namespace {
+
+struct SosCoef { double b0, b1, b2, a1, a2; };
+
+__global__ void odd_ext_kernel(const float* __restrict__ x, long long n, int pad, double* __restrict__ ext) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = n + 2 * pad;
+  if (i >= total) return;
+  double v;
+  if (i < pad) v = 2.0 * (double)x[0] - (double)x[pad - i];
+  else if (i < pad + n) v = (double)x[i - pad];
+  else v = 2.0 * (double)x[n - 1] - (double)x[n - 2 - (i - pad - n)];
+  ext[i] = v;
+}
+
+__global__ void sos_block_zs_kernel(const double* __restrict__ x, double* __restrict__ y, double* __restrict__ zs_end,
+                                    long long n, int L, SosCoef c, int reverse) {
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long nblk = (n + L - 1) / L;
+  if (k >= nblk) return;
+  double z0 = 0.0, z1 = 0.0;
+  const long long beg = k * L, end = min(n, beg + (long long)L);
+  for (long long t = beg; t < end; ++t) {
+    const long long i = reverse ? (n - 1 - t) : t;
+    const double xv = x[i];
+    const double yv = c.b0 * xv + z0;
+    z0 = c.b1 * xv + z1 - c.a1 * yv;
+    z1 = c.b2 * xv - c.a2 * yv;
+    y[i] = yv;
+  }
+  zs_end[k * 2 + 0] = z0;
+  zs_end[k * 2 + 1] = z1;
+}
+
+__global__ void sos_scan_states_kernel(const double* __restrict__ zs_end, const double* __restrict__ ML,
+                                       const double* __restrict__ zi, const double* __restrict__ scale_sample,
+                                       double* __restrict__ states, long long nblk) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double s0 = zi[0] * scale_sample[0], s1 = zi[1] * scale_sample[0];
+  const double m00 = ML[0], m01 = ML[1], m10 = ML[2], m11 = ML[3];
+  for (long long k = 0; k < nblk; ++k) {
+    states[k * 2 + 0] = s0;
+    states[k * 2 + 1] = s1;
+    const double t0 = zs_end[k * 2 + 0] + m00 * s0 + m01 * s1;
+    const double t1 = zs_end[k * 2 + 1] + m10 * s0 + m11 * s1;
+    s0 = t0;
+    s1 = t1;
+  }
+}
+
+__global__ void sos_fix_kernel(double* __restrict__ y, const double* __restrict__ states, const double* __restrict__ H,
+                               long long n, int L, int reverse) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const long long k = t / L;
+  const int j = (int)(t % L);
+  const long long i = reverse ? (n - 1 - t) : t;
+  y[i] += H[j * 2 + 0] * states[k * 2 + 0] + H[j * 2 + 1] * states[k * 2 + 1];
+}
+
+__global__ void copy_slice_f64_kernel(const double* __restrict__ src, double* __restrict__ dst, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i];
+}
+}  // namespace
+}  // namespace b200vc
+
+extern "C" {
+
+int b200vc_sosfiltfilt_f64(const float* x, int64_t n, const double* sos_host, int nsec, const double* zi_dev,
+                           const double* H_dev, const double* ML_dev, int L, int padlen, double* work, double* out,
+                           void* stream) {
+  using namespace b200vc;
+  B200VC_REQUIRE(x && sos_host && zi_dev && H_dev && ML_dev && work && out && nsec >= 1 && nsec <= 8 && L >= 16 &&
+                     padlen >= 0 && n > padlen + 1, "sosfiltfilt: bad args");
+  cudaStream_t s = (cudaStream_t)stream;
+  const long long ne = n + 2 * padlen;
+  const long long nblk = (ne + L - 1) / L;
+  double* bufA = work;
+  double* bufB = work + ne;
+  double* edge = work + 2 * ne;           // 2 doubles: scale samples
+  double* zs = edge + 2;
+  double* st = zs + nblk * 2;
+  const unsigned ge = (unsigned)((ne + 255) / 256), gb = (unsigned)((nblk + 63) / 64);
+  odd_ext_kernel<<<ge, 256, 0, s>>>(x, n, padlen, bufA);
+  int launches = 1;
+  double* cur = bufA;
+  double* nxt = bufB;
+  for (int dir = 0; dir < 2; ++dir) {
+    // all sections share the scale sample: first sample of the (direction's) input signal (scipy: zi * x_0)
+    const double* scale_src = dir == 0 ? cur : cur + (ne - 1);
+    B200VC_CHECK_CUDA(cudaMemcpyAsync(edge + dir, scale_src, sizeof(double), cudaMemcpyDeviceToDevice, s));
+    for (int sec = 0; sec < nsec; ++sec) {
+      const double* q = sos_host + sec * 6;
+      SosCoef c{q[0] / q[3], q[1] / q[3], q[2] / q[3], q[4] / q[3], q[5] / q[3]};
+      sos_block_zs_kernel<<<gb, 64, 0, s>>>(cur, nxt, zs, ne, L, c, dir);
+      sos_scan_states_kernel<<<1, 32, 0, s>>>(zs, ML_dev + sec * 4, zi_dev + sec * 2, edge + dir, st, nblk);
+      sos_fix_kernel<<<ge, 256, 0, s>>>(nxt, st, H_dev + (long long)sec * L * 2, ne, L, dir);
+      launches += 3;
+      double* t = cur; cur = nxt; nxt = t;
+    }
+  }
+  copy_slice_f64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(cur + padlen, out, n);
+  count_launch(launches + 1);
+  B200VC_LAUNCH_CHECK();
+  return kOk;
+}
+
+}  // extern "C"

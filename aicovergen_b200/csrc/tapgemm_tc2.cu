@@ -109,8 +109,6 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   constexpr int B_STAGE_BYTES = BN * 128;
   constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   constexpr uint32_t TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;     // power of two for BN in {32,64,128,256}
-  constexpr uint32_t IDESC = make_idesc_tf32(128, BN);
-
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -196,6 +194,11 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         mbar_wait(tempty_bar(acc), (use & 1u) ^ 1u);      // epilogue has drained this accumulator stage
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        // instruction N = the live part of this n-tile rounded up to 16 (e.g. 48 for the MDX c=48 layers)
+        int w0_, h0_, tb_, n0_;
+        tile_coords(tile, w0_, h0_, tb_, n0_);
+        const int nrem = p.N - n0_;
+        const uint32_t IDESC = make_idesc_tf32(128, nrem >= BN ? BN : ((nrem + 15) & ~15));
         for (int chunk = 0; chunk < nchunks; ++chunk, ++it_chunk) {
           const int s = it_chunk % STAGES;
           const uint32_t ph = (it_chunk / STAGES) & 1;

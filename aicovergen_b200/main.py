@@ -86,9 +86,8 @@ class CoverEngine:
         n16 = int(vocals_44k.shape[1] * 16000 // 44100)
         mono = torch.empty(n16, device=self.device)
         ops.resample_sinc_mono(vocals_44k.contiguous(), mono, 44100, 16000)
-        audio = mono.cpu().numpy()
         times = [0, 0, 0]
-        return self.vc.pipeline(self.hubert, self.net_g, 0, audio, "array", times, pitch_change, f0_method, self.index_path,
+        return self.vc.pipeline(self.hubert, self.net_g, 0, mono, "array", times, pitch_change, f0_method, self.index_path,
                                 index_rate, self.cpt.get("f0", 1), filter_radius, self.tgt_sr, 0, rms_mix_rate,
                                 self.cpt.get("version", "v1"), protect, 128)
 

@@ -43,6 +43,9 @@ _ffi.declare("b200vc_mdx_ola_store", [_P, _P, _P, _P, _P, _P, _i64, _i32, _i32, 
 _ffi.declare("b200vc_mdx_finalize", [_P, _P, _P, _i64, _f32, _f32, _P])
 _ffi.declare("b200vc_resample_sinc_mono", [_P, _i64, _i32, _P, _i64, C.c_double, _i32, _P])
 _ffi.declare("b200vc_mix3", [_P, _i64, C.c_double, _P, _P, _P, _i64, _f32, _f32, _f32, _P])
+_ffi.declare("b200vc_change_rms", [_P, _i64, _i32, _P, _i64, _i32, C.c_double, _P, _P])
+_ffi.declare("b200vc_to_int16_peak_guard", [_P, _i64, _P, _P, _P])
+_ffi.declare("b200vc_sosfiltfilt_f64", [_P, _i64, _P, _i32, _P, _P, _P, _i32, _i32, _P, _P, _P])
 
 
 def _s():
@@ -252,3 +255,66 @@ def mix3(a_mono, rate_a, b, c, out, rate, ga, gb, gc):
     assert a_mono.is_contiguous() and b.is_contiguous() and c.is_contiguous() and out.is_contiguous()
     _ffi.check(_ffi.lib().b200vc_mix3(_p(_f32c(a_mono)), a_mono.numel(), float(rate_a) / float(rate), _p(b), _p(c), _p(out), n,
                                       float(ga), float(gb), float(gc), _s()), "mix3")
+
+
+def change_rms(data1, sr1, data2, sr2, rate):
+    """In-place loudness-envelope mix of data2 (fp32 device) towards data1 (fp64 device)."""
+    assert data1.dtype == torch.float64 and data2.dtype == torch.float32 and data1.is_contiguous() and data2.is_contiguous()
+    n1, n2 = data1.numel(), data2.numel()
+    scratch = torch.empty(4 + n1 // (sr1 // 2) + n2 // (sr2 // 2), dtype=torch.float64, device=data2.device)
+    _ffi.check(_ffi.lib().b200vc_change_rms(_p(data1), n1, sr1, _p(data2), n2, sr2, float(rate), _p(scratch), _s()), "change_rms")
+
+
+def to_int16_peak_guard(x):
+    """float32 device waveform -> int16 device tensor with the reference's peak guard."""
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    out = torch.empty(x.numel(), dtype=torch.int16, device=x.device)
+    scratch = torch.zeros(1, dtype=torch.float32, device=x.device)
+    _ffi.check(_ffi.lib().b200vc_to_int16_peak_guard(_p(x), x.numel(), _p(scratch), _p(out), _s()), "to_int16_peak_guard")
+    return out
+
+
+_FILTFILT_CACHE = {}
+
+
+def _sos_tables(b, a, L, device):
+    """tf2sos sections, sosfilt_zi, and per section the zero-input response table / L-step state transition (float64)."""
+    import numpy as np
+    from scipy import signal
+
+    key = (tuple(np.asarray(b).tolist()), tuple(np.asarray(a).tolist()), L, str(device))
+    if key not in _FILTFILT_CACHE:
+        sos = np.ascontiguousarray(signal.tf2sos(b, a), dtype=np.float64)
+        zi = signal.sosfilt_zi(sos)
+        nsec = sos.shape[0]
+        H = np.zeros((nsec, L, 2))
+        ML = np.zeros((nsec, 2, 2))
+        for s_ in range(nsec):
+            a1, a2 = sos[s_, 4] / sos[s_, 3], sos[s_, 5] / sos[s_, 3]
+            for q in range(2):
+                z = np.zeros(2)
+                z[q] = 1.0
+                for j in range(L):
+                    y = z[0]
+                    H[s_, j, q] = y
+                    z = np.array([z[1] - a1 * y, -a2 * y])
+                ML[s_, :, q] = z
+        t = lambda v: torch.from_numpy(np.ascontiguousarray(v)).to(device)
+        _FILTFILT_CACHE[key] = (sos, t(zi), t(H), t(ML))
+    return _FILTFILT_CACHE[key]
+
+
+def filtfilt(x, b, a, L=512):
+    """Zero-phase IIR of a float32 device vector -> float64 device vector (scipy filtfilt defaults: odd extension,
+    padlen = 3*max(len(a), len(b)); evaluated as a second-order-section cascade)."""
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    n = x.numel()
+    sos, zi, H, ML = _sos_tables(b, a, L, x.device)
+    padlen = 3 * max(len(a), len(b))
+    ne = n + 2 * padlen
+    nblk = (ne + L - 1) // L
+    work = torch.empty(2 * ne + 2 + 4 * nblk + 16, dtype=torch.float64, device=x.device)
+    out = torch.empty(n, dtype=torch.float64, device=x.device)
+    _ffi.check(_ffi.lib().b200vc_sosfiltfilt_f64(_p(x), n, sos.ctypes.data_as(C.c_void_p), sos.shape[0], _p(zi), _p(H), _p(ML), L,
+                                                 padlen, _p(work), _p(out), _s()), "sosfiltfilt")
+    return out

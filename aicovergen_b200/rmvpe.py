@@ -148,7 +148,10 @@ class RMVPEB200:
 
     def infer_from_audio(self, audio: np.ndarray, thred: float = 0.03) -> np.ndarray:
         """Reference signature (rmvpe.py:366-383): np.ndarray[N] -> np.ndarray[1 + N//160] (float64 Hz, 0 = unvoiced)."""
-        a = torch.from_numpy(np.ascontiguousarray(audio)).float().to(self.device)
+        if isinstance(audio, torch.Tensor):
+            a = audio.detach().to(self.device).float().contiguous()      # extension: device tensor in, no H2D
+        else:
+            a = torch.from_numpy(np.ascontiguousarray(audio)).float().to(self.device)
         pl = self._plan(int(a.numel()))
         pl.run(a)
         ops.rmvpe_decode(pl.sal, pl.f0, pl.n_frames, thred, cents=pl.cents)

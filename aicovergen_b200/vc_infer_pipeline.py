@@ -68,6 +68,8 @@ class VC(object):
         self.t_max = self.sr * self.x_max            # below this no cutting
         self.device = config.device
         self._noise_gen: Optional[torch.Generator] = None
+        self.keep_float = False      # tests: keep the float waveform before/after the RMS mix
+        self.exact_hpf = False       # True: scipy.signal.filtfilt on the host (the reference's exact ba-form numerics)
 
     # ------------------------------------------------------------------ extension for parity tests
     def set_noise_seed(self, seed: Optional[int]):
@@ -96,6 +98,8 @@ class VC(object):
                 from .rvc import BASE_DIR
                 self.model_rmvpe = RMVPEB200(os.path.join(BASE_DIR, "rvc_models", "rmvpe.pt"), is_half=self.is_half,
                                              device=self.device)
+            if isinstance(x, torch.Tensor) and not hasattr(self.model_rmvpe, "infer_from_audio_device"):
+                x = x.cpu().numpy()          # a reference-style RMVPE object was injected: it takes numpy
             f0 = self.model_rmvpe.infer_from_audio(x, thred=0.03)
         else:
             raise NotImplementedError(
@@ -159,21 +163,24 @@ class VC(object):
         return audio1
 
     # ------------------------------------------------------------------ whole utterance
-    def _cut_points(self, audio: np.ndarray):
-        """Quiet-point search (vc_infer_pipeline.py:514-528): 160-tap box sum of the reflect-padded signal,
-        then argmin |sum| within +-t_query of every t_center multiple. The box sum runs on the device in fp64
-        with the reference's accumulation order, the window scan on the host."""
-        audio_pad = np.pad(audio, (self.window // 2, self.window // 2), mode="reflect")
+    @staticmethod
+    def _reflect_pad(t: torch.Tensor, p: int) -> torch.Tensor:
+        """np.pad(t, (p, p), mode="reflect") for a 1-D device tensor."""
+        return torch.cat([t[1:p + 1].flip(0), t, t[-p - 1:-1].flip(0)]).contiguous()
+
+    def _cut_points(self, audio64: torch.Tensor):
+        """Quiet-point search (vc_infer_pipeline.py:514-528): 160-tap box sum of the reflect-padded signal in fp64 with
+        the reference's accumulation order (b200vc_boxsum_f64), then the first argmin of |sum| within +-t_query of every
+        t_center multiple."""
+        n = audio64.numel()
         opt_ts = []
-        if audio_pad.shape[0] > self.t_max:
-            n = audio.shape[0]
-            xd = torch.from_numpy(np.ascontiguousarray(audio_pad, dtype=np.float64)).to(self.device)
-            sd = torch.empty(n, dtype=torch.float64, device=self.device)
-            ops.boxsum_f64(xd, sd, n, self.window)
-            audio_sum = sd.cpu().numpy()
-            for t in range(self.t_center, audio.shape[0], self.t_center):
-                seg = np.abs(audio_sum[t - self.t_query: t + self.t_query])
-                opt_ts.append(t - self.t_query + np.where(seg == seg.min())[0][0])
+        if n + self.window > self.t_max:
+            audio_pad = self._reflect_pad(audio64, self.window // 2)
+            audio_sum = torch.empty(n, dtype=torch.float64, device=audio64.device)
+            ops.boxsum_f64(audio_pad, audio_sum, n, self.window)
+            for t in range(self.t_center, n, self.t_center):
+                seg = audio_sum[t - self.t_query: t + self.t_query].abs()
+                opt_ts.append(t - self.t_query + int(torch.argmin(seg).item()))   # argmin returns the first minimum
         return opt_ts
 
     def pipeline(self, model, net_g, sid, audio, input_audio_path, times, f0_up_key, f0_method, file_index,
@@ -181,20 +188,32 @@ class VC(object):
                  crepe_hop_length, f0_file=None):
         if file_index != "" and os.path.exists(file_index) and index_rate != 0:
             try:
-                index = read_index(file_index, self.device)
-                big_npy = index.reconstruct_n(0, index.ntotal)
+                # the reference re-reads the index on every call (:505-507); the device copy is cached per file version
+                key = (file_index, os.path.getmtime(file_index), os.path.getsize(file_index))
+                if getattr(self, "_index_cache", (None, None))[0] != key:
+                    self._index_cache = (key, read_index(file_index, self.device))
+                index = self._index_cache[1]
+                big_npy = index._host_vectors            # what reconstruct_n(0, ntotal) returns, without the copy
             except Exception:
                 traceback.print_exc()
                 index = big_npy = None
         else:
             index = big_npy = None
-        audio = signal.filtfilt(bh, ah, audio)
+        dev = self.device
+        if isinstance(audio, torch.Tensor):
+            a32 = audio.detach().to(dev).float().contiguous()
+        else:
+            a32 = torch.from_numpy(np.ascontiguousarray(audio, dtype=np.float32)).to(dev)
+        if self.exact_hpf:
+            audio = torch.from_numpy(signal.filtfilt(bh, ah, a32.cpu().numpy())).to(dev)
+        else:
+            audio = ops.filtfilt(a32, bh, ah)                      # fp64 on the device (sos cascade)
         opt_ts = self._cut_points(audio)
         s = 0
         audio_opt = []
         t = None
         t1 = ttime()
-        audio_pad = np.pad(audio, (self.t_pad, self.t_pad), mode="reflect")
+        audio_pad = self._reflect_pad(audio, self.t_pad)
         p_len = audio_pad.shape[0] // self.window
         inp_f0 = None
         if hasattr(f0_file, "name"):
@@ -216,7 +235,7 @@ class VC(object):
         t2 = ttime()
         times[1] += t2 - t1
         # the padded utterance goes to HBM once; segments are device slices of it
-        pad_dev = torch.from_numpy(np.ascontiguousarray(audio_pad)).to(self.device).float()
+        pad_dev = audio_pad.float()
         w = self.window
         for t in opt_ts:
             t = t // w * w
@@ -235,17 +254,16 @@ class VC(object):
         else:
             out = self.vc(model, net_g, sid, seg, None, None, times, index, big_npy, index_rate, version, protect)
         audio_opt.append(out[self.t_pad_tgt: -self.t_pad_tgt].clone())
-        audio_opt = torch.cat(audio_opt).cpu().numpy()          # the single D2H of the converted utterance
-        self.last_float_output = audio_opt.copy()                # pre-RMS-mix float waveform (parity tests)
+        audio_dev = torch.cat(audio_opt).contiguous()
+        if self.keep_float:
+            self.last_float_output = audio_dev.cpu().numpy()   # pre-RMS-mix float waveform (parity tests)
         if rms_mix_rate != 1:
-            audio_opt = change_rms(audio, 16000, audio_opt, tgt_sr, rms_mix_rate)
+            # change_rms on the device (the reference does it with librosa/torch on the host, :639-640)
+            ops.change_rms(audio, 16000, audio_dev, tgt_sr, rms_mix_rate)
         if resample_sr >= 16000 and tgt_sr != resample_sr:
             raise NotImplementedError("resample_sr != 0 needs librosa.resample; rvc_infer always passes 0 (rvc.py:150)")
-        audio_max = np.abs(audio_opt).max() / 0.99
-        max_int16 = 32768
-        if audio_max > 1:
-            max_int16 /= audio_max
-        self.last_float_mixed = audio_opt
-        audio_opt = (audio_opt * max_int16).astype(np.int16)
+        if self.keep_float:
+            self.last_float_mixed = audio_dev.cpu().numpy()
+        audio_opt = ops.to_int16_peak_guard(audio_dev).cpu().numpy()      # the single D2H of the converted utterance
         del pitch, pitchf, sid
         return audio_opt

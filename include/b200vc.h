@@ -42,8 +42,9 @@ enum {
 /* which kernel family executes a tap-GEMM */
 enum {
   B200VC_BACKEND_SIMT_FP32 = 0, /* exact fp32 FMA kernel                      */
-  B200VC_BACKEND_TC_TF32 = 1,   /* tcgen05.mma kind::tf32, TMA-fed, TMEM accum: persistent kernel (tapgemm_tc2.cu) */
-  B200VC_BACKEND_TC_TF32_V1 = 2 /* same math, one-tile-per-CTA kernel (tapgemm_tc.cu), kept as a cross-check       */
+  B200VC_BACKEND_TC_TF32 = 1,   /* tcgen05.mma kind::tf32, TMA-fed, TMEM accum: one tile per CTA, 2 CTAs/SM (tapgemm_tc.cu) */
+  B200VC_BACKEND_TC_TF32_PERSISTENT = 2 /* same math, persistent kernel with double-buffered TMEM (tapgemm_tc2.cu); measured
+                                            slower in round 1 (single epilogue per SM), kept for development */
 };
 
 typedef struct b200vc_tap {
@@ -243,6 +244,25 @@ int b200vc_resample_sinc_mono(const float* x, int64_t n_in, int channels, float*
 /* out[2,n] = ga*lerp(a_mono at ratio_a) + gb*b + gc*c : gain-and-sum stand-in for main.combine_audio (main.py:229-233) */
 int b200vc_mix3(const float* a_mono, int64_t n_a, double ratio_a, const float* b, const float* c, float* out, int64_t n,
                 float ga, float gb, float gc, void* stream);
+
+/* change_rms (vc_infer_pipeline.py:41-60) on the device: half-second RMS envelopes of data1 (fp64, rate sr1) and data2
+ * (fp32, rate sr2; librosa.feature.rms center/reflect), linear interpolation to n2 samples, data2 *= rms1^(1-rate) *
+ * max(rms2,1e-6)^(rate-1) in place. scratch: (2 + n1/(sr1/2) + n2/(sr2/2)) doubles. */
+int b200vc_change_rms(const double* data1, int64_t n1, int sr1, float* data2, int64_t n2, int sr2, double rate,
+                      double* scratch, void* stream);
+
+/* Peak guard + int16 conversion of vc_infer_pipeline.py:645-649: scale by 32768 (or 32768/(max|x|/0.99) when that
+ * exceeds 1) and truncate toward zero. scratch_absmax: one float. */
+int b200vc_to_int16_peak_guard(const float* x, int64_t n, float* scratch_absmax, int16_t* out, void* stream);
+
+/* Zero-phase IIR as a cascade of `nsec` second-order sections, fp64, block-parallel: scipy.signal.sosfiltfilt semantics
+ * (odd extension by padlen, sosfilt_zi initial conditions). Replaces signal.filtfilt(bh, ah, audio) at
+ * vc_infer_pipeline.py:22,513 (the two scipy forms of this filter agree to ~7e-7; this matches sosfiltfilt to ~4e-13).
+ * sos_host: HOST [nsec,6]; zi_dev [nsec,2], H_dev [nsec,L,2] (zero-input responses), ML_dev [nsec,4] (L-step state
+ * transition): DEVICE tables prepared by the caller; work: 2*(n+2*padlen) + 2 + 4*ceil((n+2*padlen)/L) doubles. */
+int b200vc_sosfiltfilt_f64(const float* x, int64_t n, const double* sos_host, int nsec, const double* zi_dev,
+                           const double* H_dev, const double* ML_dev, int L, int padlen, double* work, double* out,
+                           void* stream);
 
 #ifdef __cplusplus
 }

@@ -60,6 +60,7 @@ def test_vc_pipeline_parity(with_index):
     vc = VC(40000, cfg)
     vc.model_rmvpe = RMVPEB200(rsd, device="cuda:0")
     vc.set_noise_seed(5)
+    vc.keep_float = True
     hubert = HubertB200(hsd, "cuda:0")
     net_g = SynthesizerB200(cpt, "cuda:0")
     times = [0, 0, 0]
@@ -82,3 +83,43 @@ def test_vc_pipeline_parity(with_index):
           f"(ref rms {ref_rms:.3e}); int16 max diff {d16.max()} rms {np.sqrt((d16.astype(float) ** 2).mean()):.2f}; cuts {info['opt_ts']}")
     assert mism == 0
     assert e_float < 1e-3
+
+
+def test_device_filtfilt_matches_scipy():
+    """Device zero-phase HPF (sos cascade, block-parallel) vs scipy: ~1e-12 to sosfiltfilt, and within the reference's own
+    numerical noise (ba-form filtfilt vs sosfiltfilt differ by ~7e-7) of the exact call at vc_infer_pipeline.py:513."""
+    from scipy import signal
+
+    from aicovergen_b200 import ops
+    from aicovergen_b200.vc_infer_pipeline import ah, bh
+
+    x = vocal_like(23.0, seed=2)
+    ref_ba = signal.filtfilt(bh, ah, x)
+    ref_sos = signal.sosfiltfilt(signal.tf2sos(bh, ah), x, padtype="odd", padlen=18)
+    got = ops.filtfilt(torch.from_numpy(x).cuda(), bh, ah).cpu().numpy()
+    e_sos, e_ba = np.abs(got - ref_sos).max(), np.abs(got - ref_ba).max()
+    print(f"[filtfilt] max abs diff vs scipy.sosfiltfilt {e_sos:.2e}, vs scipy.filtfilt(ba) {e_ba:.2e} (scipy ba vs sos {np.abs(ref_ba - ref_sos).max():.2e})")
+    assert e_sos < 1e-10 and e_ba < 5e-6
+
+
+def test_device_change_rms_and_int16_match_host():
+    from aicovergen_b200 import ops
+    from oracle import pipeline as opipe
+
+    rng = np.random.default_rng(3)
+    a = vocal_like(6.3, seed=4).astype(np.float64) * 0.8
+    out = (0.4 * rng.standard_normal(int(6.3 * 40000))).astype(np.float32) * (0.5 + 0.5 * np.sin(np.arange(int(6.3 * 40000)) / 9000.0)).astype(np.float32)
+    ref = opipe.change_rms(a.copy(), 16000, out.copy(), 40000, 0.25)
+    d = torch.from_numpy(out.copy()).cuda()
+    ops.change_rms(torch.from_numpy(a).cuda(), 16000, d, 40000, 0.25)
+    got = d.cpu().numpy()
+    rel = np.abs(got - ref).max() / np.abs(ref).max()
+    print(f"[change_rms] max rel diff {rel:.2e}")
+    assert rel < 2e-5
+    for scale in (1.0, 3.7):          # second case triggers the peak guard
+        x = (ref * scale).astype(np.float32)
+        audio_max = np.abs(x).max() / 0.99
+        m = 32768 / audio_max if audio_max > 1 else 32768
+        want = (x * m).astype(np.int16)
+        have = ops.to_int16_peak_guard(torch.from_numpy(x).cuda()).cpu().numpy()
+        assert np.abs(have.astype(np.int32) - want.astype(np.int32)).max() <= 1
