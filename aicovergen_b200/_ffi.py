@@ -11,7 +11,7 @@ from pathlib import Path
 MAX_TAPS = 128
 
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_GELU, ACT_TANH, ACT_SIGMOID, ACT_EXP = range(7)
-BACKEND_SIMT, BACKEND_TC, BACKEND_TC_V1 = 0, 1, 2   # BACKEND_TC_V1 now selects the experimental persistent kernel
+BACKEND_SIMT, BACKEND_TC, BACKEND_TC_V1, BACKEND_TC_TILE, BACKEND_TC_WS = 0, 1, 2, 3, 4   # 2 = experimental persistent kernel
 
 
 class Tap(C.Structure):
@@ -96,6 +96,8 @@ def _declare(lib):
     lib.b200vc_tapgemm.restype = C.c_int
     lib.b200vc_tapgemm_tc_supported.argtypes = [C.POINTER(TapGemmParams)]
     lib.b200vc_tapgemm_tc_supported.restype = C.c_int
+    lib.b200vc_tapgemm_ws_applicable.argtypes = [C.POINTER(TapGemmParams)]
+    lib.b200vc_tapgemm_ws_applicable.restype = C.c_int
     # later-declared entry points register themselves via declare_optional()
     for name, (argtypes, restype) in _EXTRA.items():
         fn = getattr(lib, name)

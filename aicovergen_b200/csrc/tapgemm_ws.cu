@@ -1,0 +1,432 @@
+// tcgen05 tap-GEMM v3: WEIGHT-STATIONARY + INPUT-HALO kernel for small-channel convolutions (Cout <= 64).
+//
+// The one-tile-per-CTA kernel re-reads the input tile once per tap and the whole weight slab once per tile from L2
+// (profiles/r01: it runs at the L2->SM bandwidth limit, e.g. 432 KB of TMA traffic per 128-pixel tile for the MDX
+// c=48 3x3 layers).  Here:
+//   * every CTA is persistent and first parks ALL weights of the layer in shared memory (ntaps x kchunks tiles of
+//     [Nr x 32] fp32, <= ~112 KB) — they are never fetched again;
+//   * per output tile (1 x 128 pixel strip) and 32-channel chunk ONE TMA box brings the strip WITH ITS HALO
+//     ([KH rows] x [128 + (KW-1)*dil] pixels x 32 ch); the taps are just row offsets of the UMMA A descriptor inside
+//     that box (the 128-byte swizzle is a function of absolute shared-memory address bits, so shifting the start
+//     address by whole 128-byte rows keeps TMA's layout and the descriptor's view consistent);
+//   * TMEM accumulators are double buffered so the epilogue of tile i overlaps the MMAs of tile i+1, and the epilogue
+//     transposes 32x32 blocks through shared memory so all global traffic is full 128-byte lines (float4 per lane).
+// L2->SM traffic per tile drops to the halo box only (100 KB instead of 432 KB for MDX c=48; 37 KB instead of 336 KB for
+// the vocoder's C=64 k=7 layers).
+#include "tapgemm.cuh"
+#include <cuda.h>
+
+namespace b200vc {
+
+int encode_map_f32(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims,
+                   const cuuint64_t* strides_bytes, const cuuint32_t* box);   // tapgemm_tc.cu
+
+namespace {
+
+constexpr int KCHUNK = 32;
+constexpr int EPI_WARPS = 4;                       // one per TMEM lane quarter; each walks the 32-column groups
+constexpr int NUM_THREADS = 64 + EPI_WARPS * 32;   // warp0 TMA, warp1 MMA, warps 2..5 epilogue
+constexpr int ST_PITCH = 36;                       // floats per staged row (16-byte aligned, conflict-free float4)
+
+struct WsGeom {
+  int KH, KW, dil_w, dil_h, pad_w, pad_h;
+  int BWh;            // halo box width in pixels = 128 + (KW-1)*dil_w
+  int a_stage_bytes;  // KH * BWh * 128 rounded up to 1024
+  int b_tile_bytes;   // Nr * 128
+  int Nr;             // MMA N (N rounded up to 16)
+  int stages;
+  int total_tiles;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tapgemm_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                  const __grid_constant__ TgParams p, const WsGeom g) {
+  constexpr int TM_COLS_PER_ACC = 64;
+  constexpr uint32_t TMEM_COLS = 2 * TM_COLS_PER_ACC;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int kchunks = (p.Kc + KCHUNK - 1) / KCHUNK;
+  const int w_bytes = p.ntaps * kchunks * g.b_tile_bytes;
+  const uint32_t w_base = smem_base;                              // resident weights
+  const uint32_t a_base = smem_base + w_bytes;                    // A halo ring (w_bytes is a multiple of 1024)
+  const uint32_t bar_base = a_base + g.stages * g.a_stage_bytes;
+  auto a_stage = [&](int s) { return a_base + s * g.a_stage_bytes; };
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (4 + s); };
+  const uint32_t w_bar = bar_base + 8u * 8;
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (9 + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (11 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * 13;
+  const int misc_off = w_bytes + g.stages * g.a_stage_bytes + 8 * 14;
+  float* stage_f = reinterpret_cast<float*>(smem_gen + ((misc_off + 15) & ~15));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntw = (p.OW + 127) / 128;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
+    for (int s = 0; s < g.stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(w_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  auto tile_coords = [&](int tile, int& w0, int& h0, int& tb) {
+    const int tw = tile % ntw;
+    int r = tile / ntw;
+    h0 = r % p.OH;
+    tb = r / p.OH;
+    w0 = tw * 128;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      // park the whole weight slab: [tap][kchunk] tiles of Nr x 32
+      mbar_expect_tx(w_bar, (uint32_t)w_bytes);
+      for (int j = 0; j < p.ntaps; ++j)
+        for (int kc = 0; kc < kchunks; ++kc)
+          tma_load_3d(w_base + (uint32_t)((j * kchunks + kc) * g.b_tile_bytes), &tmW, w_bar, kc * KCHUNK, 0, j);
+      int it = 0;
+      const uint32_t a_tx = (uint32_t)(g.KH * g.BWh * 128);
+      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+        int w0, h0, tb;
+        tile_coords(tile, w0, h0, tb);
+        for (int kc = 0; kc < kchunks; ++kc, ++it) {
+          const int s = it % g.stages;
+          const uint32_t ph = (it / g.stages) & 1;
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          mbar_expect_tx(full_bar(s), a_tx);
+          tma_load_5d(a_stage(s), &tmA, full_bar(s), kc * KCHUNK, w0 - g.pad_w, h0 - g.pad_h, tb, 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t IDESC = make_idesc_tf32(128, g.Nr);
+      mbar_wait(w_bar, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      int it = 0, ti = 0;
+      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++ti) {
+        const int acc = ti & 1;
+        const uint32_t use = (uint32_t)(ti >> 1);
+        mbar_wait(tempty_bar(acc), (use & 1u) ^ 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TM_COLS_PER_ACC);
+        for (int kc = 0; kc < kchunks; ++kc, ++it) {
+          const int s = it % g.stages;
+          const uint32_t ph = (it / g.stages) & 1;
+          mbar_wait(full_bar(s), ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a0 = a_stage(s);
+          for (int j = 0; j < p.ntaps; ++j) {
+            const int kh = j / g.KW, kw = j - kh * g.KW;
+            const uint32_t rowoff = (uint32_t)(kh * g.BWh + kw * g.dil_w);   // first row of this tap inside the halo box
+            const uint64_t adesc = make_smem_desc(a0 + rowoff * 128u);
+            const uint64_t bdesc = make_smem_desc(w_base + (uint32_t)((j * kchunks + kc) * g.b_tile_bytes));
+#pragma unroll
+            for (int k = 0; k < KCHUNK / 8; ++k)
+              umma_tf32(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, (kc > 0 || j > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(s));
+        }
+        umma_commit(tfull_bar(acc));
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;                         // TMEM lane quarter
+    float* st = stage_f + (warp - 2) * 32 * ST_PITCH;
+    int ti = 0;
+    for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++ti) {
+      int w0, h0, tb;
+      tile_coords(tile, w0, h0, tb);
+      const int acc = ti & 1;
+      const uint32_t use = (uint32_t)(ti >> 1);
+      mbar_wait(tfull_bar(acc), use & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int ngroups = (p.N + 31) / 32;
+      for (int cg = 0; cg < ngroups; ++cg) {
+        const int c0 = cg * 32;
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TM_COLS_PER_ACC + c0), v);
+        if (cg == ngroups - 1) {
+          // accumulator stage fully read -> hand it back to the MMA warp before touching global memory
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          if (lane == 0) mbar_arrive(tempty_bar(acc));
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(&st[lane * ST_PITCH + j]) =
+              make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+        __syncwarp();
+        const int cl = (lane & 7) * 4;              // 8 lanes x float4 = one 128-byte row segment
+        const int n = c0 + cl;
+        const bool vec = (p.vec4 & 2) && (n + 3 < p.N);
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias && !p.bias_per_row) {
+          if (n + 0 < p.N) bias4.x = __ldg(p.bias + n + 0);
+          if (n + 1 < p.N) bias4.y = __ldg(p.bias + n + 1);
+          if (n + 2 < p.N) bias4.z = __ldg(p.bias + n + 2);
+          if (n + 3 < p.N) bias4.w = __ldg(p.bias + n + 3);
+        }
+#pragma unroll 2
+        for (int it8 = 0; it8 < 8; ++it8) {
+          const int r = it8 * 4 + (lane >> 3);
+          const TgRow info = tg_row(p, tb, h0, w0 + q * 32 + r);
+          if (!info.valid || n >= p.N) continue;
+          const float4 a = *reinterpret_cast<const float4*>(&st[r * ST_PITCH + cl]);
+          float x[4] = {a.x + bias4.x, a.y + bias4.y, a.z + bias4.z, a.w + bias4.w};
+          if (p.bias && p.bias_per_row) {
+            const float bb = __ldg(p.bias + info.brow);
+            x[0] += bb; x[1] += bb; x[2] += bb; x[3] += bb;
+          }
+          const float rs = p.row_scale ? __ldg(p.row_scale + info.brow) : 1.f;
+          float rr[4] = {0.f, 0.f, 0.f, 0.f}, r2[4] = {0.f, 0.f, 0.f, 0.f};
+          if (p.res) {
+            if (vec) {
+              const float4 t = *reinterpret_cast<const float4*>(p.res + info.r_off + n);
+              rr[0] = t.x; rr[1] = t.y; rr[2] = t.z; rr[3] = t.w;
+            } else {
+              for (int e = 0; e < 4; ++e) if (n + e < p.N) rr[e] = p.res[info.r_off + n + e];
+            }
+          }
+          if (p.res2) {
+            if (vec) {
+              const float4 t = *reinterpret_cast<const float4*>(p.res2 + info.o_off + n);
+              r2[0] = t.x; r2[1] = t.y; r2[2] = t.z; r2[3] = t.w;
+            } else {
+              for (int e = 0; e < 4; ++e) if (n + e < p.N) r2[e] = p.res2[info.o_off + n + e];
+            }
+          }
+          float y[4], y2[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float t = apply_act(x[e], p.act_pre, p.act_pre_p) * rs;
+            if (p.res) t = (p.res_op & 1) ? t * rr[e] : t + rr[e];
+            t *= p.scale;
+            t += r2[e];
+            t = apply_act(t, p.act_post, p.act_post_p);
+            y2[e] = apply_act(t, p.act2, p.act2_p);
+            y[e] = (p.round_tf32 & 1) ? round_tf32(t) : t;
+            if (p.round_tf32 & 2) y2[e] = round_tf32(y2[e]);
+          }
+          if (vec) {
+            *reinterpret_cast<float4*>(p.out + info.o_off + n) = make_float4(y[0], y[1], y[2], y[3]);
+            if (p.out2) *reinterpret_cast<float4*>(p.out2 + info.o_off + n) = make_float4(y2[0], y2[1], y2[2], y2[3]);
+          } else {
+            for (int e = 0; e < 4; ++e)
+              if (n + e < p.N) {
+                p.out[info.o_off + n + e] = y[e];
+                if (p.out2) p.out2[info.o_off + n + e] = y2[e];
+              }
+          }
+        }
+        __syncwarp();                               // staging tile is reused by the next column group / tile
+      }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+int num_sms_ws() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+constexpr int SMEM_LIMIT = 227 * 1024;
+
+// Does the descriptor describe a dense stride-1 convolution over a regular tap grid, small enough for the weights to
+// stay in shared memory?  Fills the geometry when it does.
+bool ws_geometry(const TgParams& p, WsGeom& g) {
+  if (!tapgemm_tc_supported(p)) return false;
+  if (p.N > 64 || p.BW != 128 || p.BH != 1 || p.OW < 128 || p.w_batch_step != 0 || p.ntaps < 2) return false;
+  // recover (KH, KW, dilation, padding) from the tap table
+  int KW = 1;
+  while (KW < p.ntaps && p.taps[KW].dh == p.taps[0].dh) ++KW;
+  if (p.ntaps % KW) return false;
+  const int KH = p.ntaps / KW;
+  const int dil_w = KW > 1 ? p.taps[1].dw - p.taps[0].dw : 1;
+  const int dil_h = KH > 1 ? p.taps[KW].dh - p.taps[0].dh : 1;
+  if (dil_w < 1 || dil_h != 1) return false;          // rows of the halo box are consecutive image rows
+  for (int j = 0; j < p.ntaps; ++j) {
+    const b200vc_tap& t = p.taps[j];
+    const int kh = j / KW, kw = j % KW;
+    if (t.c_off != 0 || t.dp != 0 || t.widx != j) return false;
+    if (t.dw != p.taps[0].dw + kw * dil_w || t.dh != p.taps[0].dh + kh * dil_h) return false;
+  }
+  g.KH = KH; g.KW = KW; g.dil_w = dil_w; g.dil_h = dil_h;
+  g.pad_w = -p.taps[0].dw; g.pad_h = -p.taps[0].dh;
+  g.BWh = 128 + (KW - 1) * dil_w;
+  if (g.BWh > 256 || KH > 256) return false;
+  g.Nr = (p.N + 15) & ~15;                 // MMA N and weight-tile rows (16 rows x 128 B = 2 KB granules: stays 1024-aligned)
+  g.b_tile_bytes = g.Nr * 128;
+  g.a_stage_bytes = ((KH * g.BWh * 128 + 1023) / 1024) * 1024;   // 1024-aligned stages (swizzle atom = 8 rows x 128 B)
+  const int kchunks = (p.Kc + KCHUNK - 1) / KCHUNK;
+  const int w_bytes = p.ntaps * kchunks * g.b_tile_bytes;
+  const int fixed = 8 * 14 + 16 + EPI_WARPS * 32 * ST_PITCH * 4 + 1024;
+  int stages = (SMEM_LIMIT - fixed - w_bytes) / g.a_stage_bytes;
+  if (stages > 4) stages = 4;
+  if (stages < 2) return false;
+  g.stages = stages;
+  const long long tiles = (long long)((p.OW + 127) / 128) * p.OH * p.OB;
+  if (tiles <= 0 || tiles >= (1ll << 31)) return false;
+  g.total_tiles = (int)tiles;
+  return true;
+}
+
+}  // namespace
+
+bool tapgemm_ws_applicable(const TgParams& p) {
+  WsGeom g;
+  return ws_geometry(p, g);
+}
+
+int tapgemm_ws_launch(const TgParams& p, cudaStream_t stream) {
+  WsGeom g;
+  B200VC_REQUIRE(ws_geometry(p, g), "tapgemm_ws: descriptor is not a small-channel regular convolution");
+  const int kchunks = (p.Kc + KCHUNK - 1) / KCHUNK;
+  CUtensorMap tmA, tmW;
+  {
+    cuuint64_t dims[5], strides[4];
+    cuuint32_t box[5] = {KCHUNK, (cuuint32_t)g.BWh, (cuuint32_t)g.KH, 1, 1};
+    long long span = 1;
+    for (int i = 0; i < 5; ++i) {
+      dims[i] = (cuuint64_t)(p.a_dim[i] > 0 ? p.a_dim[i] : 1);
+      if (i > 0) {
+        long long st = p.a_stride[i];
+        if (p.a_dim[i] <= 1) st = ((span + 3) / 4) * 4;
+        strides[i - 1] = (cuuint64_t)st * 4ull;
+        span = st * (long long)dims[i];
+      } else {
+        span = (long long)dims[0];
+      }
+    }
+    int rc = encode_map_f32(&tmA, p.A, 5, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)p.Kc, (cuuint64_t)p.N, (cuuint64_t)p.ntaps};
+    cuuint64_t strides[2] = {(cuuint64_t)p.ldw * 4ull, (cuuint64_t)p.wstride * 4ull};
+    cuuint32_t box[3] = {KCHUNK, (cuuint32_t)g.Nr, 1};
+    int rc = encode_map_f32(&tmW, p.Wt, 3, dims, strides, box);
+    if (rc) return rc;
+  }
+  const int w_bytes = p.ntaps * kchunks * g.b_tile_bytes;
+  const int smem = w_bytes + g.stages * g.a_stage_bytes + 8 * 14 + 16 + EPI_WARPS * 32 * ST_PITCH * 4 + 1024;
+  static int configured = 0;
+  if (configured < smem) {
+    B200VC_CHECK_CUDA(cudaFuncSetAttribute(tapgemm_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    configured = SMEM_LIMIT;
+  }
+  const int grid = g.total_tiles < num_sms_ws() ? g.total_tiles : num_sms_ws();
+  tapgemm_ws_kernel<<<grid, NUM_THREADS, smem, stream>>>(tmA, tmW, p, g);
+  count_launch();
+  B200VC_LAUNCH_CHECK();
+  return kOk;
+}
+
+}  // namespace b200vc

@@ -19,7 +19,7 @@ import torch
 
 from . import _ffi
 from ._ffi import (ACT_EXP, ACT_GELU, ACT_LRELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH,
-                   BACKEND_SIMT, BACKEND_TC, BACKEND_TC_V1, MAX_TAPS, TapGemmParams)
+                   BACKEND_SIMT, BACKEND_TC, BACKEND_TC_TILE, BACKEND_TC_V1, BACKEND_TC_WS, MAX_TAPS, TapGemmParams)
 
 __all__ = [
     "View", "Weights", "Out", "Epi", "TapGemm", "view", "out_of",
@@ -27,7 +27,7 @@ __all__ = [
     "conv2d_k2s2", "bmm_nt",
     "pack_conv1d", "pack_convt1d", "pack_conv2d", "pack_convt2d",
     "ACT_NONE", "ACT_RELU", "ACT_LRELU", "ACT_GELU", "ACT_TANH", "ACT_SIGMOID", "ACT_EXP",
-    "BACKEND_SIMT", "BACKEND_TC", "BACKEND_TC_V1",
+    "BACKEND_SIMT", "BACKEND_TC", "BACKEND_TC_V1", "BACKEND_TC_TILE", "BACKEND_TC_WS",
 ]
 
 
@@ -234,13 +234,16 @@ class TapGemm:
             self._tc_ok = bool(_ffi.lib().b200vc_tapgemm_tc_supported(C.byref(self.params)))
         return self._tc_ok
 
+    def ws_applicable(self) -> bool:
+        return bool(_ffi.lib().b200vc_tapgemm_ws_applicable(C.byref(self.params)))
+
     def flops(self) -> int:
         p = self.params
         return 2 * p.OW * p.OH * p.OB * p.N * p.Kc * p.ntaps
 
     def __call__(self, stream: Optional[int] = None, backend: Optional[int] = None):
         be = self.backend if backend is None else backend
-        if be in (BACKEND_TC, BACKEND_TC_V1) and not self.tc_supported():
+        if be in (BACKEND_TC, BACKEND_TC_V1, BACKEND_TC_TILE) and not self.tc_supported():
             be = BACKEND_SIMT   # operand not TMA-addressable (e.g. C==1); still CUDA, still fp32-exact
         if stream is None:
             stream = torch.cuda.current_stream().cuda_stream

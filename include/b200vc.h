@@ -42,9 +42,12 @@ enum {
 /* which kernel family executes a tap-GEMM */
 enum {
   B200VC_BACKEND_SIMT_FP32 = 0, /* exact fp32 FMA kernel                      */
-  B200VC_BACKEND_TC_TF32 = 1,   /* tcgen05.mma kind::tf32, TMA-fed, TMEM accum: one tile per CTA, 2 CTAs/SM (tapgemm_tc.cu) */
-  B200VC_BACKEND_TC_TF32_PERSISTENT = 2 /* same math, persistent kernel with double-buffered TMEM (tapgemm_tc2.cu); measured
-                                            slower in round 1 (single epilogue per SM), kept for development */
+  B200VC_BACKEND_TC_TF32 = 1,   /* tcgen05.mma kind::tf32, TMA-fed, TMEM accumulators. Picks the weight-stationary +
+                                   halo kernel (tapgemm_ws.cu) for small-channel regular convolutions, else the
+                                   one-tile-per-CTA kernel (tapgemm_tc.cu)                                          */
+  B200VC_BACKEND_TC_TF32_PERSISTENT = 2, /* persistent double-buffered-TMEM variant (tapgemm_tc2.cu), development     */
+  B200VC_BACKEND_TC_TF32_TILE = 3,       /* force tapgemm_tc.cu                                                       */
+  B200VC_BACKEND_TC_TF32_WS = 4          /* force tapgemm_ws.cu (error if the descriptor does not qualify)            */
 };
 
 typedef struct b200vc_tap {
@@ -109,6 +112,8 @@ int64_t b200vc_sizeof_tapgemm_params(void);
 int b200vc_tapgemm(const b200vc_tapgemm_params* p, int backend, void* stream);
 /* 1 when the descriptor satisfies the TMA alignment rules of the tcgen05 path */
 int b200vc_tapgemm_tc_supported(const b200vc_tapgemm_params* p);
+/* 1 when the descriptor is a small-channel regular convolution the weight-stationary kernel handles */
+int b200vc_tapgemm_ws_applicable(const b200vc_tapgemm_params* p);
 
 /* ---- row / elementwise kernels (fp32, HBM-bound) ---- */
 

@@ -8,7 +8,8 @@ from aicovergen_b200 import tapgemm as tg
 
 pytestmark = pytest.mark.gpu
 
-BACKENDS = [("simt", tg.BACKEND_SIMT, 2e-5), ("tc", tg.BACKEND_TC, 2e-3), ("tc1", tg.BACKEND_TC_V1, 2e-3)]
+BACKENDS = [("simt", tg.BACKEND_SIMT, 2e-5), ("tc", tg.BACKEND_TC, 2e-3), ("tile", tg.BACKEND_TC_TILE, 2e-3),
+            ("persist", tg.BACKEND_TC_V1, 2e-3)]
 
 
 def rel_rms(a, b):
@@ -112,7 +113,8 @@ def test_conv_transpose1d(bname, backend, tol, k, s, Ci, Co):
 
 
 @pytest.mark.parametrize("bname,backend,tol", BACKENDS)
-@pytest.mark.parametrize("B,H,W,Ci,Co", [(1, 64, 128, 16, 16), (2, 33, 32, 64, 128), (1, 96, 4, 256, 512), (1, 40, 256, 48, 96)])
+@pytest.mark.parametrize("B,H,W,Ci,Co", [(1, 64, 128, 16, 16), (2, 33, 32, 64, 128), (1, 96, 4, 256, 512), (1, 40, 256, 48, 96),
+                                        (2, 21, 384, 48, 48), (1, 9, 200, 64, 32)])
 def test_conv2d_3x3(bname, backend, tol, B, H, W, Ci, Co):
     g = torch.Generator().manual_seed(H + W + Ci)
     x = torch.randn(B, H, W, Ci, generator=g)
@@ -211,3 +213,18 @@ def test_overlapping_frames_dft(bname, backend, tol):
     tg.TapGemm(a, tg.weights(bd), [(0, 0, 0, 0, 0)], (nfr, 1, 1), tg.out_of(out), backend=backend)()
     torch.cuda.synchronize()
     check(out, ref, tol, f"dft-frames[{bname}]")
+
+
+def test_weight_stationary_kernel_is_selected_and_forced():
+    """Small-channel regular convolutions qualify for tapgemm_ws.cu; forcing it on a non-qualifying descriptor errors."""
+    x = torch.randn(1000, 64, device="cuda")
+    w = torch.randn(7, 64, 64, device="cuda")
+    out = torch.empty(1000, 64, device="cuda")
+    op = tg.conv1d(x, w, out, dilation=3)
+    assert op.ws_applicable()
+    op(backend=tg.BACKEND_TC_WS)
+    torch.cuda.synchronize()
+    big = tg.conv1d(torch.randn(1000, 256, device="cuda"), torch.randn(3, 256, 256, device="cuda"), torch.empty(1000, 256, device="cuda"))
+    assert not big.ws_applicable()
+    with pytest.raises(RuntimeError):
+        big(backend=tg.BACKEND_TC_WS)

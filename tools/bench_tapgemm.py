@@ -30,7 +30,7 @@ def main():
     ap.add_argument("--simt", action="store_true")
     ap.add_argument("--out", default="gpurun_out/bench_tapgemm.jsonl")
     args = ap.parse_args()
-    backends = [("tc2", tg.BACKEND_TC), ("tc1", tg.BACKEND_TC_V1)] + ([("simt", tg.BACKEND_SIMT)] if args.simt else [])
+    backends = [("auto", tg.BACKEND_TC), ("tile", tg.BACKEND_TC_TILE)] + ([("simt", tg.BACKEND_SIMT)] if args.simt else [])
     shapes = [
         # name, T, Cin, Cout, k, dil
         ("voc.s1 C256 k3", 65980, 256, 256, 3, 1),
@@ -60,6 +60,24 @@ def main():
                 rec = dict(shape=name, backend=bname, ms=ms, tflops=fl / ms / 1e9, gbs=by / ms / 1e6)
                 print(json.dumps(rec), flush=True)
                 f.write(json.dumps(rec) + "\n")
+        main2d(f)
+
+
+def main2d(f):
+    """MDX-style 3x3 convolutions (NHWC), the layers that dominate the separation pass."""
+    for name, B, H, W, C in [("mdx.l0 2d c48", 1, 256, 3072, 48), ("mdx.l1 2d c96", 1, 128, 1536, 96), ("mdx.l3 2d c192", 2, 32, 384, 192)]:
+        x = torch.randn(B, H, W, C, device="cuda")
+        w = torch.randn(9, C, C, device="cuda") / (9 * C) ** 0.5
+        b = torch.randn(C, device="cuda")
+        out = torch.empty(B, H, W, C, device="cuda")
+        for bname, be in [("auto", tg.BACKEND_TC), ("tile", tg.BACKEND_TC_TILE)]:
+            op = tg.conv2d(x, w, out, 3, 3, (1, 1), tg.Epi(bias=b, act_pre=tg.ACT_RELU), backend=be)
+            ms = timeit(op)
+            fl = 2.0 * B * H * W * C * C * 9
+            by = 8.0 * B * H * W * C
+            rec = dict(shape=name, backend=bname, ms=ms, tflops=fl / ms / 1e9, gbs=by / ms / 1e6, ws=op.ws_applicable())
+            print(json.dumps(rec), flush=True)
+            f.write(json.dumps(rec) + "\n")
 
 
 if __name__ == "__main__":
