@@ -128,6 +128,114 @@ __device__ __forceinline__ void tg_store4(const TgParams& p, const TgRow& r, int
   }
 }
 
+// Activation over a register array; the switch is warp-uniform so it costs one branch per group, not per element.
+template <int NV>
+__device__ __forceinline__ void tg_act_vec(float (&v)[NV], int act, float prm) {
+  switch (act) {
+    case ACT_NONE: break;
+    case ACT_RELU:
+#pragma unroll
+      for (int j = 0; j < NV; ++j) v[j] = fmaxf(v[j], 0.f);
+      break;
+    case ACT_LRELU:
+#pragma unroll
+      for (int j = 0; j < NV; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * prm;
+      break;
+    default:
+#pragma unroll
+      for (int j = 0; j < NV; ++j) v[j] = apply_act(v[j], act, prm);
+      break;
+  }
+}
+
+// Store 16 consecutive n (n % 16 == 0) of one GEMM row straight from accumulator registers: the epilogue the tcgen05
+// kernels use (one thread owns one TMEM lane = one row).  Every stage is a pass over the register array behind a
+// warp-uniform test, so a plain bias+activation epilogue is ~5 instructions per element.  Same arithmetic, in the same
+// order, as tg_epi1.
+__device__ __forceinline__ void tg_store16(const TgParams& p, const TgRow& r, int n, const uint32_t* acc) {
+  if (!r.valid || n >= p.N) return;
+  if (!((p.vec4 & 2) && n + 15 < p.N)) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 4)
+      tg_store4(p, r, n + j, make_float4(__uint_as_float(acc[j]), __uint_as_float(acc[j + 1]), __uint_as_float(acc[j + 2]),
+                                         __uint_as_float(acc[j + 3])));
+    return;
+  }
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
+  if (p.bias) {
+    if (p.bias_per_row) {
+      const float bb = __ldg(p.bias + r.brow);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] += bb;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
+        v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
+      }
+    }
+  }
+  tg_act_vec(v, p.act_pre, p.act_pre_p);
+  if (p.row_scale) {
+    const float rs = __ldg(p.row_scale + r.brow);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] *= rs;
+  }
+  if (p.res) {
+    const float4* rp = reinterpret_cast<const float4*>(p.res + r.r_off + n);
+    if (p.res_op & 1) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 rr = rp[j];
+        v[4 * j] *= rr.x; v[4 * j + 1] *= rr.y; v[4 * j + 2] *= rr.z; v[4 * j + 3] *= rr.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 rr = rp[j];
+        v[4 * j] += rr.x; v[4 * j + 1] += rr.y; v[4 * j + 2] += rr.z; v[4 * j + 3] += rr.w;
+      }
+    }
+  }
+  if (p.scale != 1.f) {
+    const float sc = p.scale;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] *= sc;
+  }
+  if (p.res2) {
+    const float4* rp = reinterpret_cast<const float4*>(p.res2 + r.o_off + n);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 rr = rp[j];
+      v[4 * j] += rr.x; v[4 * j + 1] += rr.y; v[4 * j + 2] += rr.z; v[4 * j + 3] += rr.w;
+    }
+  }
+  tg_act_vec(v, p.act_post, p.act_post_p);
+  float4* op = reinterpret_cast<float4*>(p.out + r.o_off + n);
+  if (p.round_tf32 & 1) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      op[j] = make_float4(round_tf32(v[4 * j]), round_tf32(v[4 * j + 1]), round_tf32(v[4 * j + 2]), round_tf32(v[4 * j + 3]));
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  }
+  if (p.out2) {
+    tg_act_vec(v, p.act2, p.act2_p);
+    float4* op2 = reinterpret_cast<float4*>(p.out2 + r.o_off + n);
+    if (p.round_tf32 & 2) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        op2[j] = make_float4(round_tf32(v[4 * j]), round_tf32(v[4 * j + 1]), round_tf32(v[4 * j + 2]), round_tf32(v[4 * j + 3]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) op2[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+  }
+}
+
 // Host-side launchers (tapgemm_simt.cu / tapgemm_tc.cu).
 int tapgemm_simt_launch(const TgParams& p, cudaStream_t stream);
 int tapgemm_tc_launch(const TgParams& p, cudaStream_t stream);    // v1: one tile per CTA

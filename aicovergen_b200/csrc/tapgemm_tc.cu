@@ -221,12 +221,8 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (n0 + c0 >= p.N) break;            // warp-uniform
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        tg_store4(p, r, n0 + c0 + j,
-                  make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                              __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
-      }
+      tg_store16(p, r, n0 + c0, v);
+      tg_store16(p, r, n0 + c0 + 16, v + 16);
     }
   }
 

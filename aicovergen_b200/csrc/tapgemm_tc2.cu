@@ -95,13 +95,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-struct RowInfo {
-  long long o_off;
-  long long r_off;
-  int brow;
-  int valid;
-};
-
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
@@ -111,7 +104,6 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   constexpr uint32_t TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;     // power of two for BN in {32,64,128,256}
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
   auto a_stage = [&](int s) { return smem_base + s * STAGE_BYTES; };
   auto b_stage = [&](int s) { return smem_base + s * STAGE_BYTES + A_STAGE_BYTES; };
@@ -120,9 +112,6 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
-  // epilogue staging (generic pointers): per warp a 32 x 33 fp32 transpose tile + 32 row records
-  float* stage_f = reinterpret_cast<float*>(smem_gen + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 6));
-  RowInfo* rows_s = reinterpret_cast<RowInfo*>(stage_f + EPI_WARPS * 32 * 33);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ntw = (p.OW + p.BW - 1) / p.BW;
@@ -217,59 +206,23 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int q = warp & 3;
-    const int ew = warp - 2;                       // staging slot
-    float* st = stage_f + ew * 32 * 33;
-    RowInfo* ri = rows_s + ew * 32;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       int w0, h0, tb, n0;
       tile_coords(tile, w0, h0, tb, n0);
-      {
-        const int m = q * 32 + lane;
-        const TgRow r = tg_row(p, tb, h0 + m / p.BW, w0 + m % p.BW);
-        ri[lane].o_off = r.o_off;
-        ri[lane].r_off = r.r_off;
-        ri[lane].brow = r.brow;
-        ri[lane].valid = r.valid ? 1 : 0;
-      }
+      const int m = q * 32 + lane;
+      const TgRow r = tg_row(p, tb, h0 + m / p.BW, w0 + m % p.BW);
       const int acc = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
       mbar_wait(tfull_bar(acc), use & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      __syncwarp();
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         if (n0 + c0 >= p.N) break;                 // warp-uniform
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), v);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) st[lane * 33 + j] = __uint_as_float(v[j]);
-        __syncwarp();
-        const int n = n0 + c0 + lane;
-        const bool n_ok = n < p.N;
-        const float bias_n = (p.bias && !p.bias_per_row && n_ok) ? __ldg(p.bias + n) : 0.f;
-#pragma unroll 4
-        for (int r = 0; r < 32; ++r) {
-          const RowInfo info = ri[r];
-          if (!info.valid || !n_ok) continue;
-          float x = st[r * 33 + lane];
-          if (p.bias) x += p.bias_per_row ? __ldg(p.bias + info.brow) : bias_n;
-          x = apply_act(x, p.act_pre, p.act_pre_p);
-          if (p.row_scale) x *= __ldg(p.row_scale + info.brow);
-          if (p.res) {
-            const float rr = p.res[info.r_off + n];
-            x = (p.res_op & 1) ? x * rr : x + rr;
-          }
-          x *= p.scale;
-          if (p.res2) x += p.res2[info.o_off + n];
-          x = apply_act(x, p.act_post, p.act_post_p);
-          p.out[info.o_off + n] = (p.round_tf32 & 1) ? round_tf32(x) : x;
-          if (p.out2) {
-            const float x2 = apply_act(x, p.act2, p.act2_p);
-            p.out2[info.o_off + n] = (p.round_tf32 & 2) ? round_tf32(x2) : x2;
-          }
-        }
-        __syncwarp();
+        tg_store16(p, r, n0 + c0, v);
+        tg_store16(p, r, n0 + c0 + 16, v + 16);
       }
       // all TMEM reads of this accumulator stage are complete (tcgen05.wait::ld inside tmem_ld32)
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -288,8 +241,7 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 template <int BN, int STAGES>
 int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmW, const TgParams& p, int ntiles_n, int total_tiles,
                int grid, cudaStream_t stream) {
-  constexpr int smem = STAGES * (A_STAGE_BYTES + BN * 128) + 8 * (2 * STAGES + 6) + EPI_WARPS * 32 * 33 * 4 +
-                       EPI_WARPS * 32 * (int)sizeof(RowInfo) + 1024;
+  constexpr int smem = STAGES * (A_STAGE_BYTES + BN * 128) + 8 * (2 * STAGES + 6) + 1024;
   static_assert(smem <= 227 * 1024, "shared memory budget");
   static bool configured = false;
   if (!configured) {

@@ -26,7 +26,6 @@ namespace {
 constexpr int KCHUNK = 32;
 constexpr int EPI_WARPS = 4;                       // one per TMEM lane quarter; each walks the 32-column groups
 constexpr int NUM_THREADS = 64 + EPI_WARPS * 32;   // warp0 TMA, warp1 MMA, warps 2..5 epilogue
-constexpr int ST_PITCH = 36;                       // floats per staged row (16-byte aligned, conflict-free float4)
 
 struct WsGeom {
   int KH, KW, dil_w, dil_h, pad_w, pad_h;
@@ -110,6 +109,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tapgemm_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                   const __grid_constant__ TgParams p, const WsGeom g) {
@@ -118,7 +130,6 @@ tapgemm_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const int kchunks = (p.Kc + KCHUNK - 1) / KCHUNK;
   const int w_bytes = p.ntaps * kchunks * g.b_tile_bytes;
   const uint32_t w_base = smem_base;                              // resident weights
@@ -131,8 +142,6 @@ tapgemm_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   auto tfull_bar = [&](int a) { return bar_base + 8u * (9 + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (11 + a); };
   const uint32_t tmem_slot = bar_base + 8u * 13;
-  const int misc_off = w_bytes + g.stages * g.a_stage_bytes + 8 * 14;
-  float* stage_f = reinterpret_cast<float*>(smem_gen + ((misc_off + 15) & ~15));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ntw = (p.OW + 127) / 128;
@@ -227,93 +236,35 @@ tapgemm_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int q = warp & 3;                         // TMEM lane quarter
-    float* st = stage_f + (warp - 2) * 32 * ST_PITCH;
     int ti = 0;
     for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++ti) {
       int w0, h0, tb;
       tile_coords(tile, w0, h0, tb);
+      const TgRow r = tg_row(p, tb, h0, w0 + q * 32 + lane);
       const int acc = ti & 1;
       const uint32_t use = (uint32_t)(ti >> 1);
       mbar_wait(tfull_bar(acc), use & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int ngroups = (p.N + 31) / 32;
-      for (int cg = 0; cg < ngroups; ++cg) {
-        const int c0 = cg * 32;
+      if (ngroups == 2) {
+        // both column groups in flight before the first wait; the accumulator goes back to the MMA warp at once
+        uint32_t v0[32], v1[32];
+        tmem_ld32_async(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TM_COLS_PER_ACC), v0);
+        tmem_ld32_async(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TM_COLS_PER_ACC + 32), v1);
+        tmem_ld_wait();
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        tg_store16(p, r, 0, v0);
+        tg_store16(p, r, 16, v0 + 16);
+        tg_store16(p, r, 32, v1);
+        tg_store16(p, r, 48, v1 + 16);
+      } else {
         uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TM_COLS_PER_ACC + c0), v);
-        if (cg == ngroups - 1) {
-          // accumulator stage fully read -> hand it back to the MMA warp before touching global memory
-          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          if (lane == 0) mbar_arrive(tempty_bar(acc));
-        }
-#pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(&st[lane * ST_PITCH + j]) =
-              make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-        __syncwarp();
-        const int cl = (lane & 7) * 4;              // 8 lanes x float4 = one 128-byte row segment
-        const int n = c0 + cl;
-        const bool vec = (p.vec4 & 2) && (n + 3 < p.N);
-        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias && !p.bias_per_row) {
-          if (n + 0 < p.N) bias4.x = __ldg(p.bias + n + 0);
-          if (n + 1 < p.N) bias4.y = __ldg(p.bias + n + 1);
-          if (n + 2 < p.N) bias4.z = __ldg(p.bias + n + 2);
-          if (n + 3 < p.N) bias4.w = __ldg(p.bias + n + 3);
-        }
-#pragma unroll 2
-        for (int it8 = 0; it8 < 8; ++it8) {
-          const int r = it8 * 4 + (lane >> 3);
-          const TgRow info = tg_row(p, tb, h0, w0 + q * 32 + r);
-          if (!info.valid || n >= p.N) continue;
-          const float4 a = *reinterpret_cast<const float4*>(&st[r * ST_PITCH + cl]);
-          float x[4] = {a.x + bias4.x, a.y + bias4.y, a.z + bias4.z, a.w + bias4.w};
-          if (p.bias && p.bias_per_row) {
-            const float bb = __ldg(p.bias + info.brow);
-            x[0] += bb; x[1] += bb; x[2] += bb; x[3] += bb;
-          }
-          const float rs = p.row_scale ? __ldg(p.row_scale + info.brow) : 1.f;
-          float rr[4] = {0.f, 0.f, 0.f, 0.f}, r2[4] = {0.f, 0.f, 0.f, 0.f};
-          if (p.res) {
-            if (vec) {
-              const float4 t = *reinterpret_cast<const float4*>(p.res + info.r_off + n);
-              rr[0] = t.x; rr[1] = t.y; rr[2] = t.z; rr[3] = t.w;
-            } else {
-              for (int e = 0; e < 4; ++e) if (n + e < p.N) rr[e] = p.res[info.r_off + n + e];
-            }
-          }
-          if (p.res2) {
-            if (vec) {
-              const float4 t = *reinterpret_cast<const float4*>(p.res2 + info.o_off + n);
-              r2[0] = t.x; r2[1] = t.y; r2[2] = t.z; r2[3] = t.w;
-            } else {
-              for (int e = 0; e < 4; ++e) if (n + e < p.N) r2[e] = p.res2[info.o_off + n + e];
-            }
-          }
-          float y[4], y2[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float t = apply_act(x[e], p.act_pre, p.act_pre_p) * rs;
-            if (p.res) t = (p.res_op & 1) ? t * rr[e] : t + rr[e];
-            t *= p.scale;
-            t += r2[e];
-            t = apply_act(t, p.act_post, p.act_post_p);
-            y2[e] = apply_act(t, p.act2, p.act2_p);
-            y[e] = (p.round_tf32 & 1) ? round_tf32(t) : t;
-            if (p.round_tf32 & 2) y2[e] = round_tf32(y2[e]);
-          }
-          if (vec) {
-            *reinterpret_cast<float4*>(p.out + info.o_off + n) = make_float4(y[0], y[1], y[2], y[3]);
-            if (p.out2) *reinterpret_cast<float4*>(p.out2 + info.o_off + n) = make_float4(y2[0], y2[1], y2[2], y2[3]);
-          } else {
-            for (int e = 0; e < 4; ++e)
-              if (n + e < p.N) {
-                p.out[info.o_off + n + e] = y[e];
-                if (p.out2) p.out2[info.o_off + n + e] = y2[e];
-              }
-          }
-        }
-        __syncwarp();                               // staging tile is reused by the next column group / tile
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TM_COLS_PER_ACC), v);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        tg_store16(p, r, 0, v);
+        tg_store16(p, r, 16, v + 16);
       }
     }
   }
@@ -367,7 +318,7 @@ bool ws_geometry(const TgParams& p, WsGeom& g) {
   g.a_stage_bytes = ((KH * g.BWh * 128 + 1023) / 1024) * 1024;   // 1024-aligned stages (swizzle atom = 8 rows x 128 B)
   const int kchunks = (p.Kc + KCHUNK - 1) / KCHUNK;
   const int w_bytes = p.ntaps * kchunks * g.b_tile_bytes;
-  const int fixed = 8 * 14 + 16 + EPI_WARPS * 32 * ST_PITCH * 4 + 1024;
+  const int fixed = 8 * 14 + 16 + 1024;
   int stages = (SMEM_LIMIT - fixed - w_bytes) / g.a_stage_bytes;
   if (stages > 4) stages = 4;
   if (stages < 2) return false;
@@ -416,7 +367,7 @@ int tapgemm_ws_launch(const TgParams& p, cudaStream_t stream) {
     if (rc) return rc;
   }
   const int w_bytes = p.ntaps * kchunks * g.b_tile_bytes;
-  const int smem = w_bytes + g.stages * g.a_stage_bytes + 8 * 14 + 16 + EPI_WARPS * 32 * ST_PITCH * 4 + 1024;
+  const int smem = w_bytes + g.stages * g.a_stage_bytes + 8 * 14 + 16 + 1024;
   static int configured = 0;
   if (configured < smem) {
     B200VC_CHECK_CUDA(cudaFuncSetAttribute(tapgemm_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));

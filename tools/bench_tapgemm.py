@@ -30,7 +30,7 @@ def main():
     ap.add_argument("--simt", action="store_true")
     ap.add_argument("--out", default="gpurun_out/bench_tapgemm.jsonl")
     args = ap.parse_args()
-    backends = [("auto", tg.BACKEND_TC), ("tile", tg.BACKEND_TC_TILE)] + ([("simt", tg.BACKEND_SIMT)] if args.simt else [])
+    backends = [("auto", tg.BACKEND_TC), ("tile", tg.BACKEND_TC_TILE), ("persist", tg.BACKEND_TC_V1)] + ([("simt", tg.BACKEND_SIMT)] if args.simt else [])
     shapes = [
         # name, T, Cin, Cout, k, dil
         ("voc.s1 C256 k3", 65980, 256, 256, 3, 1),
@@ -70,7 +70,7 @@ def main2d(f):
         w = torch.randn(9, C, C, device="cuda") / (9 * C) ** 0.5
         b = torch.randn(C, device="cuda")
         out = torch.empty(B, H, W, C, device="cuda")
-        for bname, be in [("auto", tg.BACKEND_TC), ("tile", tg.BACKEND_TC_TILE)]:
+        for bname, be in [("auto", tg.BACKEND_TC), ("tile", tg.BACKEND_TC_TILE), ("persist", tg.BACKEND_TC_V1)]:
             op = tg.conv2d(x, w, out, 3, 3, (1, 1), tg.Epi(bias=b, act_pre=tg.ACT_RELU), backend=be)
             ms = timeit(op)
             fl = 2.0 * B * H * W * C * C * 9
