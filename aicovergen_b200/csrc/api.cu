@@ -37,8 +37,8 @@ int b200vc_tapgemm(const b200vc_tapgemm_params* p, int backend, void* stream) {
   B200VC_REQUIRE(p->OW >= 1 && p->OH >= 1 && p->OB >= 1, "tapgemm: empty output space");
   B200VC_REQUIRE(p->a_stride[0] == 1, "tapgemm: A must be channels-last (a_stride[0]==1)");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (backend == B200VC_BACKEND_TC_TF32)          // auto: weight-stationary kernel where it applies
-    return tapgemm_ws_applicable(*p) ? tapgemm_ws_launch(*p, s) : tapgemm_tc_launch(*p, s);
+  if (backend == B200VC_BACKEND_TC_TF32)          // auto: weight-stationary kernel where it applies, else persistent
+    return tapgemm_ws_applicable(*p) ? tapgemm_ws_launch(*p, s) : tapgemm_tc2_launch(*p, s);
   if (backend == B200VC_BACKEND_TC_TF32_PERSISTENT) return tapgemm_tc2_launch(*p, s);
   if (backend == B200VC_BACKEND_TC_TF32_TILE) return tapgemm_tc_launch(*p, s);
   if (backend == B200VC_BACKEND_TC_TF32_WS) return tapgemm_ws_launch(*p, s);

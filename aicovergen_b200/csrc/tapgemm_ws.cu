@@ -218,15 +218,21 @@ tapgemm_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const uint32_t ph = (it / g.stages) & 1;
           mbar_wait(full_bar(s), ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t a0 = a_stage(s);
-          for (int j = 0; j < p.ntaps; ++j) {
-            const int kh = j / g.KW, kw = j - kh * g.KW;
-            const uint32_t rowoff = (uint32_t)(kh * g.BWh + kw * g.dil_w);   // first row of this tap inside the halo box
-            const uint64_t adesc = make_smem_desc(a0 + rowoff * 128u);
-            const uint64_t bdesc = make_smem_desc(w_base + (uint32_t)((j * kchunks + kc) * g.b_tile_bytes));
+          // descriptors differ only in their 14-bit start-address field: walk it with adds (this loop runs on one thread)
+          uint64_t adesc_row = make_smem_desc(a_stage(s));
+          uint64_t bdesc = make_smem_desc(w_base + (uint32_t)(kc * g.b_tile_bytes));
+          const uint64_t b_step = (uint64_t)((kchunks * g.b_tile_bytes) >> 4);
+          const uint64_t a_kw_step = (uint64_t)(g.dil_w * 8), a_kh_step = (uint64_t)(g.BWh * 8);   // rows x 128 B >> 4
+          uint32_t accum = kc > 0 ? 1u : 0u;
+          for (int kh = 0; kh < g.KH; ++kh, adesc_row += a_kh_step) {
+            uint64_t adesc = adesc_row;
+            for (int kw = 0; kw < g.KW; ++kw, adesc += a_kw_step, bdesc += b_step) {
 #pragma unroll
-            for (int k = 0; k < KCHUNK / 8; ++k)
-              umma_tf32(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, (kc > 0 || j > 0 || k > 0) ? 1u : 0u);
+              for (int k = 0; k < KCHUNK / 8; ++k) {
+                umma_tf32(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, accum);
+                accum = 1u;
+              }
+            }
           }
           umma_commit(empty_bar(s));
         }

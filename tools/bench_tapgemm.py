@@ -12,7 +12,12 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from aicovergen_b200 import tapgemm as tg  # noqa: E402
 
 
-def timeit(fn, warm=3, iters=10):
+WARM, ITERS = 3, 10
+
+
+def timeit(fn, warm=None, iters=None):
+    warm = WARM if warm is None else warm
+    iters = ITERS if iters is None else iters
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
@@ -29,7 +34,12 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--simt", action="store_true")
     ap.add_argument("--out", default="gpurun_out/bench_tapgemm.jsonl")
+    ap.add_argument("--only", default="", help="substring filter on the shape name")
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--warm", type=int, default=3)
     args = ap.parse_args()
+    global WARM, ITERS
+    WARM, ITERS = args.warm, args.iters
     backends = [("auto", tg.BACKEND_TC), ("tile", tg.BACKEND_TC_TILE), ("persist", tg.BACKEND_TC_V1)] + ([("simt", tg.BACKEND_SIMT)] if args.simt else [])
     shapes = [
         # name, T, Cin, Cout, k, dil
@@ -48,6 +58,8 @@ def main():
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     with open(args.out, "w") as f:
         for name, T, Ci, Co, k, d in shapes:
+            if args.only not in name:
+                continue
             x = torch.randn(T, Ci, device="cuda")
             w = torch.randn(k, Co, Ci, device="cuda") / (Ci * k) ** 0.5
             b = torch.randn(Co, device="cuda")
@@ -60,12 +72,14 @@ def main():
                 rec = dict(shape=name, backend=bname, ms=ms, tflops=fl / ms / 1e9, gbs=by / ms / 1e6)
                 print(json.dumps(rec), flush=True)
                 f.write(json.dumps(rec) + "\n")
-        main2d(f)
+        main2d(f, args.only)
 
 
-def main2d(f):
+def main2d(f, only=""):
     """MDX-style 3x3 convolutions (NHWC), the layers that dominate the separation pass."""
     for name, B, H, W, C in [("mdx.l0 2d c48", 1, 256, 3072, 48), ("mdx.l1 2d c96", 1, 128, 1536, 96), ("mdx.l3 2d c192", 2, 32, 384, 192)]:
+        if only not in name:
+            continue
         x = torch.randn(B, H, W, C, device="cuda")
         w = torch.randn(9, C, C, device="cuda") / (9 * C) ** 0.5
         b = torch.randn(C, device="cuda")
