@@ -152,7 +152,9 @@ __device__ __forceinline__ void tg_act_vec(float (&v)[NV], int act, float prm) {
 // kernels use (one thread owns one TMEM lane = one row).  Every stage is a pass over the register array behind a
 // warp-uniform test, so a plain bias+activation epilogue is ~5 instructions per element.  Same arithmetic, in the same
 // order, as tg_epi1.
-__device__ __forceinline__ void tg_store16(const TgParams& p, const TgRow& r, int n, const uint32_t* acc) {
+// `pre_bias`: the 16 per-column biases already in registers (persistent kernels whose warps keep the same columns).
+__device__ __forceinline__ void tg_store16(const TgParams& p, const TgRow& r, int n, const uint32_t* acc,
+                                           const float* pre_bias = nullptr) {
   if (!r.valid || n >= p.N) return;
   if (!((p.vec4 & 2) && n + 15 < p.N)) {
 #pragma unroll
@@ -164,7 +166,10 @@ __device__ __forceinline__ void tg_store16(const TgParams& p, const TgRow& r, in
   float v[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
-  if (p.bias) {
+  if (pre_bias) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] += pre_bias[j];
+  } else if (p.bias) {
     if (p.bias_per_row) {
       const float bb = __ldg(p.bias + r.brow);
 #pragma unroll

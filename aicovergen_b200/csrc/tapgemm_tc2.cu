@@ -3,9 +3,9 @@
 //   grid  = min(#tiles, #SMs) CTAs, each loops over output tiles (n-tile fastest so neighbouring CTAs share the A box in L2)
 //   warp 0 : TMA producer — the shared-memory ring keeps filling across tile boundaries
 //   warp 1 : TMEM allocator (2 x BN columns) + single-thread tcgen05.mma issuer; tcgen05.commit -> smem-empty / tmem-full
-//   warps 2-5 : epilogue — tcgen05.ld of accumulator stage `it & 1` while the MMA warp already fills the other stage;
-//               the 32x32 fp32 block of each warp is transposed through padded shared memory so every global
-//               store / residual load is a full 128-byte line (the v1 kernel wrote 16 B per row per instruction)
+//   warps 2-9 : epilogue — tcgen05.ld of accumulator stage `it & 1` while the MMA warp already fills the other stage;
+//               warp = (TMEM lane quarter, even/odd 32-column group), two warps per SM sub-partition, each thread
+//               finishing its row's columns in registers (tg_store16)
 //
 // Same descriptor, same epilogue semantics as tapgemm.cuh (scalar form tg_epi1).
 #include "tapgemm.cuh"
@@ -20,8 +20,8 @@ namespace {
 
 constexpr int KCHUNK = 32;
 constexpr int A_STAGE_BYTES = TG_TILE_M * 128;
-constexpr int NUM_THREADS = 192;
-constexpr int EPI_WARPS = 4;
+constexpr int EPI_WARPS = 8;
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -128,7 +128,7 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), EPI_WARPS);
+      mbar_init(tempty_bar(a), BN >= 64 ? EPI_WARPS : 4);   // BN == 32: only the first column group has work
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -206,7 +206,9 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int q = warp & 3;
+    const int cpar = (warp - 2) >> 2;              // this warp takes the 32-column groups with index % 2 == cpar
     int it = 0;
+    if (cpar * 32 < BN)
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       int w0, h0, tb, n0;
       tile_coords(tile, w0, h0, tb, n0);
@@ -217,7 +219,7 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       mbar_wait(tfull_bar(acc), use & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = cpar * 32; c0 < BN; c0 += 64) {
         if (n0 + c0 >= p.N) break;                 // warp-uniform
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), v);

@@ -9,8 +9,10 @@
 //     ([KH rows] x [128 + (KW-1)*dil] pixels x 32 ch); the taps are just row offsets of the UMMA A descriptor inside
 //     that box (the 128-byte swizzle is a function of absolute shared-memory address bits, so shifting the start
 //     address by whole 128-byte rows keeps TMA's layout and the descriptor's view consistent);
-//   * TMEM accumulators are double buffered so the epilogue of tile i overlaps the MMAs of tile i+1, and the epilogue
-//     transposes 32x32 blocks through shared memory so all global traffic is full 128-byte lines (float4 per lane).
+//   * TMEM accumulators are double buffered so the epilogue of tile i overlaps the MMAs of tile i+1; SIXTEEN epilogue
+//     warps (4 per SM sub-partition: lane quarter x 16-column group) keep the register-resident epilogue off the
+//     critical path (ncu r01: with 4 warps the kernel was latency-bound on the epilogue's own instruction stream),
+//     with the bias held in registers across tiles and tile coordinates advanced incrementally (no divisions).
 // L2->SM traffic per tile drops to the halo box only (100 KB instead of 432 KB for MDX c=48; 37 KB instead of 336 KB for
 // the vocoder's C=64 k=7 layers).
 #include "tapgemm.cuh"
@@ -24,8 +26,8 @@ int encode_map_f32(CUtensorMap* tm, const void* base, int rank, const cuuint64_t
 namespace {
 
 constexpr int KCHUNK = 32;
-constexpr int EPI_WARPS = 4;                       // one per TMEM lane quarter; each walks the 32-column groups
-constexpr int NUM_THREADS = 64 + EPI_WARPS * 32;   // warp0 TMA, warp1 MMA, warps 2..5 epilogue
+constexpr int EPI_WARPS = 16;                      // (TMEM lane quarter) x (16-column group)
+constexpr int NUM_THREADS = 64 + EPI_WARPS * 32;   // warp0 TMA, warp1 MMA, warps 2..17 epilogue
 
 struct WsGeom {
   int KH, KW, dil_w, dil_h, pad_w, pad_h;
@@ -122,6 +124,34 @@ __device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t (&r)[32
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Tile walker: tile = first + i * stride decomposed into (strip, row, batch) and advanced with carries.
+struct TileWalk {
+  int tw, h, b;        // current coordinates
+  int dw, dh, db;      // stride decomposition
+  int left;            // tiles still to process
+  __device__ __forceinline__ void init(int first, int stride, int total, int ntw, int OH) {
+    tw = first % ntw; int t = first / ntw; h = t % OH; b = t / OH;
+    dw = stride % ntw; t = stride / ntw; dh = t % OH; db = t / OH;
+    left = first < total ? (total - first + stride - 1) / stride : 0;
+  }
+  __device__ __forceinline__ void next(int ntw, int OH) {
+    tw += dw; if (tw >= ntw) { tw -= ntw; ++h; }
+    h += dh; if (h >= OH) { h -= OH; ++b; }
+    b += db;
+    --left;
+  }
+};
+
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tapgemm_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                   const __grid_constant__ TgParams p, const WsGeom g) {
@@ -156,7 +186,7 @@ tapgemm_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     mbar_init(w_bar, 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), EPI_WARPS);
+      mbar_init(tempty_bar(a), 4 * ((p.N + 15) / 16));   // one arrival per participating epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -170,14 +200,6 @@ tapgemm_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  auto tile_coords = [&](int tile, int& w0, int& h0, int& tb) {
-    const int tw = tile % ntw;
-    int r = tile / ntw;
-    h0 = r % p.OH;
-    tb = r / p.OH;
-    w0 = tw * 128;
-  };
-
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
@@ -188,15 +210,14 @@ tapgemm_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           tma_load_3d(w_base + (uint32_t)((j * kchunks + kc) * g.b_tile_bytes), &tmW, w_bar, kc * KCHUNK, 0, j);
       int it = 0;
       const uint32_t a_tx = (uint32_t)(g.KH * g.BWh * 128);
-      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
-        int w0, h0, tb;
-        tile_coords(tile, w0, h0, tb);
+      TileWalk tk;
+      for (tk.init(blockIdx.x, gridDim.x, g.total_tiles, ntw, p.OH); tk.left > 0; tk.next(ntw, p.OH)) {
         for (int kc = 0; kc < kchunks; ++kc, ++it) {
           const int s = it % g.stages;
           const uint32_t ph = (it / g.stages) & 1;
           mbar_wait(empty_bar(s), ph ^ 1u);
           mbar_expect_tx(full_bar(s), a_tx);
-          tma_load_5d(a_stage(s), &tmA, full_bar(s), kc * KCHUNK, w0 - g.pad_w, h0 - g.pad_h, tb, 0);
+          tma_load_5d(a_stage(s), &tmA, full_bar(s), kc * KCHUNK, tk.tw * 128 - g.pad_w, tk.h - g.pad_h, tk.b, 0);
         }
       }
     }
@@ -207,7 +228,8 @@ tapgemm_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_wait(w_bar, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       int it = 0, ti = 0;
-      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++ti) {
+      const int my_tiles = (int)blockIdx.x < g.total_tiles ? (g.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+      for (; ti < my_tiles; ++ti) {
         const int acc = ti & 1;
         const uint32_t use = (uint32_t)(ti >> 1);
         mbar_wait(tempty_bar(acc), (use & 1u) ^ 1u);
@@ -241,36 +263,27 @@ tapgemm_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
-    const int q = warp & 3;                         // TMEM lane quarter
-    int ti = 0;
-    for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++ti) {
-      int w0, h0, tb;
-      tile_coords(tile, w0, h0, tb);
-      const TgRow r = tg_row(p, tb, h0, w0 + q * 32 + lane);
-      const int acc = ti & 1;
-      const uint32_t use = (uint32_t)(ti >> 1);
-      mbar_wait(tfull_bar(acc), use & 1u);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int ngroups = (p.N + 31) / 32;
-      if (ngroups == 2) {
-        // both column groups in flight before the first wait; the accumulator goes back to the MMA warp at once
-        uint32_t v0[32], v1[32];
-        tmem_ld32_async(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TM_COLS_PER_ACC), v0);
-        tmem_ld32_async(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TM_COLS_PER_ACC + 32), v1);
-        tmem_ld_wait();
+    const int q = warp & 3;                         // TMEM lane quarter this warp may read
+    const int n = ((warp - 2) >> 2) * 16;           // its 16-column group
+    if (n < p.N) {
+      float bias16[16];
+      const bool pre_bias = p.bias && !p.bias_per_row && (p.vec4 & 2) && n + 15 < p.N;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) bias16[j] = pre_bias ? __ldg(p.bias + n + j) : 0.f;
+      int ti = 0;
+      TileWalk tk;
+      for (tk.init(blockIdx.x, gridDim.x, g.total_tiles, ntw, p.OH); tk.left > 0; tk.next(ntw, p.OH), ++ti) {
+        const TgRow r = tg_row(p, tk.b, tk.h, tk.tw * 128 + q * 32 + lane);
+        const int acc = ti & 1;
+        const uint32_t use = (uint32_t)(ti >> 1);
+        mbar_wait(tfull_bar(acc), use & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TM_COLS_PER_ACC + n), v);
+        // registers hold the data: hand the accumulator back to the MMA warp before touching global memory
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         if (lane == 0) mbar_arrive(tempty_bar(acc));
-        tg_store16(p, r, 0, v0);
-        tg_store16(p, r, 16, v0 + 16);
-        tg_store16(p, r, 32, v1);
-        tg_store16(p, r, 48, v1 + 16);
-      } else {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TM_COLS_PER_ACC), v);
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        if (lane == 0) mbar_arrive(tempty_bar(acc));
-        tg_store16(p, r, 0, v);
-        tg_store16(p, r, 16, v + 16);
+        tg_store16(p, r, n, v, pre_bias ? bias16 : nullptr);
       }
     }
   }
