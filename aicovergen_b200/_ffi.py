@@ -53,6 +53,14 @@ class TapGemmParams(C.Structure):
         ("r_sb", C.c_int64),
         ("r_sh", C.c_int64),
         ("r_sw", C.c_int64),
+        ("o_sn", C.c_int64),
+        ("r_sn", C.c_int64),
+        ("o2_sb", C.c_int64),
+        ("o2_sh", C.c_int64),
+        ("o2_sw", C.c_int64),
+        ("o2_sn", C.c_int64),
+        ("out2_own", C.c_int32),
+        ("row_scale_pre", C.c_void_p),
         ("bias", C.c_void_p),
         ("bias_per_row", C.c_int32),
         ("act_pre", C.c_int32),

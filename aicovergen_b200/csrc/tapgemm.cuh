@@ -32,9 +32,10 @@ using TgParams = b200vc_tapgemm_params;
 
 // One GEMM row's addressing state.
 struct TgRow {
-  long long o_off;   // offset into out/out2/res2 (n added later)
-  long long r_off;   // offset into res
-  int brow;          // index for per-row bias
+  long long o_off;   // offset into out/res2 (n * o_sn added later)
+  long long r_off;   // offset into res (n * r_sn added later)
+  long long o2_off;  // offset into out2 (n * its n-stride added later)
+  int brow;          // index for per-row bias / row scales
   bool valid;
 };
 
@@ -47,38 +48,52 @@ __device__ __forceinline__ TgRow tg_row(const TgParams& p, int b, int h, int w) 
   // residual #1 is addressed by the GEMM pixel, or by the mapped output pixel when res_op bit1 is set
   if (p.res_op & 2) r.r_off = (long long)b * p.r_sb + (long long)mh * p.r_sh + (long long)mw * p.r_sw;
   else r.r_off = (long long)b * p.r_sb + (long long)h * p.r_sh + (long long)w * p.r_sw;
+  r.o2_off = p.out2_own ? (long long)b * p.o2_sb + (long long)mh * p.o2_sh + (long long)mw * p.o2_sw : r.o_off;
   r.brow = h * p.OW + w;
   return r;
 }
 
 __device__ __forceinline__ float tg_epi1(const TgParams& p, const TgRow& r, int n, float acc) {
   float v = acc;
+  if (p.row_scale_pre) v *= __ldg(p.row_scale_pre + r.brow);
   if (p.bias) v += p.bias_per_row ? __ldg(p.bias + r.brow) : __ldg(p.bias + n);
   v = apply_act(v, p.act_pre, p.act_pre_p);
   if (p.row_scale) v *= __ldg(p.row_scale + r.brow);
-  if (p.res) { const float rr = p.res[r.r_off + n]; v = (p.res_op & 1) ? v * rr : v + rr; }
+  if (p.res) { const float rr = p.res[r.r_off + n * p.r_sn]; v = (p.res_op & 1) ? v * rr : v + rr; }
   v *= p.scale;
-  if (p.res2) v += p.res2[r.o_off + n];
+  if (p.res2) v += p.res2[r.o_off + n * p.o_sn];
   v = apply_act(v, p.act_post, p.act_post_p);
   return v;
 }
 
-// Scalar store of one element.
+// Scalar store of one element (any layout).
 __device__ __forceinline__ void tg_store1(const TgParams& p, const TgRow& r, int n, float acc) {
   if (!r.valid || n >= p.N) return;
   float v = tg_epi1(p, r, n, acc);
-  p.out[r.o_off + n] = (p.round_tf32 & 1) ? round_tf32(v) : v;
+  p.out[r.o_off + n * p.o_sn] = (p.round_tf32 & 1) ? round_tf32(v) : v;
   if (p.out2) {
     float v2 = apply_act(v, p.act2, p.act2_p);
-    p.out2[r.o_off + n] = (p.round_tf32 & 2) ? round_tf32(v2) : v2;
+    p.out2[r.o2_off + n * (p.out2_own ? p.o2_sn : p.o_sn)] = (p.round_tf32 & 2) ? round_tf32(v2) : v2;
   }
 }
 
-// Store 4 consecutive n (n % 4 == 0). Uses float4 when p.vec4 and fully in range.
+// vec4 bits (set by the host binding; a bit is also set when the tensor it talks about is absent)
+constexpr int TG_VEC_K = 1;      // k-vectorised operand loads (SIMT kernel)
+constexpr int TG_VEC_OUT = 2;    // out / res2 (and out2 when it shares out's layout): channels-last, 16-byte aligned
+constexpr int TG_VEC_BIAS = 4;   // per-column bias float4-loadable
+constexpr int TG_VEC_OUT2 = 8;   // own-layout out2 channels-last + aligned
+constexpr int TG_VEC_RES = 16;   // res channels-last + aligned
+constexpr int TG_VEC_ALL = TG_VEC_OUT | TG_VEC_BIAS | TG_VEC_OUT2 | TG_VEC_RES;
+
+// Store 4 consecutive n (n % 4 == 0). Uses float4 when every epilogue tensor is channels-last + aligned and in range.
 __device__ __forceinline__ void tg_store4(const TgParams& p, const TgRow& r, int n, float4 acc) {
   if (!r.valid || n >= p.N) return;
-  if ((p.vec4 & 2) && n + 3 < p.N) {
+  if ((p.vec4 & TG_VEC_ALL) == TG_VEC_ALL && n + 3 < p.N) {
     float v[4] = {acc.x, acc.y, acc.z, acc.w};
+    if (p.row_scale_pre) {
+      const float rs = __ldg(p.row_scale_pre + r.brow);
+      v[0] *= rs; v[1] *= rs; v[2] *= rs; v[3] *= rs;
+    }
     if (p.bias) {
       if (p.bias_per_row) {
         float bb = __ldg(p.bias + r.brow);
@@ -118,7 +133,7 @@ __device__ __forceinline__ void tg_store4(const TgParams& p, const TgRow& r, int
         v[i] = apply_act(v[i], p.act2, p.act2_p);
         if (p.round_tf32 & 2) v[i] = round_tf32(v[i]);
       }
-      *reinterpret_cast<float4*>(p.out2 + r.o_off + n) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(p.out2 + r.o2_off + n) = make_float4(v[0], v[1], v[2], v[3]);
     }
   } else {
     tg_store1(p, r, n + 0, acc.x);
@@ -148,6 +163,43 @@ __device__ __forceinline__ void tg_act_vec(float (&v)[NV], int act, float prm) {
   }
 }
 
+// 16 values <- 16 consecutive n at `ptr` with element stride `sn` (float4 loads when the caller knows sn == 1 and the
+// address is 16-byte aligned).
+__device__ __forceinline__ void tg_load16(float (&d)[16], const float* ptr, long long sn, bool vec) {
+  if (vec) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 t = reinterpret_cast<const float4*>(ptr)[j];
+      d[4 * j] = t.x; d[4 * j + 1] = t.y; d[4 * j + 2] = t.z; d[4 * j + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) d[j] = ptr[j * sn];
+  }
+}
+__device__ __forceinline__ void tg_put16(float* ptr, long long sn, bool vec, bool rnd, const float (&v)[16]) {
+  if (vec) {
+    float4* op = reinterpret_cast<float4*>(ptr);
+    if (rnd) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        op[j] = make_float4(round_tf32(v[4 * j]), round_tf32(v[4 * j + 1]), round_tf32(v[4 * j + 2]), round_tf32(v[4 * j + 3]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+  } else {
+    // transposed layouts: consecutive lanes own consecutive pixels, so each of these scalar stores is lane-coalesced
+    if (rnd) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) ptr[j * sn] = round_tf32(v[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) ptr[j * sn] = v[j];
+    }
+  }
+}
+
 // Store 16 consecutive n (n % 16 == 0) of one GEMM row straight from accumulator registers: the epilogue the tcgen05
 // kernels use (one thread owns one TMEM lane = one row).  Every stage is a pass over the register array behind a
 // warp-uniform test, so a plain bias+activation epilogue is ~5 instructions per element.  Same arithmetic, in the same
@@ -156,16 +208,22 @@ __device__ __forceinline__ void tg_act_vec(float (&v)[NV], int act, float prm) {
 __device__ __forceinline__ void tg_store16(const TgParams& p, const TgRow& r, int n, const uint32_t* acc,
                                            const float* pre_bias = nullptr) {
   if (!r.valid || n >= p.N) return;
-  if (!((p.vec4 & 2) && n + 15 < p.N)) {
+  if (n + 15 >= p.N) {      // ragged tail of N: element-wise path with bounds checks
 #pragma unroll
     for (int j = 0; j < 16; j += 4)
       tg_store4(p, r, n + j, make_float4(__uint_as_float(acc[j]), __uint_as_float(acc[j + 1]), __uint_as_float(acc[j + 2]),
                                          __uint_as_float(acc[j + 3])));
     return;
   }
+  const bool vec = (p.vec4 & TG_VEC_OUT) != 0;
   float v[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
+  if (p.row_scale_pre) {
+    const float rs = __ldg(p.row_scale_pre + r.brow);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] *= rs;
+  }
   if (pre_bias) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] += pre_bias[j];
@@ -174,12 +232,15 @@ __device__ __forceinline__ void tg_store16(const TgParams& p, const TgRow& r, in
       const float bb = __ldg(p.bias + r.brow);
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] += bb;
-    } else {
+    } else if (p.vec4 & TG_VEC_BIAS) {
 #pragma unroll
       for (int j = 0; j < 16; j += 4) {
         const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
         v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
       }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] += __ldg(p.bias + n + j);
     }
   }
   tg_act_vec(v, p.act_pre, p.act_pre_p);
@@ -189,19 +250,14 @@ __device__ __forceinline__ void tg_store16(const TgParams& p, const TgRow& r, in
     for (int j = 0; j < 16; ++j) v[j] *= rs;
   }
   if (p.res) {
-    const float4* rp = reinterpret_cast<const float4*>(p.res + r.r_off + n);
+    float rr[16];
+    tg_load16(rr, p.res + r.r_off + n * p.r_sn, p.r_sn, (p.vec4 & TG_VEC_RES) != 0);
     if (p.res_op & 1) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float4 rr = rp[j];
-        v[4 * j] *= rr.x; v[4 * j + 1] *= rr.y; v[4 * j + 2] *= rr.z; v[4 * j + 3] *= rr.w;
-      }
+      for (int j = 0; j < 16; ++j) v[j] *= rr[j];
     } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float4 rr = rp[j];
-        v[4 * j] += rr.x; v[4 * j + 1] += rr.y; v[4 * j + 2] += rr.z; v[4 * j + 3] += rr.w;
-      }
+      for (int j = 0; j < 16; ++j) v[j] += rr[j];
     }
   }
   if (p.scale != 1.f) {
@@ -210,34 +266,17 @@ __device__ __forceinline__ void tg_store16(const TgParams& p, const TgRow& r, in
     for (int j = 0; j < 16; ++j) v[j] *= sc;
   }
   if (p.res2) {
-    const float4* rp = reinterpret_cast<const float4*>(p.res2 + r.o_off + n);
+    float rr[16];
+    tg_load16(rr, p.res2 + r.o_off + n * p.o_sn, p.o_sn, vec);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float4 rr = rp[j];
-      v[4 * j] += rr.x; v[4 * j + 1] += rr.y; v[4 * j + 2] += rr.z; v[4 * j + 3] += rr.w;
-    }
+    for (int j = 0; j < 16; ++j) v[j] += rr[j];
   }
   tg_act_vec(v, p.act_post, p.act_post_p);
-  float4* op = reinterpret_cast<float4*>(p.out + r.o_off + n);
-  if (p.round_tf32 & 1) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      op[j] = make_float4(round_tf32(v[4 * j]), round_tf32(v[4 * j + 1]), round_tf32(v[4 * j + 2]), round_tf32(v[4 * j + 3]));
-  } else {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-  }
+  tg_put16(p.out + r.o_off + n * p.o_sn, p.o_sn, vec, (p.round_tf32 & 1) != 0, v);
   if (p.out2) {
     tg_act_vec(v, p.act2, p.act2_p);
-    float4* op2 = reinterpret_cast<float4*>(p.out2 + r.o_off + n);
-    if (p.round_tf32 & 2) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        op2[j] = make_float4(round_tf32(v[4 * j]), round_tf32(v[4 * j + 1]), round_tf32(v[4 * j + 2]), round_tf32(v[4 * j + 3]));
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) op2[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-    }
+    const long long sn2 = p.out2_own ? p.o2_sn : p.o_sn;
+    tg_put16(p.out2 + r.o2_off + n * sn2, sn2, p.out2_own ? (p.vec4 & TG_VEC_OUT2) != 0 : vec, (p.round_tf32 & 2) != 0, v);
   }
 }
 

@@ -267,7 +267,7 @@ tapgemm_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int n = ((warp - 2) >> 2) * 16;           // its 16-column group
     if (n < p.N) {
       float bias16[16];
-      const bool pre_bias = p.bias && !p.bias_per_row && (p.vec4 & 2) && n + 15 < p.N;
+      const bool pre_bias = p.bias && !p.bias_per_row && n + 15 < p.N;
 #pragma unroll
       for (int j = 0; j < 16; ++j) bias16[j] = pre_bias ? __ldg(p.bias + n + j) : 0.f;
       int ti = 0;

@@ -196,7 +196,7 @@ class _NetPlan:
         self.spec_in = torch.empty(B, 2, T, 2 * F, **f32)
         self.spec_out = torch.empty(B, 2, T, 2 * F, **f32)
         max_elems = B * T * F * g
-        pool = [torch.empty(max_elems, **f32) for _ in range(4)]       # t1, t2, xt, ot scratch shared by all levels
+        pool = [torch.empty(max_elems, **f32) for _ in range(3)]       # t1, t2, xt scratch shared by all levels
 
         def buf(slot, *shape):
             nel = 1
@@ -211,24 +211,38 @@ class _NetPlan:
             return vec.repeat(rows_pc).contiguous()
 
         def tfc_tdf(x, key, Hh, Ww, c, out):
+            """TFC (l 3x3 convs) + TDF (two bias-free linears along frequency, each BN + ReLU) + residual.  The TDF GEMMs
+            run over rows (b, t, c) with K = frequency, i.e. on the NHCW transpose of the activations; both transposes
+            live in GEMM epilogues (the last TFC conv also writes NHCW; the second TDF linear writes NHWC and adds the
+            residual), so no standalone transpose pass touches HBM."""
             cur = x
+            xt = buf(2, B, Hh, c, Ww)
             for j in range(l):
                 dst = buf(j % 2, B, Hh, Ww, c)
-                add(tg.conv2d(cur, W[f"{key}.c{j}.w"], dst, 3, 3, (1, 1),
-                              Epi(bias=W[f"{key}.c{j}.b"], act_pre=tg.ACT_RELU, round_out=R and j < l - 1), be, name=f"{key}.c{j}"))
+                last = j == l - 1
+                epi = Epi(bias=W[f"{key}.c{j}.b"], act_pre=tg.ACT_RELU, round_out=R and not last)
+                if last:   # second output: the same values in NHCW order, RN-rounded for the TDF GEMM
+                    epi.out2 = tg.Out(xt, Hh * c * Ww, c * Ww, 1, Hh, Ww, sn=Ww)
+                    epi.round_out2 = R
+                add(tg.conv2d(cur, W[f"{key}.c{j}.w"], dst, 3, 3, (1, 1), epi, be, name=f"{key}.c{j}"))
                 cur = dst
             t = cur
-            xt = buf(2, B, Hh, c, Ww)
-            add(lambda t=t, xt=xt: ops.nhwc_to_nhcw(t, W[key + ".s1"], xt, R))
-            rows = B * Hh * c
-            h = torch.empty(rows, Ww // bnf, **f32)
-            b1, s2, b2 = rep(W[key + ".b1"], B * Hh), rep(W[key + ".s2"], B * Hh), rep(W[key + ".b2"], B * Hh)
+            rows, Kb = B * Hh * c, Ww // bnf
+            h = torch.empty(rows, Kb, **f32)
+            s1, b1 = rep(W[key + ".s1"], B * Hh), rep(W[key + ".b1"], B * Hh)
+            s2, b2 = rep(W[key + ".s2"], B * Hh), rep(W[key + ".b2"], B * Hh)
             add(tg.linear(xt.view(rows, Ww), W[key + ".w1"], h,
-                          Epi(bias=b1, bias_per_row=True, act_pre=tg.ACT_RELU, row_scale=s2, round_out=R), be, name=f"{key}.tdf1"))
-            ot = buf(3, B, Hh, c, Ww)
-            add(tg.linear(h, W[key + ".w2"], ot.view(rows, Ww), Epi(bias=b2, bias_per_row=True, act_pre=tg.ACT_RELU), be,
-                          name=f"{key}.tdf2"))
-            add(lambda ot=ot, t=t, out=out: ops.nhcw_to_nhwc_add(ot, t, out, R))
+                          Epi(row_scale_pre=s1, bias=b1, bias_per_row=True, act_pre=tg.ACT_RELU, row_scale=s2, round_out=R), be,
+                          name=f"{key}.tdf1"))
+            # rows tiled as (w = channel, h = (b, t)) so the epilogue can address NHWC: out[(b,t), n = f, c]
+            bw = 1
+            while bw < 128 and c % (2 * bw) == 0:
+                bw *= 2
+            a2 = tg.View(h, (Kb, c, B * Hh, 1, 1), (1, Kb, c * Kb, 0, 0))
+            o2 = tg.Out(out, 0, Ww * c, 1, B * Hh, c, sn=c)
+            add(tg.TapGemm(a2, tg.weights(W[key + ".w2"]), [(0, 0, 0, 0, 0)], (c, B * Hh, 1), o2,
+                           Epi(bias=b2, bias_per_row=True, act_pre=tg.ACT_RELU, res=t, res_strides=(0, Ww * c, 1, c), round_out=R),
+                           be, box=(bw, 128 // bw), name=f"{key}.tdf2"))
 
         # ---- first conv (1x1, 4 -> g) reading [B, ch, T, F, ri]: one tap per stereo channel, K = (re, im)
         x = torch.empty(B, T, F, g, **f32)

@@ -83,7 +83,8 @@ def weights(w: torch.Tensor) -> Weights:
 
 @dataclass
 class Out:
-    """Output addressing: element (b,h,w,n) at t[off + b*sb + (h*osh+ooh)*sh + (w*osw+oow)*sw + n]."""
+    """Output addressing: element (b,h,w,n) at t[off + b*sb + (h*osh+ooh)*sh + (w*osw+oow)*sw + n*sn]
+    (sn = 1: channels-last; anything else writes a transposed layout)."""
     t: torch.Tensor
     sb: int
     sh: int
@@ -95,6 +96,7 @@ class Out:
     osw: int = 1
     ooh: int = 0
     oow: int = 0
+    sn: int = 1
 
     def ptr(self) -> int:
         return self.t.data_ptr() + 4 * self.off
@@ -114,7 +116,9 @@ def out_of(x: torch.Tensor, **kw) -> Out:
 
 @dataclass
 class Epi:
-    """Fused epilogue: v=acc+bias; v=act_pre(v); v+=res; v*=scale; v+=res2; v=act_post(v); out=v; out2=act2(v)."""
+    """Fused epilogue: v=acc*row_scale_pre+bias; v=act_pre(v); v*=row_scale; v(+|*)=res; v*=scale; v+=res2;
+    v=act_post(v); out=v; out2=act2(v)."""
+    row_scale_pre: Optional[torch.Tensor] = None   # [OH*OW] per-output-row multiplier applied to the accumulator
     bias: Optional[torch.Tensor] = None
     bias_per_row: bool = False
     act_pre: int = ACT_NONE
@@ -123,11 +127,12 @@ class Epi:
     res: Optional[torch.Tensor] = None     # channels-last tensor over the output pixel space
     res_mul: bool = False                  # v *= res instead of v += res
     res_mapped: bool = False               # address res by the mapped output pixel (conv-transpose phases)
+    res_strides: Optional[Tuple[int, int, int, int]] = None   # explicit (sb, sh, sw, sn) element strides of `res`
     scale: float = 1.0
     res2: Optional[torch.Tensor] = None    # same addressing as out
     act_post: int = ACT_NONE
     act_post_p: float = 0.0
-    out2: Optional[torch.Tensor] = None    # same addressing as out
+    out2: Optional[object] = None          # Tensor: same addressing as out; Out: its own (possibly transposed) layout
     act2: int = ACT_NONE
     act2_p: float = 0.0
     round_out: bool = False     # store `out` rounded (RN) to TF32: for tensors only consumed by TF32 GEMMs
@@ -172,9 +177,14 @@ class TapGemm:
         p.BW, p.BH = bw, bh
         p.osh, p.osw, p.ooh, p.oow = out.osh, out.osw, out.ooh, out.oow
         p.o_fh, p.o_fw = int(out.fh), int(out.fw)
-        p.o_sb, p.o_sh, p.o_sw = int(out.sb), int(out.sh), int(out.sw)
+        p.o_sb, p.o_sh, p.o_sw, p.o_sn = int(out.sb), int(out.sh), int(out.sw), int(out.sn)
+        p.r_sn = 1
         self._keep = [a.t, w.t, out.t]
         # ---- epilogue
+        if epi.row_scale_pre is not None:
+            assert epi.row_scale_pre.dtype == torch.float32 and epi.row_scale_pre.is_contiguous()
+            p.row_scale_pre = epi.row_scale_pre.data_ptr()
+            self._keep.append(epi.row_scale_pre)
         if epi.bias is not None:
             assert epi.bias.dtype == torch.float32 and epi.bias.is_contiguous()
             p.bias = epi.bias.data_ptr()
@@ -188,11 +198,15 @@ class TapGemm:
         p.r_sb = p.r_sh = p.r_sw = 0
         if epi.res is not None:
             r = epi.res
-            assert r.dtype == torch.float32 and r.stride(-1) == 1
-            st = list(r.stride())
-            while len(st) < 4:
-                st.insert(0, 0)
-            p.r_sb, p.r_sh, p.r_sw = int(st[0]), int(st[1]), int(st[2])
+            assert r.dtype == torch.float32
+            if epi.res_strides is not None:
+                p.r_sb, p.r_sh, p.r_sw, p.r_sn = (int(v_) for v_ in epi.res_strides)
+            else:
+                assert r.stride(-1) == 1
+                st = list(r.stride())
+                while len(st) < 4:
+                    st.insert(0, 0)
+                p.r_sb, p.r_sh, p.r_sw = int(st[0]), int(st[1]), int(st[2])
             p.res = r.data_ptr()
             p.res_op = (1 if epi.res_mul else 0) | (2 if epi.res_mapped else 0)
             self._keep.append(r)
@@ -203,7 +217,13 @@ class TapGemm:
             self._keep.append(epi.res2)
         p.act_post, p.act_post_p = epi.act_post, float(epi.act_post_p)
         p.out = out.ptr()
-        if epi.out2 is not None:
+        if isinstance(epi.out2, Out):
+            o2 = epi.out2
+            p.out2 = o2.ptr()
+            p.out2_own = 1
+            p.o2_sb, p.o2_sh, p.o2_sw, p.o2_sn = int(o2.sb), int(o2.sh), int(o2.sw), int(o2.sn)
+            self._keep.append(o2.t)
+        elif epi.out2 is not None:
             assert epi.out2.stride() == out.t.stride()
             p.out2 = epi.out2.data_ptr() + 4 * out.off
             self._keep.append(epi.out2)
@@ -219,10 +239,19 @@ class TapGemm:
         k_ok = k_ok and all(t[0] % 4 == 0 for t in self.taps)
         if k_ok:
             v |= 1
-        n_ok = all((q or 0) % 16 == 0 for q in (p.out, p.out2, p.res, p.res2, p.bias))
-        n_ok = n_ok and all(s % 4 == 0 for s in (p.o_sb, p.o_sh, p.o_sw, p.r_sb, p.r_sh, p.r_sw))
-        if n_ok:
+
+        def al(ptr, *strides):
+            return (ptr or 0) % 16 == 0 and all(s_ % 4 == 0 for s_ in strides)
+
+        shared2 = p.out2 if not p.out2_own else 0
+        if p.o_sn == 1 and al(p.out, p.o_sb, p.o_sh, p.o_sw) and al(shared2) and al(p.res2):
             v |= 2
+        if al(p.bias) or p.bias_per_row:
+            v |= 4
+        if not p.out2_own or (p.o2_sn == 1 and al(p.out2, p.o2_sb, p.o2_sh, p.o2_sw)):
+            v |= 8
+        if not p.res or (p.r_sn == 1 and al(p.res, p.r_sb, p.r_sh, p.r_sw)):
+            v |= 16
         p.vec4 = v
         self.params = p
         self.backend = backend

@@ -79,11 +79,18 @@ typedef struct b200vc_tapgemm_params {
   int32_t o_fh, o_fw;   /* full output extents: mapped pixel must lie in [0,o_fh) x [0,o_fw) */
   int64_t o_sb, o_sh, o_sw;   /* output element strides                       */
   int64_t r_sb, r_sh, r_sw;   /* residual #1 element strides (pixel b,h,w)    */
+  int64_t o_sn, r_sn;   /* element stride of the n (channel) index in out/res2 and in res: 1 = channels-last; any
+                           other value writes/reads a transposed layout (MDX-Net TDF: NHCW <-> NHWC)            */
+  int64_t o2_sb, o2_sh, o2_sw, o2_sn; /* out2 strides when out2_own != 0 (addressed by the mapped output pixel) */
+  int32_t out2_own;     /* 0: out2 shares out's addressing; 1: out2 uses the o2_* strides                       */
+  const float* row_scale_pre; /* optional: acc *= row_scale_pre[h*OW + w] BEFORE the bias                        */
   const float* bias;
   int32_t bias_per_row;
   int32_t act_pre;
   float act_pre_p;
   const float* row_scale; /* optional: v *= row_scale[h*OW + w] after act_pre (per-output-row scale)   */
+  /* epilogue: v = acc * row_scale_pre + bias; v = act_pre(v); v *= row_scale; v (+|*)= res; v *= scale; v += res2;
+   *           v = act_post(v); out = v; out2 = act2(v)                                                         */
   const float* res;
   int32_t res_op;       /* bit0: v *= res instead of v += res (MDX-Net multiplicative skip); bit1: address res by the
                            mapped output pixel (h*osh+ooh, w*osw+oow) instead of the GEMM pixel */
@@ -95,7 +102,9 @@ typedef struct b200vc_tapgemm_params {
   float* out2;
   int32_t act2;
   float act2_p;
-  int32_t vec4;         /* bit0: k-vectorised loads ok, bit1: n-vectorised epilogue ok */
+  int32_t vec4;         /* vectorisation licences (a bit is also set when its tensor is absent): 1 = k-vectorised operand
+                           loads; 2 = out/res2 (and a layout-sharing out2) channels-last + 16-byte aligned; 4 = per-column
+                           bias float4-loadable; 8 = own-layout out2 channels-last + aligned; 16 = res likewise        */
   int32_t round_tf32;   /* bit0: round `out` to TF32 (RN), bit1: round `out2` — for tensors only consumed by TF32 GEMMs */
   b200vc_tap taps[B200VC_MAX_TAPS];
 } b200vc_tapgemm_params;

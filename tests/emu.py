@@ -71,6 +71,8 @@ def emulate(op) -> None:
             acc[sel] += vals[sel] @ Wm.t()
     # ---- epilogue
     v = acc
+    if epi.row_scale_pre is not None:
+        v = v * epi.row_scale_pre.double()[(hh * OW + ww)][:, None]
     if epi.bias is not None:
         bias = epi.bias.double()
         if epi.bias_per_row:
@@ -83,30 +85,39 @@ def emulate(op) -> None:
     n_idx = torch.arange(N)
     if epi.res is not None:
         r = epi.res
-        st = list(r.stride())
-        while len(st) < 4:
-            st.insert(0, 0)
+        if epi.res_strides is not None:
+            st = list(epi.res_strides)
+        else:
+            st = list(r.stride())
+            while len(st) < 4:
+                st.insert(0, 0)
+            st = st[:3] + [1]
         rf = _flat(r).double()
         if epi.res_mapped:
             ridx = r.storage_offset() + bb * st[0] + (hh * out.osh + out.ooh).clamp(0, out.fh - 1) * st[1] + (ww * out.osw + out.oow).clamp(0, out.fw - 1) * st[2]
         else:
             ridx = r.storage_offset() + bb * st[0] + hh * st[1] + ww * st[2]
-        rv = rf[ridx[:, None] + n_idx[None, :]]
+        rv = rf[ridx[:, None] + n_idx[None, :] * st[3]]
         v = v * rv if epi.res_mul else v + rv
     v = v * epi.scale
     mh, mw = hh * out.osh + out.ooh, ww * out.osw + out.oow
     valid = (mh >= 0) & (mh < out.fh) & (mw >= 0) & (mw < out.fw)
     o_rel = bb * out.sb + mh * out.sh + mw * out.sw
-    o_idx = (out.t.storage_offset() + out.off + o_rel)[:, None] + n_idx[None, :]
+    o_idx = (out.t.storage_offset() + out.off + o_rel)[:, None] + n_idx[None, :] * out.sn
     if epi.res2 is not None:
         r2 = _flat(epi.res2).double()
-        r2_idx = (epi.res2.storage_offset() + out.off + o_rel)[:, None] + n_idx[None, :]
+        r2_idx = (epi.res2.storage_offset() + out.off + o_rel)[:, None] + n_idx[None, :] * out.sn
         v = v + torch.where(valid[:, None], r2[r2_idx.clamp(0, r2.numel() - 1)], torch.zeros((), dtype=torch.float64))
     v = _act(v, epi.act_post, epi.act_post_p)
     of = _flat(out.t)
     sel = valid
     of[o_idx[sel].reshape(-1)] = v[sel].reshape(-1).to(of.dtype)
-    if epi.out2 is not None:
+    if epi.out2 is not None and hasattr(epi.out2, "sn"):       # tapgemm.Out: its own layout, addressed by the mapped pixel
+        q = epi.out2
+        o2 = _flat(q.t)
+        o2_idx = (q.t.storage_offset() + q.off + bb * q.sb + mh * q.sh + mw * q.sw)[:, None] + n_idx[None, :] * q.sn
+        o2[o2_idx[sel].reshape(-1)] = _act(v, epi.act2, epi.act2_p)[sel].reshape(-1).to(o2.dtype)
+    elif epi.out2 is not None:
         o2 = _flat(epi.out2)
-        o2_idx = (epi.out2.storage_offset() + out.off + o_rel)[:, None] + n_idx[None, :]
+        o2_idx = (epi.out2.storage_offset() + out.off + o_rel)[:, None] + n_idx[None, :] * out.sn
         o2[o2_idx[sel].reshape(-1)] = _act(v, epi.act2, epi.act2_p)[sel].reshape(-1).to(o2.dtype)

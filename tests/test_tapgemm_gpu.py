@@ -228,3 +228,19 @@ def test_weight_stationary_kernel_is_selected_and_forced():
     assert not big.ws_applicable()
     with pytest.raises(RuntimeError):
         big(backend=tg.BACKEND_TC_WS)
+
+
+@pytest.mark.parametrize("bname,backend,tol", BACKENDS)
+@pytest.mark.parametrize("B,H,W,C,bnf", [(2, 5, 24, 16, 4), (1, 16, 256, 48, 8), (2, 8, 128, 96, 8), (1, 4, 64, 40, 4)])
+def test_transposed_epilogues_tdf_chain(bname, backend, tol, B, H, W, C, bnf):
+    """conv -> (NHWC, NHCW) dual store; TDF linears over (b,t,c) rows; NHWC store + residual from the transposed GEMM."""
+    from test_tapgemm_lowering import _tdf_problem, tdf_ops
+    x, wc, bc, w1, w2, s1, b1, s2, b2, t_ref, ref = _tdf_problem(B, H, W, C, bnf, seed=B + H + W + C)
+    args = dev(x, tg.pack_conv2d(wc), bc, w1, w2, s1, b1, s2, b2)
+    ops, t, xt, out = tdf_ops(*args, backend=backend)
+    for op in ops:
+        op()
+    torch.cuda.synchronize()
+    check(t, t_ref.permute(0, 2, 3, 1).contiguous(), tol, f"tfc[{bname}]")
+    check(xt, t_ref.permute(0, 2, 1, 3).contiguous(), tol, f"tfc^T[{bname}]")
+    check(out, ref, 2 * tol, f"tdf[{bname}]")

@@ -154,3 +154,53 @@ def test_bias_per_row_role_swap():
     op = tg.linear(wv, x, out[:, :T], tg.Epi(bias=b, bias_per_row=True))
     emulate(op)
     close(out[:, :T], (x @ wv.t() + b).t())
+
+
+def _tdf_problem(B=2, H=5, W=24, C=16, bnf=4, seed=3):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, H, W, C, generator=g)
+    wc = torch.randn(C, C, 3, 3, generator=g) / (9 * C) ** 0.5
+    bc = torch.randn(C, generator=g)
+    w1 = torch.randn(W // bnf, W, generator=g) / W ** 0.5
+    w2 = torch.randn(W, W // bnf, generator=g) / (W // bnf) ** 0.5
+    s1, b1, s2, b2 = (torch.randn(C, generator=g) for _ in range(4))
+    t = F.relu(F.conv2d(x.permute(0, 3, 1, 2), wc, bc, padding=1))                 # [B,C,H,W]
+    h = F.relu(F.linear(t, w1) * s1[None, :, None, None] + b1[None, :, None, None])
+    y = F.relu(F.linear(h, w2) * s2[None, :, None, None] + b2[None, :, None, None])
+    ref = (t + y).permute(0, 2, 3, 1).contiguous()                                 # NHWC
+    return x, wc, bc, w1, w2, s1, b1, s2, b2, t, ref
+
+
+def tdf_ops(x, wc, bc, w1, w2, s1, b1, s2, b2, backend=tg.BACKEND_TC, rnd=False):
+    """The MDX-Net TFC->TDF->residual chain with both transposes inside GEMM epilogues (aicovergen_b200/mdx.py)."""
+    B, H, W, C = x.shape
+    Kb = w1.shape[0]
+    kw = dict(device=x.device)
+    t = torch.zeros(B, H, W, C, **kw)
+    xt = torch.zeros(B, H, C, W, **kw)
+    hbuf = torch.zeros(B * H * C, Kb, **kw)
+    out = torch.zeros(B, H, W, C, **kw)
+    rep = lambda v: v.repeat(B * H).contiguous()
+    ops = [tg.conv2d(x, tg.pack_conv2d(wc) if wc.dim() == 4 else wc, t, 3, 3, (1, 1),
+                     tg.Epi(bias=bc, act_pre=tg.ACT_RELU, out2=tg.Out(xt, H * C * W, C * W, 1, H, W, sn=W), round_out2=rnd), backend),
+           tg.linear(xt.view(B * H * C, W), w1, hbuf,
+                     tg.Epi(row_scale_pre=rep(s1), bias=rep(b1), bias_per_row=True, act_pre=tg.ACT_RELU, row_scale=rep(s2), round_out=rnd),
+                     backend)]
+    bw = 1
+    while bw < 128 and C % (2 * bw) == 0:
+        bw *= 2
+    a2 = tg.View(hbuf, (Kb, C, B * H, 1, 1), (1, Kb, C * Kb, 0, 0))
+    ops.append(tg.TapGemm(a2, tg.weights(w2), [(0, 0, 0, 0, 0)], (C, B * H, 1), tg.Out(out, 0, W * C, 1, B * H, C, sn=C),
+                          tg.Epi(bias=rep(b2), bias_per_row=True, act_pre=tg.ACT_RELU, res=t, res_strides=(0, W * C, 1, C)),
+                          backend, box=(bw, 128 // bw)))
+    return ops, t, xt, out
+
+
+def test_transposed_epilogues_tdf_chain():
+    x, wc, bc, w1, w2, s1, b1, s2, b2, t_ref, ref = _tdf_problem()
+    ops, t, xt, out = tdf_ops(x, wc, bc, w1, w2, s1, b1, s2, b2)
+    for op in ops:
+        emulate(op)
+    close(t, t_ref.permute(0, 2, 3, 1))
+    close(xt, t_ref.permute(0, 2, 1, 3))
+    close(out, ref)
