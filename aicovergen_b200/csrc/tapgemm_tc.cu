@@ -100,6 +100,16 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
                : "memory");
 }
 
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -134,7 +144,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform role index
 
   // ---- tile coordinates
   const int ntw = (p.OW + p.BW - 1) / p.BW;
@@ -174,11 +184,11 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      for (int chunk = 0; chunk < nchunks; ++chunk) {
-        const int s = chunk % STAGES;
-        const uint32_t ph = (chunk / STAGES) & 1;
-        mbar_wait(empty_bar(s), ph ^ 1u);
+    for (int chunk = 0; chunk < nchunks; ++chunk) {
+      const int s = chunk % STAGES;
+      const uint32_t ph = (chunk / STAGES) & 1;
+      mbar_wait(empty_bar(s), ph ^ 1u);
+      if (elect_one()) {
         const int tap_i = chunk / kchunks;
         const int kc0 = (chunk - tap_i * kchunks) * KCHUNK;
         const TgTap tap = p.taps[tap_i];
@@ -187,15 +197,17 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     tap.dp);
         tma_load_3d(b_stage(s), &tmW, full_bar(s), kc0, n0, tap.widx + tb * p.w_batch_step);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      for (int chunk = 0; chunk < nchunks; ++chunk) {
-        const int s = chunk % STAGES;
-        const uint32_t ph = (chunk / STAGES) & 1;
-        mbar_wait(full_bar(s), ph);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // whole warp walks the loop (uniform control flow -> descriptors stay in uniform registers); one elected lane issues
+    for (int chunk = 0; chunk < nchunks; ++chunk) {
+      const int s = chunk % STAGES;
+      const uint32_t ph = (chunk / STAGES) & 1;
+      mbar_wait(full_bar(s), ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (elect_one()) {
         const uint64_t adesc = make_smem_desc(a_stage(s));
         const uint64_t bdesc = make_smem_desc(b_stage(s));
 #pragma unroll
@@ -205,8 +217,9 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     (chunk > 0 || k > 0) ? 1u : 0u);
         }
         umma_commit(empty_bar(s));   // frees this smem stage once the MMAs have read it
+        if (chunk == nchunks - 1) umma_commit(tmem_full_bar);    // accumulator complete
       }
-      umma_commit(tmem_full_bar);    // accumulator complete
+      __syncwarp();
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================

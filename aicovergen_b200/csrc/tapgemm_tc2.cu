@@ -45,6 +45,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "}" ::"r"(bar), "r"(parity)
       : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2,
                                             int c3, int c4) {
   asm volatile(
@@ -113,7 +123,7 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform role index
   const int ntw = (p.OW + p.BW - 1) / p.BW;
   const int nth = (p.OH + p.BH - 1) / p.BH;
   const int kchunks = (p.Kc + KCHUNK - 1) / KCHUNK;
@@ -155,7 +165,7 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    {
       int it_chunk = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int w0, h0, tb, n0;
@@ -164,18 +174,22 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           const int s = it_chunk % STAGES;
           const uint32_t ph = (it_chunk / STAGES) & 1;
           mbar_wait(empty_bar(s), ph ^ 1u);
-          const int tap_i = chunk / kchunks;
-          const int kc0 = (chunk - tap_i * kchunks) * KCHUNK;
-          const TgTap tap = p.taps[tap_i];
-          mbar_expect_tx(full_bar(s), STAGE_BYTES);
-          tma_load_5d(a_stage(s), &tmA, full_bar(s), tap.c_off + kc0, w0 + tap.dw, h0 + tap.dh, tb, tap.dp);
-          tma_load_3d(b_stage(s), &tmW, full_bar(s), kc0, n0, tap.widx + tb * p.w_batch_step);
+          if (elect_one()) {
+            const int tap_i = chunk / kchunks;
+            const int kc0 = (chunk - tap_i * kchunks) * KCHUNK;
+            const TgTap tap = p.taps[tap_i];
+            mbar_expect_tx(full_bar(s), STAGE_BYTES);
+            tma_load_5d(a_stage(s), &tmA, full_bar(s), tap.c_off + kc0, w0 + tap.dw, h0 + tap.dh, tb, tap.dp);
+            tma_load_3d(b_stage(s), &tmW, full_bar(s), kc0, n0, tap.widx + tb * p.w_batch_step);
+          }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // whole warp walks the loops (uniform control flow -> descriptors stay in uniform registers); one elected lane issues
+    {
       int it_chunk = 0, it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int acc = it & 1;
@@ -184,8 +198,7 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
         // instruction N = the live part of this n-tile rounded up to 16 (e.g. 48 for the MDX c=48 layers)
-        int w0_, h0_, tb_, n0_;
-        tile_coords(tile, w0_, h0_, tb_, n0_);
+        const int n0_ = (tile % ntiles_n) * BN;
         const int nrem = p.N - n0_;
         const uint32_t IDESC = make_idesc_tf32(128, nrem >= BN ? BN : ((nrem + 15) & ~15));
         for (int chunk = 0; chunk < nchunks; ++chunk, ++it_chunk) {
@@ -193,14 +206,17 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           const uint32_t ph = (it_chunk / STAGES) & 1;
           mbar_wait(full_bar(s), ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint64_t adesc = make_smem_desc(a_stage(s));
-          const uint64_t bdesc = make_smem_desc(b_stage(s));
+          if (elect_one()) {
+            const uint64_t adesc = make_smem_desc(a_stage(s));
+            const uint64_t bdesc = make_smem_desc(b_stage(s));
 #pragma unroll
-          for (int k = 0; k < KCHUNK / 8; ++k)
-            umma_tf32(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, (chunk > 0 || k > 0) ? 1u : 0u);
-          umma_commit(empty_bar(s));
+            for (int k = 0; k < KCHUNK / 8; ++k)
+              umma_tf32(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, (chunk > 0 || k > 0) ? 1u : 0u);
+            umma_commit(empty_bar(s));
+            if (chunk == nchunks - 1) umma_commit(tfull_bar(acc));
+          }
+          __syncwarp();
         }
-        umma_commit(tfull_bar(acc));
       }
     }
   } else {

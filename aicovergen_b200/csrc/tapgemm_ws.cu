@@ -61,6 +61,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "}" ::"r"(bar), "r"(parity)
       : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2,
                                             int c3, int c4) {
   asm volatile(
@@ -173,7 +183,7 @@ tapgemm_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   auto tempty_bar = [&](int a) { return bar_base + 8u * (11 + a); };
   const uint32_t tmem_slot = bar_base + 8u * 13;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform role index
   const int ntw = (p.OW + 127) / 128;
 
   if (warp == 0 && lane == 0) {
@@ -202,12 +212,15 @@ tapgemm_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    {
       // park the whole weight slab: [tap][kchunk] tiles of Nr x 32
-      mbar_expect_tx(w_bar, (uint32_t)w_bytes);
-      for (int j = 0; j < p.ntaps; ++j)
-        for (int kc = 0; kc < kchunks; ++kc)
-          tma_load_3d(w_base + (uint32_t)((j * kchunks + kc) * g.b_tile_bytes), &tmW, w_bar, kc * KCHUNK, 0, j);
+      if (elect_one()) {
+        mbar_expect_tx(w_bar, (uint32_t)w_bytes);
+        for (int j = 0; j < p.ntaps; ++j)
+          for (int kc = 0; kc < kchunks; ++kc)
+            tma_load_3d(w_base + (uint32_t)((j * kchunks + kc) * g.b_tile_bytes), &tmW, w_bar, kc * KCHUNK, 0, j);
+      }
+      __syncwarp();
       int it = 0;
       const uint32_t a_tx = (uint32_t)(g.KH * g.BWh * 128);
       TileWalk tk;
@@ -216,14 +229,19 @@ tapgemm_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const int s = it % g.stages;
           const uint32_t ph = (it / g.stages) & 1;
           mbar_wait(empty_bar(s), ph ^ 1u);
-          mbar_expect_tx(full_bar(s), a_tx);
-          tma_load_5d(a_stage(s), &tmA, full_bar(s), kc * KCHUNK, tk.tw * 128 - g.pad_w, tk.h - g.pad_h, tk.b, 0);
+          if (elect_one()) {
+            mbar_expect_tx(full_bar(s), a_tx);
+            tma_load_5d(a_stage(s), &tmA, full_bar(s), kc * KCHUNK, tk.tw * 128 - g.pad_w, tk.h - g.pad_h, tk.b, 0);
+          }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The whole warp walks the loops (warp-uniform control flow keeps descriptors in uniform registers); one elected
+    // lane issues the tcgen05 instructions.
+    {
       const uint32_t IDESC = make_idesc_tf32(128, g.Nr);
       mbar_wait(w_bar, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -246,19 +264,22 @@ tapgemm_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const uint64_t b_step = (uint64_t)((kchunks * g.b_tile_bytes) >> 4);
           const uint64_t a_kw_step = (uint64_t)(g.dil_w * 8), a_kh_step = (uint64_t)(g.BWh * 8);   // rows x 128 B >> 4
           uint32_t accum = kc > 0 ? 1u : 0u;
-          for (int kh = 0; kh < g.KH; ++kh, adesc_row += a_kh_step) {
-            uint64_t adesc = adesc_row;
-            for (int kw = 0; kw < g.KW; ++kw, adesc += a_kw_step, bdesc += b_step) {
+          if (elect_one()) {
+            for (int kh = 0; kh < g.KH; ++kh, adesc_row += a_kh_step) {
+              uint64_t adesc = adesc_row;
+              for (int kw = 0; kw < g.KW; ++kw, adesc += a_kw_step, bdesc += b_step) {
 #pragma unroll
-              for (int k = 0; k < KCHUNK / 8; ++k) {
-                umma_tf32(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, accum);
-                accum = 1u;
+                for (int k = 0; k < KCHUNK / 8; ++k) {
+                  umma_tf32(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, accum);
+                  accum = 1u;
+                }
               }
             }
+            umma_commit(empty_bar(s));
+            if (kc == kchunks - 1) umma_commit(tfull_bar(acc));
           }
-          umma_commit(empty_bar(s));
+          __syncwarp();
         }
-        umma_commit(tfull_bar(acc));
       }
     }
   } else {
