@@ -125,7 +125,7 @@ def build_engine(device: str, rank_seed: int = 0):
 
 def install_tc_profiler():
     """Wrap TapGemm.__call__ so every tcgen05 launch inside the timed region is bracketed by CUDA events on the
-    launching stream; returns the record list [(tile_n, flops, bytes, start, end)]."""
+    launching stream; returns the record list [(kernel family, flops, bytes, start, end)]."""
     from aicovergen_b200 import tapgemm as tg
 
     records = []
@@ -135,13 +135,15 @@ def install_tc_profiler():
         be = self.backend if backend is None else backend
         if be == tg.BACKEND_TC and self.tc_supported() and install_tc_profiler.enabled:
             p = self.params
-            tile_n = 256 if p.N > 128 else (128 if p.N > 64 else (64 if p.N > 32 else 32))
+            if not hasattr(self, "_family"):
+                tile_n = 256 if p.N > 128 else (128 if p.N > 64 else (64 if p.N > 32 else 32))
+                self._family = "ws" if self.ws_applicable() else f"tc2<{tile_n}>"
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
             orig(self, stream, backend)
             e.record()
             rows = p.OW * p.OH * p.OB
-            records.append((tile_n, self.flops(), 4.0 * rows * (p.N + p.Kc), s, e))
+            records.append((self._family, self.flops(), 4.0 * rows * (p.N + p.Kc), s, e))
         else:
             orig(self, stream, backend)
 
@@ -374,14 +376,25 @@ def main():
     if fam:
         top = max(fam.items(), key=lambda kv: kv[1][0])
         tn, (ms, fl, by, cnt) = top
-        achieved = fl / (ms / 1000.0) / 1e12
-        tf32_peak = pk["bf16_tflops_sustained"] / 2.0
-        roof = {"kernel": f"tapgemm_tc_kernel<BN={tn}> (tcgen05.mma kind::tf32)", "bound": "tensor", "achieved": round(achieved, 2),
-                "peak": round(tf32_peak, 1), "unit": "TFLOP/s", "frac": round(achieved / tf32_peak, 4), "traffic": None,
-                "peak_source": f"{pk_src} bf16_tflops_sustained / 2 (nominal tf32:bf16 ratio)", "launches": cnt,
-                "avg_launch_ms": round(ms / cnt, 4), "share_of_step": round(ms / args.steps / (dev_ms / args.steps), 4),
-                "algorithmic_gbs": round(by / (ms / 1000.0) / 1e9, 1),
-                "families_ms_per_step": {str(k): round(v[0] / args.steps, 2) for k, v in sorted(fam.items())}}
+        common = {"launches": cnt, "avg_launch_ms": round(ms / cnt, 4),
+                  "share_of_step": round(ms / args.steps / (dev_ms / args.steps), 4),
+                  "algorithmic_tflops": round(fl / (ms / 1000.0) / 1e12, 2),
+                  "algorithmic_gbs": round(by / (ms / 1000.0) / 1e9, 1),
+                  "traffic_note": "per-launch DRAM bytes of representative launches: profiles/r01_ncu_kernels.md",
+                  "families_ms_per_step": {str(k): round(v[0] / args.steps, 2) for k, v in sorted(fam.items())}}
+        if tn == "ws":
+            # small-channel convolutions: arithmetic intensity below the machine balance -> HBM roofline
+            achieved = by / (ms / 1000.0) / 1e9
+            roof = {"kernel": "tapgemm_ws_kernel (weight-stationary + halo, tcgen05.mma kind::tf32)", "bound": "hbm",
+                    "achieved": round(achieved, 1), "peak": round(pk["hbm_gbs"], 1), "unit": "GB/s",
+                    "frac": round(achieved / pk["hbm_gbs"], 4), "traffic": None, "peak_source": f"{pk_src} hbm_gbs", **common}
+        else:
+            achieved = fl / (ms / 1000.0) / 1e12
+            tf32_peak = pk["bf16_tflops_sustained"] / 2.0
+            roof = {"kernel": f"tapgemm_{tn} (persistent tcgen05.mma kind::tf32, double-buffered TMEM)", "bound": "tensor",
+                    "achieved": round(achieved, 2), "peak": round(tf32_peak, 1), "unit": "TFLOP/s",
+                    "frac": round(achieved / tf32_peak, 4), "traffic": None,
+                    "peak_source": f"{pk_src} bf16_tflops_sustained / 2 (nominal tf32:bf16 ratio)", **common}
 
     if rank == 0:
         line = {

@@ -67,6 +67,27 @@ wrap(eng.vc, "pipeline", "vc.pipeline(total)")
 wrap(eng, "mix", "mix")
 wrap(ops, "resample_sinc_mono", "resample")
 
+# ---- per-GEMM timing by name (CUDA events around every tap-GEMM launch, all backends)
+import re  # noqa: E402
+from aicovergen_b200 import tapgemm as tg  # noqa: E402
+
+gemm_rec = []
+orig_call = tg.TapGemm.__call__
+
+
+def timed_call(self, stream=None, backend=None):
+    if not enabled[0]:
+        return orig_call(self, stream, backend)
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    orig_call(self, stream, backend)
+    e.record()
+    be = self.backend if backend is None else backend
+    gemm_rec.append((self.name, be, self.flops(), s, e))
+
+
+tg.TapGemm.__call__ = timed_call
+
 for _ in range(args.warmup):
     eng.cover_device(song)
 enabled[0] = True
@@ -76,4 +97,13 @@ eng.cover_device(song)
 torch.cuda.synchronize()
 total = (time.perf_counter() - t0) * 1e3
 acc["vc.pipeline(glue: hpf, index, pad, rms, int16)"] = acc["vc.pipeline(total)"] - acc.get("hubert", 0) - acc.get("rmvpe", 0) - acc.get("synthesizer", 0)
-print(json.dumps({"seconds": args.seconds, "total_ms": total, "stages_ms": acc}, indent=1))
+by = collections.defaultdict(lambda: [0, 0.0, 0.0])
+for name, be, fl, s_, e_ in gemm_rec:
+    key = re.sub(r"\d+", "#", name) + ("/simt" if be == tg.BACKEND_SIMT else "")
+    by[key][0] += 1
+    by[key][1] += s_.elapsed_time(e_)
+    by[key][2] += fl
+gemms = {k: {"launches": v[0], "ms": round(v[1], 2), "tflops": round(v[2] / v[1] / 1e9, 1) if v[1] > 0 else 0}
+         for k, v in sorted(by.items(), key=lambda kv: -kv[1][1])}
+print(json.dumps({"seconds": args.seconds, "total_ms": total, "stages_ms": acc,
+                  "gemm_ms_total": round(sum(v[1] for v in by.values()), 1), "gemms": gemms}, indent=1))
