@@ -31,6 +31,56 @@ __global__ void mdx_gather_chunks_kernel(const float* __restrict__ wave, long lo
   out[e] = round_out ? round_tf32(v) : v;
 }
 
+// First 1x1 convolution of the TFC-TDF net (4 -> g channels, BatchNorm folded, ReLU), reading the DFT-friendly
+// spectrogram layout spec[B][2 ch][T][F][2 ri] and writing NHWC x[B][T][F][g].  Pointwise and write-bound: one thread
+// per (pixel, 4-channel group) so every store instruction covers contiguous 16-byte pieces of one NHWC row.
+__global__ void mdx_first_conv_kernel(const float* __restrict__ spec, const float* __restrict__ w4,
+                                      const float* __restrict__ bias, float* __restrict__ out, long long npix,
+                                      long long TF, int g4, int round_out) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= npix * g4) return;
+  const long long pix = idx / g4;
+  const int cg = (int)(idx - pix * g4);
+  const long long b = pix / TF, tf = pix - b * TF;
+  const float2 x0 = __ldg(reinterpret_cast<const float2*>(spec + ((b * 2 + 0) * TF + tf) * 2));
+  const float2 x1 = __ldg(reinterpret_cast<const float2*>(spec + ((b * 2 + 1) * TF + tf) * 2));
+  float v[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 w = __ldg(reinterpret_cast<const float4*>(w4) + cg * 4 + j);   // (ch0 re, ch0 im, ch1 re, ch1 im)
+    float a = 0.f;
+    a = fmaf(x0.x, w.x, a); a = fmaf(x0.y, w.y, a); a = fmaf(x1.x, w.z, a); a = fmaf(x1.y, w.w, a);
+    a = fmaxf(a + __ldg(bias + cg * 4 + j), 0.f);
+    v[j] = round_out ? round_tf32(a) : a;
+  }
+  reinterpret_cast<float4*>(out)[idx] = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+// Final 1x1 convolution (c -> 4 channels + bias): NHWC x[B][T][F][c] -> spec[B][2 ch][T][F][2 ri].  Read-bound: one
+// thread per pixel streams its c contiguous floats (float4) and keeps the four dot products in registers.
+__global__ void mdx_final_conv_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                      float* __restrict__ spec, long long npix, long long TF, int c, int round_out) {
+  extern __shared__ float ws[];            // [4][c]
+  for (int i = threadIdx.x; i < 4 * c; i += blockDim.x) ws[i] = w[i];
+  __syncthreads();
+  const long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (pix >= npix) return;
+  const float4* xp = reinterpret_cast<const float4*>(x + pix * c);
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  for (int k = 0; k < c; k += 4) {
+    const float4 t = __ldg(xp + (k >> 2));
+    a0 = fmaf(t.x, ws[k], a0); a0 = fmaf(t.y, ws[k + 1], a0); a0 = fmaf(t.z, ws[k + 2], a0); a0 = fmaf(t.w, ws[k + 3], a0);
+    a1 = fmaf(t.x, ws[c + k], a1); a1 = fmaf(t.y, ws[c + k + 1], a1); a1 = fmaf(t.z, ws[c + k + 2], a1); a1 = fmaf(t.w, ws[c + k + 3], a1);
+    a2 = fmaf(t.x, ws[2 * c + k], a2); a2 = fmaf(t.y, ws[2 * c + k + 1], a2); a2 = fmaf(t.z, ws[2 * c + k + 2], a2); a2 = fmaf(t.w, ws[2 * c + k + 3], a2);
+    a3 = fmaf(t.x, ws[3 * c + k], a3); a3 = fmaf(t.y, ws[3 * c + k + 1], a3); a3 = fmaf(t.z, ws[3 * c + k + 2], a3); a3 = fmaf(t.w, ws[3 * c + k + 3], a3);
+  }
+  a0 += __ldg(bias + 0); a1 += __ldg(bias + 1); a2 += __ldg(bias + 2); a3 += __ldg(bias + 3);
+  if (round_out) { a0 = round_tf32(a0); a1 = round_tf32(a1); a2 = round_tf32(a2); a3 = round_tf32(a3); }
+  const long long b = pix / TF, tf = pix - b * TF;
+  reinterpret_cast<float2*>(spec)[(b * 2 + 0) * TF + tf] = make_float2(a0, a1);
+  reinterpret_cast<float2*>(spec)[(b * 2 + 1) * TF + tf] = make_float2(a2, a3);
+}
+
 // x [R, W, C] -> out [R, C, W] with per-channel scale (R = B*H): 32x32 shared-memory tiles
 __global__ void nhwc_to_nhcw_kernel(const float* __restrict__ x, const float* __restrict__ scale,
                                     float* __restrict__ out, int W, int C, int round_out) {
@@ -131,6 +181,30 @@ int b200vc_mdx_gather_chunks(const float* wave, int64_t n_song, const int64_t* s
   mdx_gather_chunks_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
       wave, n_song, reinterpret_cast<const long long*>(src_start), reinterpret_cast<const long long*>(lo),
       reinterpret_cast<const long long*>(hi), out, B, chunk, half, sign, round_out);
+  count_launch();
+  B200VC_LAUNCH_CHECK();
+  return kOk;
+}
+
+int b200vc_mdx_first_conv(const float* spec, const float* w4, const float* bias, float* out, int B, int T, int F, int g,
+                          int round_out, void* stream) {
+  B200VC_REQUIRE(spec && w4 && bias && out && B > 0 && T > 0 && F > 0 && g > 0 && g % 4 == 0, "mdx_first_conv: bad args (g=%d)", g);
+  B200VC_REQUIRE(((uintptr_t)spec % 8 == 0) && ((uintptr_t)w4 % 16 == 0) && ((uintptr_t)out % 16 == 0), "mdx_first_conv: alignment");
+  const long long npix = (long long)B * T * F;
+  mdx_first_conv_kernel<<<blocks_for(npix * (g / 4), 256), 256, 0, (cudaStream_t)stream>>>(spec, w4, bias, out, npix, (long long)T * F,
+                                                                                          g / 4, round_out);
+  count_launch();
+  B200VC_LAUNCH_CHECK();
+  return kOk;
+}
+
+int b200vc_mdx_final_conv(const float* x, const float* w, const float* bias, float* spec, int B, int T, int F, int c,
+                          int round_out, void* stream) {
+  B200VC_REQUIRE(x && w && bias && spec && B > 0 && T > 0 && F > 0 && c > 0 && c % 4 == 0 && c <= 2048, "mdx_final_conv: bad args (c=%d)", c);
+  B200VC_REQUIRE(((uintptr_t)x % 16 == 0) && ((uintptr_t)spec % 8 == 0), "mdx_final_conv: alignment");
+  const long long npix = (long long)B * T * F;
+  mdx_final_conv_kernel<<<blocks_for(npix, 128), 128, 4 * c * sizeof(float), (cudaStream_t)stream>>>(x, w, bias, spec, npix,
+                                                                                                  (long long)T * F, c, round_out);
   count_launch();
   B200VC_LAUNCH_CHECK();
   return kOk;

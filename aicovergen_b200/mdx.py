@@ -150,7 +150,7 @@ class ConvTDFNetB200:
     def _load(self, sd):
         s, b = self._bn(sd, "first_conv.1")
         w = sd["first_conv.0.weight"].float()[:, :, 0, 0] * s[:, None]                 # [g, 4] -> taps per channel pair
-        self.W["first.w"] = self._dev(w.view(-1, 2, 2).permute(1, 0, 2), False)         # [ch, g, ri]
+        self.W["first.w4"] = self._dev(w, False)                                        # [g, (ch0re, ch0im, ch1re, ch1im)]
         self.W["first.b"] = self._dev(sd["first_conv.0.bias"].float() * s + b, False)
         for i in range(self.n):
             self._tfc_tdf(sd, f"encoding_blocks.{i}", f"enc{i}")
@@ -244,11 +244,9 @@ class _NetPlan:
                            Epi(bias=b2, bias_per_row=True, act_pre=tg.ACT_RELU, res=t, res_strides=(0, Ww * c, 1, c), round_out=R),
                            be, box=(bw, 128 // bw), name=f"{key}.tdf2"))
 
-        # ---- first conv (1x1, 4 -> g) reading [B, ch, T, F, ri]: one tap per stereo channel, K = (re, im)
+        # ---- first conv (1x1, 4 -> g) reading [B, ch, T, F, ri]: pointwise, write-bound -> its own row kernel
         x = torch.empty(B, T, F, g, **f32)
-        a = tg.View(self.spec_in, (2, F, T, B, 2), (1, 2, 2 * F, 2 * T * 2 * F, T * 2 * F))
-        add(tg.TapGemm(a, tg.Weights(W["first.w"], 2, g, 2, 2 * g), [(0, 0, 0, 0, 0), (0, 0, 0, 1, 1)], (F, T, B),
-                       tg.out_of(x), Epi(bias=W["first.b"], act_pre=tg.ACT_RELU, round_out=R), tg.BACKEND_SIMT, name="first_conv"))
+        add(lambda x=x: ops.mdx_first_conv(self.spec_in, W["first.w4"], W["first.b"], x, R))
         Hh, Ww, c = T, F, g
         skips = []
         for i in range(n):
@@ -264,19 +262,16 @@ class _NetPlan:
         for i in range(n):
             sk, Hs, Ws, cs = skips[-1 - i]
             u = torch.empty(B, Hs, Ws, cs, **f32)
-            for op in tg.conv_transpose2d_s2(x, W[f"us{i}.w"], u, 2, 0,
-                                             Epi(bias=W[f"us{i}.b"], act_pre=tg.ACT_RELU, res=sk, res_mul=True, res_mapped=True, round_out=R),
-                                             be, name=f"us{i}"):
+            for op in tg.conv_transpose2d_k2s2(x, W[f"us{i}.w"], u,
+                                               Epi(bias=W[f"us{i}.b"], act_pre=tg.ACT_RELU, res=sk, res_mul=True, res_mapped=True, round_out=R),
+                                               be, name=f"us{i}"):
                 add(op)
             Hh, Ww, c = Hs, Ws, cs
             y = torch.empty(B, Hh, Ww, c, **f32)
             tfc_tdf(u, f"dec{i}", Hh, Ww, c, y)
             x = y
-        # ---- final conv (1x1, g -> 4) writing [B, ch, T, F, ri]: one GEMM per stereo channel (N = re, im)
-        for ch in range(2):
-            o = tg.Out(self.spec_out, 2 * T * 2 * F, 2 * F, 2, T, F, off=ch * T * 2 * F)
-            add(tg.TapGemm(tg.view(x), tg.Weights(W["final.w"], c, 2, c, 0, off=ch * 2 * c), [(0, 0, 0, 0, 0)], (F, T, B), o,
-                           Epi(bias=W["final.b"][2 * ch: 2 * ch + 2], round_out=R), tg.BACKEND_SIMT, name=f"final_conv.{ch}"))
+        # ---- final conv (1x1, g -> 4) writing [B, ch, T, F, ri]: pointwise, read-bound -> its own row kernel
+        add(lambda x=x: ops.mdx_final_conv(x, W["final.w"], W["final.b"], self.spec_out, R))
         self.steps = steps
 
     def run(self):

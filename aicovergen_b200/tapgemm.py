@@ -27,7 +27,7 @@ __all__ = [
     "conv2d_k2s2", "bmm_nt",
     "pack_conv1d", "pack_convt1d", "pack_conv2d", "pack_convt2d",
     "ACT_NONE", "ACT_RELU", "ACT_LRELU", "ACT_GELU", "ACT_TANH", "ACT_SIGMOID", "ACT_EXP",
-    "BACKEND_SIMT", "BACKEND_TC", "BACKEND_TC_V1", "BACKEND_TC_TILE", "BACKEND_TC_WS",
+    "BACKEND_SIMT", "BACKEND_TC", "BACKEND_TC_V1", "BACKEND_TC_TILE", "BACKEND_TC_WS", "conv_transpose2d_k2s2",
 ]
 
 
@@ -404,6 +404,35 @@ def conv_transpose2d_s2(x: torch.Tensor, wp: torch.Tensor, out: torch.Tensor, k:
             o = out_of(out, osh=sh_, osw=sw_, ooh=ry - pad, oow=rx - pad)
             ops.append(TapGemm(a, weights(wp), taps, (W + (k - 1) // sw_, H + (k - 1) // sh_, B), o, epi,
                                backend, name=f"{name}.ph{ry}{rx}"))
+    return ops
+
+
+def conv_transpose2d_k2s2(x: torch.Tensor, wp: torch.Tensor, out: torch.Tensor, epi: Optional[Epi] = None,
+                          backend: int = BACKEND_TC, name: str = "convT2d_k2s2"):
+    """ConvTranspose2d(kernel 2, stride 2, no padding) as TWO GEMMs (one per output row parity) with N = 2*Cout:
+    the outputs for column parities 0/1 of one input pixel are adjacent in NHWC memory, so they form one 2*Cout-wide
+    GEMM row written at pixel stride 2*Cout.  Half the input reads and twice the MMA width of the 4-phase form.
+    x [B,H,W,Cin]; wp [4,Cout,Cin] (pack_convt2d); out [B,2H,2W,Cout] contiguous.  A mapped residual (MDX-Net skip)
+    and a per-column bias are re-addressed for the widened rows here."""
+    import dataclasses
+    a = view(x)
+    B, H, W = a.dims[3], a.dims[2], a.dims[1]
+    four, Cout, Cin = wp.shape
+    assert four == 4 and wp.is_contiguous() and tuple(out.shape) == (B, 2 * H, 2 * W, Cout) and out.stride(-1) == 1
+    assert out.stride(2) == Cout, "output pixels must be densely packed"
+    e2 = dataclasses.replace(epi) if epi is not None else Epi()
+    assert e2.res2 is None and e2.out2 is None and e2.row_scale is None and e2.row_scale_pre is None
+    if e2.bias is not None and not e2.bias_per_row:
+        e2.bias = torch.cat([e2.bias, e2.bias]).contiguous()
+    if e2.res is not None:
+        assert e2.res_mapped and tuple(e2.res.shape) == tuple(out.shape) and e2.res.stride(-1) == 1 and e2.res.stride(2) == Cout
+        st = e2.res.stride()
+        e2.res_strides = (st[0], st[1], 2 * st[2], 1)
+    ops = []
+    for ry in range(2):
+        w2 = Weights(wp, Cin, 2 * Cout, Cin, 2 * Cout * Cin, off=ry * 2 * Cout * Cin)
+        o = Out(out, out.stride(0), out.stride(1), 2 * out.stride(2), 2 * H, W, osh=2, ooh=ry)
+        ops.append(TapGemm(a, w2, [(0, 0, 0, 0, 0)], (W, H, B), o, e2, backend, name=f"{name}.ph{ry}"))
     return ops
 
 

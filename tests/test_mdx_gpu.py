@@ -100,3 +100,23 @@ def test_process_wave_full_geometry():
     a = float(np.sqrt(((got - ref) ** 2).mean()))
     print(f"[mdx full geometry tc] rel rms {e:.3e}, abs rms {a:.3e} (ref rms {np.sqrt((ref ** 2).mean()):.3e})")
     assert got.shape == wave.shape and e < 8e-3
+
+
+def test_first_and_final_conv_row_kernels():
+    """The pointwise 4->g / g->4 convolutions at the ends of the U-Net against torch (fp32, same summation order)."""
+    from aicovergen_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    B, T, Fq, ch = 2, 8, 96, 48
+    spec = torch.randn(B, 2, T, 2 * Fq, generator=g)
+    w4, b4 = torch.randn(ch, 4, generator=g), torch.randn(ch, generator=g)
+    x_nchw = spec.view(B, 2, T, Fq, 2).permute(0, 1, 4, 2, 3).reshape(B, 4, T, Fq)            # channel = ch*2 + ri
+    ref = torch.relu(torch.einsum("bkth,ck->bthc", x_nchw, w4) + b4)
+    out = torch.empty(B, T, Fq, ch, device="cuda")
+    ops.mdx_first_conv(spec.cuda(), w4.cuda(), b4.cuda(), out)
+    assert (out.cpu() - ref).abs().max() < 1e-5
+    wf, bf = torch.randn(4, ch, generator=g) / ch ** 0.5, torch.randn(4, generator=g)
+    y = torch.einsum("bthc,kc->bkth", ref, wf) + bf[None, :, None, None]                        # [B,4,T,F]
+    ref_spec = y.view(B, 2, 2, T, Fq).permute(0, 1, 3, 4, 2).reshape(B, 2, T, 2 * Fq)
+    so = torch.empty(B, 2, T, 2 * Fq, device="cuda")
+    ops.mdx_final_conv(out, wf.cuda(), bf.cuda(), so)
+    assert (so.cpu() - ref_spec).abs().max() < 1e-4

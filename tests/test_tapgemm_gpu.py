@@ -244,3 +244,21 @@ def test_transposed_epilogues_tdf_chain(bname, backend, tol, B, H, W, C, bnf):
     check(t, t_ref.permute(0, 2, 3, 1).contiguous(), tol, f"tfc[{bname}]")
     check(xt, t_ref.permute(0, 2, 1, 3).contiguous(), tol, f"tfc^T[{bname}]")
     check(out, ref, 2 * tol, f"tdf[{bname}]")
+
+
+@pytest.mark.parametrize("bname,backend,tol", BACKENDS)
+@pytest.mark.parametrize("B,H,W,Ci,Co", [(2, 5, 7, 12, 8), (1, 16, 192, 96, 48), (2, 8, 64, 288, 240)])
+def test_conv_transpose2d_k2s2_two_gemms(bname, backend, tol, B, H, W, Ci, Co):
+    g = torch.Generator().manual_seed(Ci + Co)
+    x = torch.randn(B, H, W, Ci, generator=g)
+    w = torch.randn(Ci, Co, 2, 2, generator=g) / Ci ** 0.5
+    b = torch.randn(Co, generator=g)
+    sk = torch.randn(B, 2 * H, 2 * W, Co, generator=g)
+    ref = (F.relu(F.conv_transpose2d(x.permute(0, 3, 1, 2), w, b, stride=2)).permute(0, 2, 3, 1) * sk).contiguous()
+    xd, wd, bd, sd = dev(x, tg.pack_convt2d(w), b, sk)
+    out = torch.full((B, 2 * H, 2 * W, Co), float("nan"), device="cuda")
+    for op in tg.conv_transpose2d_k2s2(xd, wd, out, tg.Epi(bias=bd, act_pre=tg.ACT_RELU, res=sd, res_mul=True, res_mapped=True),
+                                       backend=backend):
+        op()
+    torch.cuda.synchronize()
+    check(out, ref, tol, f"convT k2s2[{bname}]")

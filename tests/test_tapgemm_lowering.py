@@ -204,3 +204,18 @@ def test_transposed_epilogues_tdf_chain():
     close(t, t_ref.permute(0, 2, 3, 1))
     close(xt, t_ref.permute(0, 2, 1, 3))
     close(out, ref)
+
+
+def test_conv_transpose2d_k2s2_two_gemms_with_mapped_skip():
+    g = torch.Generator().manual_seed(5)
+    B, H, W, Ci, Co = 2, 5, 7, 12, 8
+    x = torch.randn(B, H, W, Ci, generator=g)
+    w = torch.randn(Ci, Co, 2, 2, generator=g)
+    b = torch.randn(Co, generator=g)
+    sk = torch.randn(B, 2 * H, 2 * W, Co, generator=g)
+    out = torch.zeros(B, 2 * H, 2 * W, Co)
+    for op in tg.conv_transpose2d_k2s2(x, tg.pack_convt2d(w), out,
+                                       tg.Epi(bias=b, act_pre=tg.ACT_RELU, res=sk, res_mul=True, res_mapped=True)):
+        emulate(op)
+    ref = F.relu(F.conv_transpose2d(x.permute(0, 3, 1, 2), w, b, stride=2)).permute(0, 2, 3, 1) * sk
+    close(out, ref)
