@@ -15,6 +15,7 @@ import torch
 
 from . import ops
 from . import tapgemm as tg
+from .plans import PlanCache
 from .synth import round_tf32
 from .tapgemm import Epi
 
@@ -27,7 +28,7 @@ class HubertB200:
         self.device = torch.device(device)
         self.backend = backend
         self.n_heads = n_heads
-        self._plans: Dict[tuple, "_HubertPlan"] = {}
+        self._plans = PlanCache()
         self._load(state_dict)
 
     def _dev(self, t, rnd=True):
@@ -86,12 +87,7 @@ class HubertB200:
         L = int(source.shape[1])
         nl = self.n_layers if output_layer is None else int(output_layer)
         key = (L, nl)
-        plan = self._plans.get(key)
-        if plan is None:
-            if len(self._plans) >= 3:
-                self._plans.pop(next(iter(self._plans)))
-            plan = _HubertPlan(self, L, nl)
-            self._plans[key] = plan
+        plan = self._plans.get_or_build(key, lambda: _HubertPlan(self, L, nl))
         return plan.run(source), padding_mask
 
     @torch.no_grad()

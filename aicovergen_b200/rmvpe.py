@@ -17,6 +17,7 @@ import torch
 
 from . import ops
 from . import tapgemm as tg
+from .plans import PlanCache
 from .tapgemm import Epi
 
 BN_EPS = 1e-5
@@ -64,7 +65,7 @@ class RMVPEB200:
         self.is_half = is_half          # kept for interface parity; arithmetic is fp32 (or TF32 if backend=TC)
         self.backend = backend
         self.n_blocks, self.n_enc, self.n_inter = n_blocks, n_enc, n_inter
-        self._plans: Dict[int, "_RmvpePlan"] = {}
+        self._plans = PlanCache()
         self._load(sd)
 
     def _dev(self, t):
@@ -123,13 +124,7 @@ class RMVPEB200:
 
     # ------------------------------------------------------------------
     def _plan(self, n_samples: int) -> "_RmvpePlan":
-        pl = self._plans.get(n_samples)
-        if pl is None:
-            if len(self._plans) >= 2:
-                self._plans.pop(next(iter(self._plans)))
-            pl = _RmvpePlan(self, n_samples)
-            self._plans[n_samples] = pl
-        return pl
+        return self._plans.get_or_build(n_samples, lambda: _RmvpePlan(self, n_samples))
 
     @torch.no_grad()
     def salience_from_audio(self, audio: torch.Tensor) -> torch.Tensor:

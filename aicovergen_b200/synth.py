@@ -19,6 +19,7 @@ import torch
 
 from . import ops
 from . import tapgemm as tg
+from .plans import PlanCache
 from .tapgemm import Epi
 
 LRELU = 0.1
@@ -54,7 +55,7 @@ class SynthesizerB200:
         self.device = torch.device(device)
         self.backend = backend
         self.window = 10
-        self._plans: Dict[int, "_Plan"] = {}
+        self._plans = PlanCache()
         self._cond_cache: Dict[int, dict] = {}
         self._load(cpt["weight"])
 
@@ -182,12 +183,7 @@ class SynthesizerB200:
             sid, pitch = pitch, None   # _nono call form: infer(phone, lengths, sid)
         P = int(phone.shape[1])
         sid_i = int(sid.reshape(-1)[0].item()) if sid is not None else 0
-        plan = self._plans.get(P)
-        if plan is None:
-            if len(self._plans) >= 3:
-                self._plans.pop(next(iter(self._plans)))
-            plan = _Plan(self, P)
-            self._plans[P] = plan
+        plan = self._plans.get_or_build(P, lambda: _Plan(self, P))
         cond = self._cond(sid_i)
         return plan.run(phone, pitch, nsff0, cond, noise_z, noise_src)
 

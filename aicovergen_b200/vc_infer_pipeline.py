@@ -131,7 +131,7 @@ class VC(object):
         assert feats.dim() == 1, feats.dim()
         n_in = feats.shape[0]
         feats = feats.view(1, -1).to(dev)
-        padding_mask = torch.zeros(feats.shape, dtype=torch.bool, device=dev)
+        padding_mask = torch.zeros(feats.shape, dtype=torch.bool)          # host-side: checking it must not sync the stream
         t0 = ttime()
         logits = model.extract_features(source=feats, padding_mask=padding_mask, output_layer=9 if version == "v1" else 12)
         feats = model.final_proj(logits[0]) if version == "v1" else logits[0]
