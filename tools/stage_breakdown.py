@@ -17,6 +17,7 @@ import bench  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--seconds", type=float, default=240.0)
 ap.add_argument("--warmup", type=int, default=2)
+ap.add_argument("--fine", action="store_true", help="keep layer indices in the per-GEMM table")
 args = ap.parse_args()
 
 eng = bench.build_engine("cuda:0")
@@ -83,7 +84,8 @@ def timed_call(self, stream=None, backend=None):
     orig_call(self, stream, backend)
     e.record()
     be = self.backend if backend is None else backend
-    gemm_rec.append((self.name, be, self.flops(), s, e))
+    p_ = self.params
+    gemm_rec.append((f"{self.name} [M={p_.OW * p_.OH * p_.OB} N={p_.N} K={p_.Kc}x{p_.ntaps}]" if args.fine else self.name, be, self.flops(), s, e))
 
 
 tg.TapGemm.__call__ = timed_call
@@ -99,7 +101,7 @@ total = (time.perf_counter() - t0) * 1e3
 acc["vc.pipeline(glue: hpf, index, pad, rms, int16)"] = acc["vc.pipeline(total)"] - acc.get("hubert", 0) - acc.get("rmvpe", 0) - acc.get("synthesizer", 0)
 by = collections.defaultdict(lambda: [0, 0.0, 0.0])
 for name, be, fl, s_, e_ in gemm_rec:
-    key = re.sub(r"\d+", "#", name) + ("/simt" if be == tg.BACKEND_SIMT else "")
+    key = (name if args.fine else re.sub(r"\d+", "#", name)) + ("/simt" if be == tg.BACKEND_SIMT else "")
     by[key][0] += 1
     by[key][1] += s_.elapsed_time(e_)
     by[key][2] += fl
