@@ -184,20 +184,25 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    for (int chunk = 0; chunk < nchunks; ++chunk) {
-      const int s = chunk % STAGES;
-      const uint32_t ph = (chunk / STAGES) & 1;
-      mbar_wait(empty_bar(s), ph ^ 1u);
-      if (elect_one()) {
-        const int tap_i = chunk / kchunks;
-        const int kc0 = (chunk - tap_i * kchunks) * KCHUNK;
+    {
+      int s = 0;
+      uint32_t ph = 0;
+      const int wsel = tb * p.w_batch_step;
+      for (int tap_i = 0; tap_i < p.ntaps; ++tap_i) {
         const TgTap tap = p.taps[tap_i];
-        mbar_expect_tx(full_bar(s), STAGE_BYTES);
-        tma_load_5d(a_stage(s), &tmA, full_bar(s), tap.c_off + kc0, w0 + tap.dw, h0 + tap.dh, tb,
-                    tap.dp);
-        tma_load_3d(b_stage(s), &tmW, full_bar(s), kc0, n0, tap.widx + tb * p.w_batch_step);
+        const int cw = w0 + tap.dw, ch = h0 + tap.dh, cp = tap.dp, widx = tap.widx + wsel;
+        int ca = tap.c_off;
+        for (int kc0 = 0; kc0 < p.Kc; kc0 += KCHUNK, ca += KCHUNK) {
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          if (elect_one()) {
+            mbar_expect_tx(full_bar(s), STAGE_BYTES);
+            tma_load_5d(a_stage(s), &tmA, full_bar(s), ca, cw, ch, tb, cp);
+            tma_load_3d(b_stage(s), &tmW, full_bar(s), kc0, n0, widx);
+          }
+          __syncwarp();
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
+        }
       }
-      __syncwarp();
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================

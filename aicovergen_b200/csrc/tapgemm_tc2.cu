@@ -165,24 +165,30 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
   if (warp == 0) {
     // ===================== TMA producer =====================
+    // This loop paces the whole kernel when it is long (ncu r01d: ~75 dependent uniform-datapath instructions per
+    // k-chunk = ~600 cycles, more than the MMAs of a 128-wide chunk): no divisions, tap record loaded once per tap,
+    // stage index / phase carried incrementally.
     {
-      int it_chunk = 0;
+      int s = 0;
+      uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int w0, h0, tb, n0;
         tile_coords(tile, w0, h0, tb, n0);
-        for (int chunk = 0; chunk < nchunks; ++chunk, ++it_chunk) {
-          const int s = it_chunk % STAGES;
-          const uint32_t ph = (it_chunk / STAGES) & 1;
-          mbar_wait(empty_bar(s), ph ^ 1u);
-          if (elect_one()) {
-            const int tap_i = chunk / kchunks;
-            const int kc0 = (chunk - tap_i * kchunks) * KCHUNK;
-            const TgTap tap = p.taps[tap_i];
-            mbar_expect_tx(full_bar(s), STAGE_BYTES);
-            tma_load_5d(a_stage(s), &tmA, full_bar(s), tap.c_off + kc0, w0 + tap.dw, h0 + tap.dh, tb, tap.dp);
-            tma_load_3d(b_stage(s), &tmW, full_bar(s), kc0, n0, tap.widx + tb * p.w_batch_step);
+        const int wsel = tb * p.w_batch_step;
+        for (int tap_i = 0; tap_i < p.ntaps; ++tap_i) {
+          const TgTap tap = p.taps[tap_i];
+          const int cw = w0 + tap.dw, ch = h0 + tap.dh, cp = tap.dp, widx = tap.widx + wsel;
+          int ca = tap.c_off;
+          for (int kc0 = 0; kc0 < p.Kc; kc0 += KCHUNK, ca += KCHUNK) {
+            mbar_wait(empty_bar(s), ph ^ 1u);
+            if (elect_one()) {
+              mbar_expect_tx(full_bar(s), STAGE_BYTES);
+              tma_load_5d(a_stage(s), &tmA, full_bar(s), ca, cw, ch, tb, cp);
+              tma_load_3d(b_stage(s), &tmW, full_bar(s), kc0, n0, widx);
+            }
+            __syncwarp();
+            if (++s == STAGES) { s = 0; ph ^= 1u; }
           }
-          __syncwarp();
         }
       }
     }
@@ -190,7 +196,8 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     // ===================== MMA issuer =====================
     // whole warp walks the loops (uniform control flow -> descriptors stay in uniform registers); one elected lane issues
     {
-      int it_chunk = 0, it = 0;
+      int it = 0, s = 0;
+      uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int acc = it & 1;
         const uint32_t use = (uint32_t)(it >> 1);
@@ -201,9 +208,7 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const int n0_ = (tile % ntiles_n) * BN;
         const int nrem = p.N - n0_;
         const uint32_t IDESC = make_idesc_tf32(128, nrem >= BN ? BN : ((nrem + 15) & ~15));
-        for (int chunk = 0; chunk < nchunks; ++chunk, ++it_chunk) {
-          const int s = it_chunk % STAGES;
-          const uint32_t ph = (it_chunk / STAGES) & 1;
+        for (int chunk = 0; chunk < nchunks; ++chunk) {
           mbar_wait(full_bar(s), ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           if (elect_one()) {
@@ -216,6 +221,7 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             if (chunk == nchunks - 1) umma_commit(tfull_bar(acc));
           }
           __syncwarp();
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
       }
     }
