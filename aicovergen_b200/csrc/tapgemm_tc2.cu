@@ -19,7 +19,6 @@ int encode_map_f32(CUtensorMap* tm, const void* base, int rank, const cuuint64_t
 namespace {
 
 constexpr int KCHUNK = 32;
-constexpr int A_STAGE_BYTES = TG_TILE_M * 128;
 constexpr int EPI_WARPS = 8;
 constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 
@@ -105,13 +104,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-template <int BN, int STAGES>
+// MH = 128-row halves per tile.  MH == 2: one B tile feeds two MMAs (rows 0-127 and 128-255 of a 256-row A box), which
+// cuts the L2->SM operand bytes per FLOP by 1.3-1.5x — the persistent kernel runs at the L2 throughput cap
+// (~43 B/clk/SM, profiles/r01_ncu_kernels.md), so that ratio is its speed.
+template <int BN, int STAGES, int MH>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-                   const __grid_constant__ TgParams p, int ntiles_n, int total_tiles) {
+                   const __grid_constant__ TgParams p, int ntiles_n, int total_tiles, int tbw, int tbh) {
+  constexpr int A_STAGE_BYTES = MH * TG_TILE_M * 128;
   constexpr int B_STAGE_BYTES = BN * 128;
   constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  constexpr uint32_t TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;     // power of two for BN in {32,64,128,256}
+  constexpr int ACC_COLS = MH * BN;                                // one accumulator stage: MH blocks of BN columns
+  constexpr int NACC = (2 * ACC_COLS <= 512) ? 2 : 1;              // double-buffered when TMEM allows
+  constexpr uint32_t TMEM_COLS = (NACC * ACC_COLS < 32) ? 32 : NACC * ACC_COLS;   // power of two for BN in {32..256}
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
@@ -124,8 +129,8 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform role index
-  const int ntw = (p.OW + p.BW - 1) / p.BW;
-  const int nth = (p.OH + p.BH - 1) / p.BH;
+  const int ntw = (p.OW + tbw - 1) / tbw;
+  const int nth = (p.OH + tbh - 1) / tbh;
   const int kchunks = (p.Kc + KCHUNK - 1) / KCHUNK;
   const int nchunks = p.ntaps * kchunks;
 
@@ -136,7 +141,7 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < NACC; ++a) {
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), BN >= 64 ? EPI_WARPS : 4);   // BN == 32: only the first column group has work
     }
@@ -158,8 +163,8 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int tw = mt % ntw; mt /= ntw;
     const int th = mt % nth; mt /= nth;
     tb = mt;
-    w0 = tw * p.BW;
-    h0 = th * p.BH;
+    w0 = tw * tbw;
+    h0 = th * tbh;
     n0 = nt * BN;
   };
 
@@ -199,11 +204,11 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       int it = 0, s = 0;
       uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int acc = it & 1;
-        const uint32_t use = (uint32_t)(it >> 1);
+        const int acc = it % NACC;
+        const uint32_t use = (uint32_t)(it / NACC);
         mbar_wait(tempty_bar(acc), (use & 1u) ^ 1u);      // epilogue has drained this accumulator stage
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
         // instruction N = the live part of this n-tile rounded up to 16 (e.g. 48 for the MDX c=48 layers)
         const int n0_ = (tile % ntiles_n) * BN;
         const int nrem = p.N - n0_;
@@ -216,7 +221,10 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             const uint64_t bdesc = make_smem_desc(b_stage(s));
 #pragma unroll
             for (int k = 0; k < KCHUNK / 8; ++k)
-              umma_tf32(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, (chunk > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+              for (int mh = 0; mh < MH; ++mh)       // 128 rows x 128 B = 16 KB further into the A box: +1024 in the (addr >> 4) field
+                umma_tf32(d_tmem + (uint32_t)(mh * BN), adesc + (uint64_t)(mh * 1024 + 2 * k), bdesc + (uint64_t)(2 * k), IDESC,
+                          (chunk > 0 || k > 0) ? 1u : 0u);
             umma_commit(empty_bar(s));
             if (chunk == nchunks - 1) umma_commit(tfull_bar(acc));
           }
@@ -234,19 +242,22 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       int w0, h0, tb, n0;
       tile_coords(tile, w0, h0, tb, n0);
-      const int m = q * 32 + lane;
-      const TgRow r = tg_row(p, tb, h0 + m / p.BW, w0 + m % p.BW);
-      const int acc = it & 1;
-      const uint32_t use = (uint32_t)(it >> 1);
+      const int acc = it % NACC;
+      const uint32_t use = (uint32_t)(it / NACC);
       mbar_wait(tfull_bar(acc), use & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-      for (int c0 = cpar * 32; c0 < BN; c0 += 64) {
-        if (n0 + c0 >= p.N) break;                 // warp-uniform
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), v);
-        tg_store16(p, r, n0 + c0, v);
-        tg_store16(p, r, n0 + c0 + 16, v + 16);
+      for (int mh = 0; mh < MH; ++mh) {
+        const int m = mh * 128 + q * 32 + lane;      // row inside the (tbw x tbh) box, w fastest
+        const TgRow r = tg_row(p, tb, h0 + m / tbw, w0 + m % tbw);
+#pragma unroll 1
+        for (int c0 = cpar * 32; c0 < BN; c0 += 64) {
+          if (n0 + c0 >= p.N) break;                 // warp-uniform
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS + mh * BN + c0), v);
+          tg_store16(p, r, n0 + c0, v);
+          tg_store16(p, r, n0 + c0 + 16, v + 16);
+        }
       }
       // all TMEM reads of this accumulator stage are complete (tcgen05.wait::ld inside tmem_ld32)
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -262,17 +273,17 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   }
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int MH>
 int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmW, const TgParams& p, int ntiles_n, int total_tiles,
-               int grid, cudaStream_t stream) {
-  constexpr int smem = STAGES * (A_STAGE_BYTES + BN * 128) + 8 * (2 * STAGES + 6) + 1024;
+               int grid, int tbw, int tbh, cudaStream_t stream) {
+  constexpr int smem = STAGES * (MH * TG_TILE_M * 128 + BN * 128) + 8 * (2 * STAGES + 6) + 1024;
   static_assert(smem <= 227 * 1024, "shared memory budget");
   static bool configured = false;
   if (!configured) {
-    B200VC_CHECK_CUDA(cudaFuncSetAttribute(tapgemm_tc2_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    B200VC_CHECK_CUDA(cudaFuncSetAttribute(tapgemm_tc2_kernel<BN, STAGES, MH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  tapgemm_tc2_kernel<BN, STAGES><<<grid, NUM_THREADS, smem, stream>>>(tmA, tmW, p, ntiles_n, total_tiles);
+  tapgemm_tc2_kernel<BN, STAGES, MH><<<grid, NUM_THREADS, smem, stream>>>(tmA, tmW, p, ntiles_n, total_tiles, tbw, tbh);
   return kOk;
 }
 
@@ -291,17 +302,27 @@ int num_sms() {
 
 int tapgemm_tc2_launch(const TgParams& p, cudaStream_t stream) {
   B200VC_REQUIRE(tapgemm_tc_supported(p), "tapgemm_tc: operand alignment not TMA-compatible");
-  const int ntw = ceil_div(p.OW, p.BW), nth = ceil_div(p.OH, p.BH);
-  const long long mtiles = (long long)ntw * nth * p.OB;
   const int BN = p.N > 128 ? 256 : (p.N > 64 ? 128 : (p.N > 32 ? 64 : 32));
   const int ntiles_n = ceil_div(p.N, BN);
+  // 256-row tiles (two MMAs per B tile) when they neither starve the SMs nor add padded rows
+  int tbw = p.BW, tbh = p.BH, MH = 1;
+  {
+    const int bw2 = p.BH == 1 ? 2 * p.BW : p.BW, bh2 = p.BH == 1 ? 1 : 2 * p.BH;
+    if (bw2 <= 256 && bh2 <= 256) {
+      const long long t1 = (long long)ceil_div(p.OW, p.BW) * ceil_div(p.OH, p.BH) * p.OB;
+      const long long t2 = (long long)ceil_div(p.OW, bw2) * ceil_div(p.OH, bh2) * p.OB;
+      if (t2 * ntiles_n >= num_sms() && 2 * t2 * 100 <= t1 * 105) { tbw = bw2; tbh = bh2; MH = 2; }
+    }
+  }
+  const int ntw = ceil_div(p.OW, tbw), nth = ceil_div(p.OH, tbh);
+  const long long mtiles = (long long)ntw * nth * p.OB;
   const long long total = mtiles * ntiles_n;
   B200VC_REQUIRE(total > 0 && total < (1ll << 31), "tapgemm_tc: bad tile count %lld", total);
 
   CUtensorMap tmA, tmW;
   {
     cuuint64_t dims[5], strides[4];
-    cuuint32_t box[5] = {KCHUNK, (cuuint32_t)p.BW, (cuuint32_t)p.BH, 1, 1};
+    cuuint32_t box[5] = {KCHUNK, (cuuint32_t)tbw, (cuuint32_t)tbh, 1, 1};
     long long span = 1;
     for (int i = 0; i < 5; ++i) {
       dims[i] = (cuuint64_t)(p.a_dim[i] > 0 ? p.a_dim[i] : 1);
@@ -331,11 +352,20 @@ int tapgemm_tc2_launch(const TgParams& p, cudaStream_t stream) {
   }
   const int grid = (int)(total < num_sms() ? total : num_sms());
   int rc;
-  switch (BN) {
-    case 256: rc = launch_cfg<256, 4>(tmA, tmW, p, ntiles_n, (int)total, grid, stream); break;
-    case 128: rc = launch_cfg<128, 6>(tmA, tmW, p, ntiles_n, (int)total, grid, stream); break;
-    case 64:  rc = launch_cfg<64, 8>(tmA, tmW, p, ntiles_n, (int)total, grid, stream); break;
-    default:  rc = launch_cfg<32, 8>(tmA, tmW, p, ntiles_n, (int)total, grid, stream); break;
+  if (MH == 2) {
+    switch (BN) {
+      case 256: rc = launch_cfg<256, 3, 2>(tmA, tmW, p, ntiles_n, (int)total, grid, tbw, tbh, stream); break;
+      case 128: rc = launch_cfg<128, 4, 2>(tmA, tmW, p, ntiles_n, (int)total, grid, tbw, tbh, stream); break;
+      case 64:  rc = launch_cfg<64, 5, 2>(tmA, tmW, p, ntiles_n, (int)total, grid, tbw, tbh, stream); break;
+      default:  rc = launch_cfg<32, 6, 2>(tmA, tmW, p, ntiles_n, (int)total, grid, tbw, tbh, stream); break;
+    }
+  } else {
+    switch (BN) {
+      case 256: rc = launch_cfg<256, 4, 1>(tmA, tmW, p, ntiles_n, (int)total, grid, tbw, tbh, stream); break;
+      case 128: rc = launch_cfg<128, 6, 1>(tmA, tmW, p, ntiles_n, (int)total, grid, tbw, tbh, stream); break;
+      case 64:  rc = launch_cfg<64, 8, 1>(tmA, tmW, p, ntiles_n, (int)total, grid, tbw, tbh, stream); break;
+      default:  rc = launch_cfg<32, 8, 1>(tmA, tmW, p, ntiles_n, (int)total, grid, tbw, tbh, stream); break;
+    }
   }
   if (rc) return rc;
   count_launch();
