@@ -106,6 +106,8 @@ def _declare(lib):
     lib.b200vc_tapgemm_tc_supported.restype = C.c_int
     lib.b200vc_tapgemm_ws_applicable.argtypes = [C.POINTER(TapGemmParams)]
     lib.b200vc_tapgemm_ws_applicable.restype = C.c_int
+    lib.b200vc_tapgemm_set_rows256.argtypes = [C.c_int]
+    lib.b200vc_tapgemm_set_rows256.restype = C.c_int
     # later-declared entry points register themselves via declare_optional()
     for name, (argtypes, restype) in _EXTRA.items():
         fn = getattr(lib, name)

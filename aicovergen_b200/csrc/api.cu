@@ -47,6 +47,11 @@ int b200vc_tapgemm(const b200vc_tapgemm_params* p, int backend, void* stream) {
   return kErrInvalidArg;
 }
 
+int b200vc_tapgemm_set_rows256(int on) {
+  tapgemm_tc2_set_rows256(on);
+  return kOk;
+}
+
 int b200vc_tapgemm_tc_supported(const b200vc_tapgemm_params* p) {
   return (p && tapgemm_tc_supported(*p)) ? 1 : 0;
 }

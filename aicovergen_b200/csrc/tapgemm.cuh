@@ -285,6 +285,7 @@ int tapgemm_simt_launch(const TgParams& p, cudaStream_t stream);
 int tapgemm_tc_launch(const TgParams& p, cudaStream_t stream);    // v1: one tile per CTA
 int tapgemm_tc2_launch(const TgParams& p, cudaStream_t stream);   // v2: persistent, double-buffered TMEM, coalesced epilogue
 bool tapgemm_tc_supported(const TgParams& p);
+void tapgemm_tc2_set_rows256(int on);                            // experimental 256-row tiles of the persistent kernel
 int tapgemm_ws_launch(const TgParams& p, cudaStream_t stream);    // v3: weight-stationary + halo (small-channel convs)
 bool tapgemm_ws_applicable(const TgParams& p);
 

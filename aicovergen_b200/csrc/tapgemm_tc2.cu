@@ -10,6 +10,7 @@
 // Same descriptor, same epilogue semantics as tapgemm.cuh (scalar form tg_epi1).
 #include "tapgemm.cuh"
 #include <cuda.h>
+#include <cstdlib>
 
 namespace b200vc {
 
@@ -300,13 +301,20 @@ int num_sms() {
 
 }  // namespace
 
+static int g_rows256 = [] { const char* e = getenv("B200VC_TC2_ROWS256"); return (e && e[0] == '1') ? 1 : 0; }();
+void tapgemm_tc2_set_rows256(int on) { g_rows256 = on ? 1 : 0; }
+
 int tapgemm_tc2_launch(const TgParams& p, cudaStream_t stream) {
   B200VC_REQUIRE(tapgemm_tc_supported(p), "tapgemm_tc: operand alignment not TMA-compatible");
   const int BN = p.N > 128 ? 256 : (p.N > 64 ? 128 : (p.N > 32 ? 64 : 32));
   const int ntiles_n = ceil_div(p.N, BN);
-  // 256-row tiles (two MMAs per B tile) when they neither starve the SMs nor add padded rows
+  // 256-row tiles (two MMAs per B tile) halve the weight-tile L2->SM traffic.  Measured on B200 they do NOT pay: the
+  // kernel is bound by shared-memory bandwidth (TMA writes + UMMA operand reads share 128 B/clk/SM, and every MMA
+  // re-reads its B slice), not by L2 — C256 k11 662 -> 608 TFLOP/s, 768->3072 linear 306 -> 221, C128 k7 486 -> 509.
+  // Kept behind b200vc_tapgemm_set_rows256(1) (initial value: env B200VC_TC2_ROWS256) for experiments and tests.
+  const bool rows256 = g_rows256 != 0;
   int tbw = p.BW, tbh = p.BH, MH = 1;
-  {
+  if (rows256) {
     const int bw2 = p.BH == 1 ? 2 * p.BW : p.BW, bh2 = p.BH == 1 ? 1 : 2 * p.BH;
     if (bw2 <= 256 && bh2 <= 256) {
       const long long t1 = (long long)ceil_div(p.OW, p.BW) * ceil_div(p.OH, p.BH) * p.OB;

@@ -119,6 +119,8 @@ int64_t b200vc_sizeof_tapgemm_params(void);
 
 /* ---- tap-GEMM ---- */
 int b200vc_tapgemm(const b200vc_tapgemm_params* p, int backend, void* stream);
+/* experimental: let the persistent tcgen05 kernel use 256-row tiles (two MMAs per weight tile); off by default */
+int b200vc_tapgemm_set_rows256(int on);
 /* 1 when the descriptor satisfies the TMA alignment rules of the tcgen05 path */
 int b200vc_tapgemm_tc_supported(const b200vc_tapgemm_params* p);
 /* 1 when the descriptor is a small-channel regular convolution the weight-stationary kernel handles */

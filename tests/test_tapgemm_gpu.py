@@ -4,6 +4,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
+from aicovergen_b200 import _ffi
 from aicovergen_b200 import tapgemm as tg
 
 pytestmark = pytest.mark.gpu
@@ -266,18 +267,23 @@ def test_conv_transpose2d_k2s2_two_gemms(bname, backend, tol, B, H, W, Ci, Co):
 
 @pytest.mark.parametrize("T,Ci,Co,k", [(50000, 64, 160, 3), (41000, 96, 96, 5), (45000, 32, 48, 3), (70001, 32, 32, 1)])
 def test_persistent_256_row_tiles_conv1d(T, Ci, Co, k):
-    """Problems with >= #SM 256-row tiles take the two-MMAs-per-B-tile path of the persistent kernel (BN 256: single
+    """(experimental path, enabled through b200vc_tapgemm_set_rows256)
+    Problems with >= #SM 256-row tiles take the two-MMAs-per-B-tile path of the persistent kernel (BN 256: single
     TMEM stage; BN <= 128: double-buffered); checked against the exact-fp32 SIMT kernel on the same device."""
     g = torch.Generator().manual_seed(T)
     x, w, b = torch.randn(T, Ci, generator=g), torch.randn(Co, Ci, k, generator=g) / (Ci * k) ** 0.5, torch.randn(Co, generator=g)
     res = torch.randn(T, Co, generator=g)
     xd, wd, bd, rd = dev(x, tg.pack_conv1d(w), b, res)
     outs = []
-    for be in (tg.BACKEND_SIMT, tg.BACKEND_TC_V1):
-        o = torch.full((T, Co), float("nan"), device="cuda")
-        tg.conv1d(xd, wd, o, dilation=2, epi=tg.Epi(bias=bd, act_pre=tg.ACT_LRELU, act_pre_p=0.1, res=rd), backend=be)()
-        outs.append(o)
-    torch.cuda.synchronize()
+    _ffi.lib().b200vc_tapgemm_set_rows256(1)
+    try:
+        for be in (tg.BACKEND_SIMT, tg.BACKEND_TC_V1):
+            o = torch.full((T, Co), float("nan"), device="cuda")
+            tg.conv1d(xd, wd, o, dilation=2, epi=tg.Epi(bias=bd, act_pre=tg.ACT_LRELU, act_pre_p=0.1, res=rd), backend=be)()
+            outs.append(o)
+        torch.cuda.synchronize()
+    finally:
+        _ffi.lib().b200vc_tapgemm_set_rows256(0)
     check(outs[1].cpu(), outs[0].cpu(), 2e-3, f"persistent 256-row tiles T={T} {Ci}->{Co} k{k}")
 
 
@@ -289,9 +295,13 @@ def test_persistent_256_row_tiles_conv2d():
     b = torch.randn(Co, generator=g)
     xd, wd, bd = dev(x, tg.pack_conv2d(w), b)
     outs = []
-    for be in (tg.BACKEND_SIMT, tg.BACKEND_TC_V1):
-        o = torch.full((B, H, W, Co), float("nan"), device="cuda")
-        tg.conv2d(xd, wd, o, 3, 3, (1, 1), tg.Epi(bias=bd, act_pre=tg.ACT_RELU), backend=be)()
-        outs.append(o)
-    torch.cuda.synchronize()
+    _ffi.lib().b200vc_tapgemm_set_rows256(1)
+    try:
+        for be in (tg.BACKEND_SIMT, tg.BACKEND_TC_V1):
+            o = torch.full((B, H, W, Co), float("nan"), device="cuda")
+            tg.conv2d(xd, wd, o, 3, 3, (1, 1), tg.Epi(bias=bd, act_pre=tg.ACT_RELU), backend=be)()
+            outs.append(o)
+        torch.cuda.synchronize()
+    finally:
+        _ffi.lib().b200vc_tapgemm_set_rows256(0)
     check(outs[1].cpu(), outs[0].cpu(), 2e-3, "persistent 256-row tiles conv2d")
