@@ -207,24 +207,31 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     // whole warp walks the loop (uniform control flow -> descriptors stay in uniform registers); one elected lane issues
-    for (int chunk = 0; chunk < nchunks; ++chunk) {
-      const int s = chunk % STAGES;
-      const uint32_t ph = (chunk / STAGES) & 1;
-      mbar_wait(full_bar(s), ph);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (elect_one()) {
-        const uint64_t adesc = make_smem_desc(a_stage(s));
-        const uint64_t bdesc = make_smem_desc(b_stage(s));
-#pragma unroll
-        for (int k = 0; k < KCHUNK / 8; ++k) {
-          // advance 8 tf32 = 32 bytes inside the swizzle atom: +2 in the (addr >> 4) field
-          umma_tf32(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC,
-                    (chunk > 0 || k > 0) ? 1u : 0u);
+    {
+      const int klast = ((p.Kc - (kchunks - 1) * KCHUNK) + 7) >> 3;   // short last k-chunk: only the K=8 steps with data
+      uint32_t accum = 0u;
+      int s = 0, kc = 0;
+      uint32_t ph = 0;
+      for (int chunk = 0; chunk < nchunks; ++chunk) {
+        mbar_wait(full_bar(s), ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int nk = (kc == kchunks - 1) ? klast : KCHUNK / 8;
+        if (elect_one()) {
+          const uint64_t adesc = make_smem_desc(a_stage(s));
+          const uint64_t bdesc = make_smem_desc(b_stage(s));
+          for (int k = 0; k < nk; ++k) {
+            // advance 8 tf32 = 32 bytes inside the swizzle atom: +2 in the (addr >> 4) field
+            umma_tf32(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, accum);
+            accum = 1u;
+          }
+          umma_commit(empty_bar(s));   // frees this smem stage once the MMAs have read it
+          if (chunk == nchunks - 1) umma_commit(tmem_full_bar);    // accumulator complete
         }
-        umma_commit(empty_bar(s));   // frees this smem stage once the MMAs have read it
-        if (chunk == nchunks - 1) umma_commit(tmem_full_bar);    // accumulator complete
+        accum = 1u;
+        __syncwarp();
+        if (++s == STAGES) { s = 0; ph ^= 1u; }
+        if (++kc == kchunks) kc = 0;
       }
-      __syncwarp();
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================

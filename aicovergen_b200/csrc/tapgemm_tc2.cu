@@ -214,23 +214,29 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const int n0_ = (tile % ntiles_n) * BN;
         const int nrem = p.N - n0_;
         const uint32_t IDESC = make_idesc_tf32(128, nrem >= BN ? BN : ((nrem + 15) & ~15));
-        for (int chunk = 0; chunk < nchunks; ++chunk) {
+        // the last k-chunk of a tap may be short (Kc = 48 -> 32 + 16): issue only the K=8 steps that hold data
+        const int klast = ((p.Kc - (kchunks - 1) * KCHUNK) + 7) >> 3;
+        uint32_t accum = 0u;
+        for (int chunk = 0, kc = 0; chunk < nchunks; ++chunk) {
           mbar_wait(full_bar(s), ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const int nk = (kc == kchunks - 1) ? klast : KCHUNK / 8;
           if (elect_one()) {
             const uint64_t adesc = make_smem_desc(a_stage(s));
             const uint64_t bdesc = make_smem_desc(b_stage(s));
-#pragma unroll
-            for (int k = 0; k < KCHUNK / 8; ++k)
+            for (int k = 0; k < nk; ++k) {
 #pragma unroll
               for (int mh = 0; mh < MH; ++mh)       // 128 rows x 128 B = 16 KB further into the A box: +1024 in the (addr >> 4) field
-                umma_tf32(d_tmem + (uint32_t)(mh * BN), adesc + (uint64_t)(mh * 1024 + 2 * k), bdesc + (uint64_t)(2 * k), IDESC,
-                          (chunk > 0 || k > 0) ? 1u : 0u);
+                umma_tf32(d_tmem + (uint32_t)(mh * BN), adesc + (uint64_t)(mh * 1024 + 2 * k), bdesc + (uint64_t)(2 * k), IDESC, accum);
+              accum = 1u;
+            }
             umma_commit(empty_bar(s));
             if (chunk == nchunks - 1) umma_commit(tfull_bar(acc));
           }
+          accum = 1u;
           __syncwarp();
           if (++s == STAGES) { s = 0; ph ^= 1u; }
+          if (++kc == kchunks) kc = 0;
         }
       }
     }
