@@ -12,7 +12,7 @@ constexpr int BK = 16;
 constexpr int NT = 256;
 
 template <int BN>
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, BN >= 128 ? 2 : (BN >= 64 ? 3 : 4))
 tapgemm_simt_kernel(const __grid_constant__ TgParams p) {
   constexpr int CPT = BN / 16;               // columns per thread
   constexpr int VW = (CPT >= 4) ? 4 : CPT;   // vector width of a column group

@@ -18,8 +18,9 @@ from .tapgemm import Epi
 
 
 class IvfIndexB200:
-    def __init__(self, centroids: np.ndarray, vectors: np.ndarray, device: str = "cuda:0"):
-        """centroids [nlist, d], vectors [ntotal, d] in insertion (id) order."""
+    def __init__(self, centroids: np.ndarray, vectors: np.ndarray, device: str = "cuda:0", list_of: Optional[np.ndarray] = None):
+        """centroids [nlist, d], vectors [ntotal, d] in insertion (id) order.  `list_of` [ntotal]: the inverted list of
+        every vector as stored in an index file; when absent vectors go to their nearest centroid (what faiss' add does)."""
         self.device = torch.device(device)
         cent = torch.from_numpy(np.ascontiguousarray(centroids, dtype=np.float32))
         vecs = torch.from_numpy(np.ascontiguousarray(vectors, dtype=np.float32))
@@ -30,7 +31,7 @@ class IvfIndexB200:
         self.cent_n2 = (cent.double() ** 2).sum(1).float().to(self.device)  # + |c|^2 as per-column bias
         # ---- inverted lists: assign every database vector to its nearest centroid (on the device, same kernels)
         vdev = vecs.to(self.device)
-        assign = self._coarse(vdev)
+        assign = self._coarse(vdev) if list_of is None else torch.from_numpy(np.ascontiguousarray(list_of, dtype=np.int64)).to(self.device)
         order = torch.argsort(assign.long(), stable=True)                   # list order == insertion order
         self.ids = order.contiguous()                                        # int64: sorted position -> original id
         self.vecs_sorted = vdev[order].contiguous()
@@ -86,10 +87,16 @@ def write_index_npz(path: str, centroids: np.ndarray, vectors: np.ndarray):
 
 
 def read_index(path: str, device: str = "cuda:0") -> IvfIndexB200:
-    """Counterpart of faiss.read_index at vc_infer_pipeline.py:505.  `.npz` (write_index_npz) is supported now;
-    decoding faiss' binary IndexIVFFlat ("IwFl") files is SURVEY.md §8(f) rank 1 and raises until then
-    (the reference's own behaviour on a failed read is to continue without an index, :508-510)."""
+    """Counterpart of faiss.read_index at vc_infer_pipeline.py:505: faiss' binary IndexIVFFlat files ("IwFl", what RVC
+    voice models ship) through aicovergen_b200.faiss_io, or the `.npz` form of write_index_npz.  Unsupported index types
+    raise (the reference's own behaviour on a failed read is to continue without an index, :508-510)."""
     if str(path).endswith(".npz"):
         z = np.load(path)
         return IvfIndexB200(z["centroids"], z["vectors"], device)
-    raise NotImplementedError(f"{path}: faiss binary index parsing is not implemented yet (use an .npz index)")
+    from .faiss_io import METRIC_L2, read_ivfflat
+    data = read_ivfflat(str(path))
+    if data.metric != METRIC_L2:
+        raise NotImplementedError(f"{path}: metric {data.metric}; the RVC path uses L2 IVF-Flat indexes")
+    if not data.ids_sequential:
+        raise NotImplementedError(f"{path}: custom ids (add_with_ids) are not addressable by reconstruct_n(0, ntotal)")
+    return IvfIndexB200(data.centroids, data.vectors, device, list_of=data.list_of)

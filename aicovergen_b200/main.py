@@ -94,7 +94,11 @@ class CoverEngine:
     @torch.no_grad()
     def mix(self, ai_vocals_i16: np.ndarray, backup: torch.Tensor, instrumental: torch.Tensor, main_gain=0, backup_gain=0,
             inst_gain=0) -> torch.Tensor:
-        a = torch.from_numpy(ai_vocals_i16.astype(np.float32) / 32768.0).to(self.device)
+        dev_i16 = getattr(self.vc, "last_output_device", None)
+        if dev_i16 is not None and dev_i16.numel() == ai_vocals_i16.size and dev_i16.device == torch.device(self.device):
+            a = dev_i16.float() / 32768.0       # the utterance VC.pipeline just produced is still in HBM: no H2D
+        else:
+            a = torch.from_numpy(ai_vocals_i16.astype(np.float32) / 32768.0).to(self.device)
         out = torch.empty_like(backup)
         ops.mix3(a, self.tgt_sr, backup.contiguous(), instrumental.contiguous(), out, 44100, db_gain(-4 + main_gain),
                  db_gain(-6 + backup_gain), db_gain(-7 + inst_gain))

@@ -264,6 +264,8 @@ class VC(object):
             raise NotImplementedError("resample_sr != 0 needs librosa.resample; rvc_infer always passes 0 (rvc.py:150)")
         if self.keep_float:
             self.last_float_mixed = audio_dev.cpu().numpy()
-        audio_opt = ops.to_int16_peak_guard(audio_dev).cpu().numpy()      # the single D2H of the converted utterance
+        out_i16 = ops.to_int16_peak_guard(audio_dev)
+        self.last_output_device = out_i16        # the same samples still in HBM (CoverEngine.mix reads them here)
+        audio_opt = out_i16.cpu().numpy()         # the single D2H of the converted utterance
         del pitch, pitchf, sid
         return audio_opt

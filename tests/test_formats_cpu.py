@@ -1,0 +1,53 @@
+"""On-disk formats: faiss IndexIVFFlat binary files."""
+import struct
+
+import numpy as np
+import pytest
+
+from aicovergen_b200 import faiss_io
+
+
+def _toy(nlist=7, d=12, n=200, seed=0):
+    rng = np.random.default_rng(seed)
+    cent = rng.standard_normal((nlist, d)).astype(np.float32)
+    vec = rng.standard_normal((n, d)).astype(np.float32)
+    d2 = ((vec[:, None, :] - cent[None]) ** 2).sum(-1)
+    return cent, vec, d2.argmin(1)
+
+
+@pytest.mark.parametrize("nlist,n", [(7, 200), (40, 25), (3, 0)])
+def test_ivfflat_round_trip(tmp_path, nlist, n):
+    cent, vec, lof = _toy(nlist=nlist, n=n)
+    p = str(tmp_path / "added_IVF7_Flat_nprobe_1_toy.index")
+    faiss_io.write_ivfflat(p, cent, vec, lof, nprobe=1)
+    data = faiss_io.read_ivfflat(p)
+    assert (data.d, data.nlist, data.nprobe, data.metric) == (12, nlist, 1, faiss_io.METRIC_L2)
+    assert data.ids_sequential
+    np.testing.assert_array_equal(data.centroids, cent)
+    np.testing.assert_array_equal(data.vectors, vec)          # reconstruct_n(0, ntotal) order
+    np.testing.assert_array_equal(data.list_of, lof)
+
+
+def test_ivfflat_byte_layout_matches_faiss_headers(tmp_path):
+    """Field widths of the published faiss 1.7 serialisation: 4-byte fourcc, 33-byte index header, u64 nlist/nprobe."""
+    cent, vec, lof = _toy()
+    p = str(tmp_path / "t.index")
+    faiss_io.write_ivfflat(p, cent, vec, lof)
+    b = open(p, "rb").read()
+    assert b[:4] == b"IwFl"
+    d, ntotal, dummy1, dummy2, trained, metric = struct.unpack_from("<iqqqBi", b, 4)
+    assert (d, ntotal, dummy1, dummy2, trained, metric) == (12, 200, 1 << 20, 1 << 20, 1, 1)
+    nlist, nprobe = struct.unpack_from("<QQ", b, 4 + 33)
+    assert (nlist, nprobe) == (7, 1)
+    assert b[4 + 33 + 16: 4 + 33 + 20] == b"IxF2"
+    assert b.find(b"ilar") > 0 and b.find(b"full") > b.find(b"ilar")
+
+
+def test_rejects_other_index_types(tmp_path):
+    p = tmp_path / "x.index"
+    p.write_bytes(b"IxF2" + b"\0" * 64)
+    with pytest.raises(faiss_io.FaissFormatError):
+        faiss_io.read_ivfflat(str(p))
+    p.write_bytes(b"IwFl" + b"\0" * 10)
+    with pytest.raises(faiss_io.FaissFormatError):
+        faiss_io.read_ivfflat(str(p))

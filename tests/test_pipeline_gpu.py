@@ -31,7 +31,7 @@ def vocal_like(seconds, sr=16000, seed=7):
     return (0.5 * x / np.abs(x).max()).astype(np.float32)
 
 
-@pytest.mark.parametrize("with_index", [False, True])
+@pytest.mark.parametrize("with_index", [False, "npz", "faiss"])
 def test_vc_pipeline_parity(with_index):
     from aicovergen_b200.hubert import HubertB200
     from aicovergen_b200.index import write_index_npz
@@ -50,9 +50,15 @@ def test_vc_pipeline_parity(with_index):
         base = ohub.extract_features(hsd, torch.from_numpy(vocal_like(4.0, seed=3))[None], 12)[0]
         cent, vecs = make_ivf_index_data(base, n_total=4000, nlist=64)
         index = IvfFlatIndex(cent, vecs)
-        tmp = tempfile.NamedTemporaryFile(suffix=".npz", delete=False)
-        tmp.close()
-        write_index_npz(tmp.name, cent, vecs)
+        if with_index == "npz":
+            tmp = tempfile.NamedTemporaryFile(suffix=".npz", delete=False)
+            tmp.close()
+            write_index_npz(tmp.name, cent, vecs)
+        else:   # the binary IndexIVFFlat layout faiss writes (what RVC voice models ship): read back through faiss_io
+            from aicovergen_b200.faiss_io import write_ivfflat
+            tmp = tempfile.NamedTemporaryFile(suffix="_IVF64_Flat_nprobe_1.index", delete=False)
+            tmp.close()
+            write_ivfflat(tmp.name, cent, vecs, index.assign)
         file_index = tmp.name
     ref_i16, info = opipe.pipeline(hsd, cpt, rsd, audio.copy(), index=index, seed=5, return_all=True, **xs)
 
