@@ -338,7 +338,7 @@ class MDX:
             raise RuntimeError("b200vc MDX has no CPU execution provider")
         self.device = torch.device(f"cuda:{processor}")
         self.model = params
-        sd = model_path if isinstance(model_path, dict) else load_mdx_weights(model_path)
+        sd = model_path if isinstance(model_path, dict) else load_mdx_weights(model_path, params.dim_t)
         if isinstance(sd, dict) and "state_dict" in sd:
             sd = sd["state_dict"]
         self.ort = ConvTDFNetB200(sd, self.device, backend)          # name kept from the reference (mdx.py:74)
@@ -434,11 +434,15 @@ class MDX:
         return out.cpu().numpy()
 
 
-def load_mdx_weights(path):
-    """`.pt/.pth` state dict of the restated ConvTDFNet. Decoding the initialisers of a UVR `.onnx` file
-    (hand-rolled protobuf reader) is SURVEY.md §8(f) rank 1."""
+def load_mdx_weights(path, dim_t: Optional[int] = None):
+    """`.pt/.pth` state dict of the restated ConvTDFNet, or a UVR `.onnx` file decoded with the hand-rolled protobuf
+    reader in onnx_io (what `ort.InferenceSession(model_path)` loads at mdx.py:74); `dim_t` (from model_data.json) is
+    needed for `.onnx` because the graph is shape-agnostic along time."""
     if str(path).endswith(".onnx"):
-        raise NotImplementedError(f"{path}: ONNX initialiser extraction is not implemented yet (provide a .pt state dict)")
+        from .onnx_io import convtdfnet_state_dict
+        if dim_t is None:
+            raise ValueError(f"{path}: dim_t (2 ** mdx_dim_t_set of the model_data.json entry) is required for .onnx weights")
+        return convtdfnet_state_dict(str(path), int(dim_t))
     return torch.load(path, map_location="cpu", weights_only=False)
 
 
@@ -508,7 +512,10 @@ def run_mdx(model_params, output_dir, model_path, filename, exclude_main=False, 
     m_threads = 1 if vram_gb < 8 else 2
     model_hash = MDX.get_hash(model_path)
     mp = model_params.get(model_hash)
-    weights = load_mdx_weights(model_path)
+    is_onnx = str(model_path).endswith(".onnx")
+    if is_onnx and mp is None:
+        raise KeyError(f"{model_path}: md5 tail {model_hash} is not in model_data.json (mdx.py:81-90)")
+    weights = load_mdx_weights(model_path, 2 ** mp["mdx_dim_t_set"] if is_onnx else None)
     if mp is None and isinstance(weights, dict) and "params" in weights:
         mp = weights["params"]                      # synthetic checkpoints carry their own model_data entry
     model = MDXModel(device, dim_f=mp["mdx_dim_f_set"], dim_t=2 ** mp["mdx_dim_t_set"], n_fft=mp["mdx_n_fft_scale_set"],

@@ -51,3 +51,30 @@ def test_rejects_other_index_types(tmp_path):
     p.write_bytes(b"IwFl" + b"\0" * 10)
     with pytest.raises(faiss_io.FaissFormatError):
         faiss_io.read_ivfflat(str(p))
+
+
+@pytest.mark.parametrize("fold_bn", [True, False])
+def test_onnx_convtdfnet_round_trip(tmp_path, fold_bn):
+    """state dict -> ONNX bytes (the node sequence an eval-mode export emits) -> hand-decoded protobuf -> state dict: the
+    recovered network computes the same function (oracle net on CPU) and the hyper-parameters are re-derived from shapes."""
+    import torch
+
+    from aicovergen_b200 import onnx_io
+    from aicovergen_b200.synthetic import make_mdx_state_dict
+    from oracle import mdx as om
+
+    sd = make_mdx_state_dict(dim_f=64, dim_t=16, g=8, l=2, n=2, bn=4)
+    p = str(tmp_path / "UVR_MDXNET_toy.onnx")
+    onnx_io.write_convtdfnet_onnx(p, sd, fold_bn=fold_bn)
+    inits, nodes = onnx_io.read_onnx(p)
+    assert sum(nd.op_type == "ConvTranspose" for nd in nodes) == 2
+    assert sum(nd.op_type == "BatchNormalization" for nd in nodes) == (2 * 5 if fold_bn else 2 * 5 + 1 + 2 * 5 + 2 + 2)
+    sd2 = onnx_io.convtdfnet_state_dict(p, dim_t=16)
+    assert [int(v) for v in sd2["_meta"]] == [int(v) for v in sd["_meta"]]
+    x = torch.randn(1, 4, 64, 16, generator=torch.Generator().manual_seed(0))
+    y1, y2 = om.convtdfnet(sd, x), om.convtdfnet(sd2, x)
+    assert float((y1 - y2).abs().max()) <= 2e-5 * float(y1.abs().max())
+    if not fold_bn:
+        for k_ in sd:
+            if k_ != "_meta":
+                assert torch.equal(sd[k_].float(), sd2[k_].float()), k_
