@@ -227,6 +227,57 @@ __global__ void nsf_source_kernel(const float* __restrict__ f0, const double* __
   har[n] = tanhf(lin_w * s + lin_b);
 }
 
+// Strided 1-D convolution FROM ONE input channel: out[t, c] = res[t, c] + bias[c] + sum_j w[c, j] * src[src_off + t*stride + j]
+// (samples outside [0, n_src) read as zero); out2 = act2(out).  K <= a few hundred MACs per output, 8-12 bytes of HBM
+// traffic per output: write-bound, so it is a row kernel (one thread = 4 channels of one frame), not a GEMM — as 128-row
+// tensor-core tiles with K = 1..80 the NSF noise convolutions ran at 12 % of HBM bandwidth.
+// Replaces Conv1d(1, C, k, stride) at infer_pack/models.py:477-486 (noise_convs, called :505-506) and the first
+// feature-extractor convolution of HuBERT (Cin = 1, k = 10, stride 5).
+__global__ void conv1d_from1_kernel(const float* __restrict__ src, long long n_src, const float* __restrict__ w,
+                                    const float* __restrict__ bias, const float* __restrict__ res, float* __restrict__ out,
+                                    float* __restrict__ out2, long long T, int C, int K, int stride, long long src_off,
+                                    int act2, float act2_p, int round_out2) {
+  extern __shared__ float wt[];                 // [K][C]: transposed so that a thread's 4 channels are one float4
+  for (int i = threadIdx.x; i < K * C; i += blockDim.x) {
+    const int c = i / K, j = i - c * K;
+    wt[j * C + c] = w[i];
+  }
+  __syncthreads();
+  const int c4 = C >> 2;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= T * c4) return;
+  const long long t = idx / c4;
+  const int c = (int)(idx - t * c4) << 2;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const long long s0 = src_off + t * stride;
+  for (int j = 0; j < K; ++j) {
+    const long long si = s0 + j;
+    const float x = (si >= 0 && si < n_src) ? __ldg(src + si) : 0.f;
+    const float4 ww = *reinterpret_cast<const float4*>(&wt[j * C + c]);
+    acc.x = fmaf(x, ww.x, acc.x); acc.y = fmaf(x, ww.y, acc.y); acc.z = fmaf(x, ww.z, acc.z); acc.w = fmaf(x, ww.w, acc.w);
+  }
+  if (bias) {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c));
+    acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+  }
+  const long long o = t * C + c;
+  if (res) {
+    const float4 r = *reinterpret_cast<const float4*>(res + o);
+    acc.x += r.x; acc.y += r.y; acc.z += r.z; acc.w += r.w;
+  }
+  *reinterpret_cast<float4*>(out + o) = acc;
+  if (out2) {
+    float v[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[i] = apply_act(v[i], act2, act2_p);
+      if (round_out2) v[i] = round_tf32(v[i]);
+    }
+    *reinterpret_cast<float4*>(out2 + o) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+
 // out[t] = act(sum_k sum_c w[k,c] * x[t + k - pad, c])  — conv_post (models.py:486,514-515), Cout = 1
 __global__ void conv1d_to1_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                   float* __restrict__ out, long long T, int C, int K, int pad, int act) {
@@ -405,6 +456,24 @@ int b200vc_nsf_source(const float* f0, const float* noise, float* har, double* s
   const long long L = (long long)T * upp;
   nsf_source_kernel<<<blocks_for(L, 256), 256, 0, s>>>(f0, scratch_cum, noise, har, L, upp, sr, lin_w, lin_b);
   count_launch(2);
+  B200VC_LAUNCH_CHECK();
+  return kOk;
+}
+
+int b200vc_conv1d_from1(const float* src, int64_t n_src, const float* w, const float* bias, const float* res, float* out,
+                        float* out2, int64_t T, int C, int K, int stride, int64_t src_off, int act2, float act2_p,
+                        int round_out2, void* stream) {
+  B200VC_REQUIRE(src && w && out && T > 0 && C > 0 && C % 4 == 0 && K > 0 && stride > 0 && (long long)K * C * 4 <= 160 * 1024,
+                 "conv1d_from1: bad args (C=%d K=%d)", C, K);
+  const size_t smem = (size_t)K * C * 4;
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    B200VC_CHECK_CUDA(cudaFuncSetAttribute(conv1d_from1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    configured = 160 * 1024;
+  }
+  conv1d_from1_kernel<<<blocks_for(T * (C / 4), 256), 256, smem, (cudaStream_t)stream>>>(
+      src, n_src, w, bias, res, out, out2, T, C, K, stride, src_off, act2, act2_p, round_out2);
+  count_launch();
   B200VC_LAUNCH_CHECK();
   return kOk;
 }

@@ -136,8 +136,7 @@ class _HubertPlan:
         # ---- conv0 (Cin = 1, k = 10, s = 5): rows are overlapping 10-sample frames, stride 5
         T0 = lens[0]
         c0 = torch.empty(T0, 512, **f32)
-        a0 = tg.View(self.wav, (CONV[0][1], T0, 1, 1, 1), (1, CONV[0][2], 0, 0, 0))
-        add(tg.TapGemm(a0, tg.weights(W["conv0.w2d"]), [(0, 0, 0, 0, 0)], (T0, 1, 1), tg.out_of(c0), None, tg.BACKEND_SIMT, name="conv0"))
+        add(lambda: ops.conv1d_from1(self.wav, W["conv0.w2d"], c0, CONV[0][2], 0))
         rows_even = lambda t: t + (t % 2)
         cur = torch.zeros(rows_even(T0), 512, **f32)
         gstats = torch.zeros(2 * 512, device=dev, dtype=torch.float64)

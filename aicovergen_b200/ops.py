@@ -122,6 +122,20 @@ def nsf_source(f0, noise, har, scratch, upp, sr, lin_w, lin_b):
                                             float(lin_w), float(lin_b), _s()), "nsf_source")
 
 
+_ffi.declare("b200vc_conv1d_from1", [_P, _i64, _P, _P, _P, _P, _P, _i64, _i32, _i32, _i32, _i64, _i32, _f32, _i32, _P])
+
+
+def conv1d_from1(src, w, out, stride, src_off, bias=None, res=None, out2=None, act2=0, act2_p=0.0, round_out2=False):
+    """out[t,c] = res[t,c] + bias[c] + sum_j w[c,j] * src[src_off + t*stride + j]; out2 = act2(out).  src 1-D, w [C,K], out [T,C]."""
+    T, Cc = out.shape
+    assert src.dim() == 1 and src.is_contiguous() and w.shape[0] == Cc and w.is_contiguous() and out.is_contiguous()
+    assert res is None or (res.shape == out.shape and res.is_contiguous())
+    assert out2 is None or (out2.shape == out.shape and out2.is_contiguous())
+    _ffi.check(_ffi.lib().b200vc_conv1d_from1(_p(_f32c(src)), src.numel(), _p(w), _p(bias), _p(res), _p(out), _p(out2), T, Cc,
+                                              w.shape[1], int(stride), int(src_off), int(act2), float(act2_p), int(round_out2), _s()),
+               "conv1d_from1")
+
+
 def conv1d_to1(x, w, out, pad, act_code):
     """out[t] = act(sum_{k,c} w[k,c] x[t+k-pad,c]); x [T,C] contiguous, w [K,C]."""
     T, Cc = x.shape

@@ -315,10 +315,10 @@ class _Plan:
                 s = int(np.prod(m.up_r[i + 1:])) if i + 1 < nst else 1
                 kk = W[f"nc{i}.w"].shape[1]
                 pad = s // 2 if i + 1 < nst else 0
-                av = tg.View(self.harbuf, (kk, T, 1, 1, 1), (1, s, 0, 0, 0), off=self.har_off - pad)
-                add(tg.TapGemm(av, tg.weights(W[f"nc{i}.w"]), [(0, 0, 0, 0, 0)], (T, 1, 1), tg.out_of(xs),
-                               Epi(bias=W[f"nc{i}.b"], res=xs, out2=xsl, act2=tg.ACT_LRELU, act2_p=LRELU, round_out2=R),
-                               be, name=f"noise_conv{i}"))
+                # x = ups(x) + noise_conv(har) (models.py:505-507) as one write-bound row kernel; xsl = leaky_relu(x)
+                add(lambda i=i, s=s, pad=pad, xs=xs, xsl=xsl: ops.conv1d_from1(
+                    self.harbuf, W[f"nc{i}.w"], xs, s, self.har_off - pad, bias=W[f"nc{i}.b"], res=xs, out2=xsl,
+                    act2=tg.ACT_LRELU, act2_p=LRELU, round_out2=R))
             else:
                 add(lambda xs=xs, xsl=xsl: ops.act(xs, xsl, tg.ACT_LRELU, LRELU, R))
             last_stage = i == nst - 1

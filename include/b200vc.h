@@ -167,6 +167,14 @@ int b200vc_act(const float* x, float* out, int64_t n, int act, float p, int roun
 int b200vc_nsf_source(const float* f0, const float* noise, float* har, double* scratch_cum, int T, int upp,
                       float sr, float lin_w, float lin_b, void* stream);
 
+/* Strided Conv1d from ONE input channel as a write-bound row kernel:
+ *   out[t,c] = res[t,c] + bias[c] + sum_j w[c,j] * src[src_off + t*stride + j]   (zero outside [0,n_src)); out2 = act2(out)
+ * res, bias, out2 may be NULL; res may alias out.  Replaces Conv1d(1, C, k, stride) at infer_pack/models.py:477-486,505-506
+ * (NSF noise_convs) and HuBERT's first feature-extractor convolution. */
+int b200vc_conv1d_from1(const float* src, int64_t n_src, const float* w, const float* bias, const float* res, float* out,
+                        float* out2, int64_t T, int C, int K, int stride, int64_t src_off, int act2, float act2_p,
+                        int round_out2, void* stream);
+
 /* out[t] = act(sum_k sum_c w[k,c] x[t+k-pad,c]) : Conv1d C->1 (conv_post + tanh, infer_pack/models.py:514-515) */
 int b200vc_conv1d_to1(const float* x, const float* w, float* out, int64_t T, int C, int K, int pad, int act,
                       void* stream);

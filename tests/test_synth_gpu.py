@@ -55,3 +55,26 @@ def test_synth_infer_parity(backend, tol_wave, tol_lat, P):
                    noise_z=nz.cuda(), noise_src=ns.cuda())[0]
     torch.cuda.synchronize()
     assert torch.equal(o, o2)
+
+
+@pytest.mark.parametrize("C,K,stride,pad", [(256, 80, 40, 20), (64, 4, 2, 1), (32, 1, 1, 0), (512, 10, 5, 0)])
+def test_conv1d_from1_row_kernel(C, K, stride, pad):
+    """NSF noise_convs / HuBERT conv0 as a row kernel: out = res + bias + Conv1d(1, C, K, stride, padding)(src)."""
+    import torch.nn.functional as F
+
+    from aicovergen_b200 import ops
+    from aicovergen_b200 import tapgemm as tg
+    g = torch.Generator().manual_seed(C + K)
+    n = 4000
+    src = torch.randn(n, generator=g)
+    w, b = torch.randn(C, K, generator=g) / K ** 0.5, torch.randn(C, generator=g)
+    ref = F.conv1d(src[None, None], w[:, None, :], b, stride=stride, padding=pad)[0].t().contiguous()     # [T, C]
+    T = ref.shape[0]
+    res = torch.randn(T, C, generator=g)
+    out = res.clone().cuda()
+    out2 = torch.empty(T, C, device="cuda")
+    ops.conv1d_from1(src.cuda(), w.cuda(), out, stride, -pad, bias=b.cuda(), res=out, out2=out2, act2=tg.ACT_LRELU, act2_p=0.1)
+    torch.cuda.synchronize()
+    want = ref + res
+    assert (out.cpu() - want).abs().max() < 1e-4
+    assert (out2.cpu() - F.leaky_relu(want, 0.1)).abs().max() < 1e-4
