@@ -163,14 +163,32 @@ __device__ __forceinline__ void tg_act_vec(float (&v)[NV], int act, float prm) {
   }
 }
 
-// 16 values <- 16 consecutive n at `ptr` with element stride `sn` (float4 loads when the caller knows sn == 1 and the
-// address is 16-byte aligned).
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): one lane moves a whole 32-byte sector, so a row-per-lane
+// epilogue issues full-sector requests instead of two 16-byte halves of every sector.
+__device__ __forceinline__ void tg_ldg256(float* d, const float* p) {
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3]), "=f"(d[4]), "=f"(d[5]), "=f"(d[6]), "=f"(d[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void tg_stg256(float* p, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+
+// 16 values <- 16 consecutive n at `ptr` with element stride `sn` (vector loads when the caller knows sn == 1 and the
+// address is 16-byte aligned; 256-bit when it is 32-byte aligned).
 __device__ __forceinline__ void tg_load16(float (&d)[16], const float* ptr, long long sn, bool vec) {
   if (vec) {
+    if ((reinterpret_cast<uintptr_t>(ptr) & 31) == 0) {
+      tg_ldg256(d, ptr);
+      tg_ldg256(d + 8, ptr + 8);
+    } else {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float4 t = reinterpret_cast<const float4*>(ptr)[j];
-      d[4 * j] = t.x; d[4 * j + 1] = t.y; d[4 * j + 2] = t.z; d[4 * j + 3] = t.w;
+      for (int j = 0; j < 4; ++j) {
+        const float4 t = reinterpret_cast<const float4*>(ptr)[j];
+        d[4 * j] = t.x; d[4 * j + 1] = t.y; d[4 * j + 2] = t.z; d[4 * j + 3] = t.w;
+      }
     }
   } else {
 #pragma unroll
@@ -179,14 +197,16 @@ __device__ __forceinline__ void tg_load16(float (&d)[16], const float* ptr, long
 }
 __device__ __forceinline__ void tg_put16(float* ptr, long long sn, bool vec, bool rnd, const float (&v)[16]) {
   if (vec) {
-    float4* op = reinterpret_cast<float4*>(ptr);
-    if (rnd) {
+    float w[16];
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        op[j] = make_float4(round_tf32(v[4 * j]), round_tf32(v[4 * j + 1]), round_tf32(v[4 * j + 2]), round_tf32(v[4 * j + 3]));
+    for (int j = 0; j < 16; ++j) w[j] = rnd ? round_tf32(v[j]) : v[j];
+    if ((reinterpret_cast<uintptr_t>(ptr) & 31) == 0) {
+      tg_stg256(ptr, w);
+      tg_stg256(ptr + 8, w + 8);
     } else {
+      float4* op = reinterpret_cast<float4*>(ptr);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      for (int j = 0; j < 4; ++j) op[j] = make_float4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
     }
   } else {
     // transposed layouts: consecutive lanes own consecutive pixels, so each of these scalar stores is lane-coalesced
