@@ -178,9 +178,9 @@ __device__ __forceinline__ void tg_stg256(float* p, const float* v) {
 
 // 16 values <- 16 consecutive n at `ptr` with element stride `sn` (vector loads when the caller knows sn == 1 and the
 // address is 16-byte aligned; 256-bit when it is 32-byte aligned).
-__device__ __forceinline__ void tg_load16(float (&d)[16], const float* ptr, long long sn, bool vec) {
+__device__ __forceinline__ void tg_load16(float (&d)[16], const float* ptr, long long sn, bool vec, bool wide) {
   if (vec) {
-    if ((reinterpret_cast<uintptr_t>(ptr) & 31) == 0) {
+    if (wide && (reinterpret_cast<uintptr_t>(ptr) & 31) == 0) {
       tg_ldg256(d, ptr);
       tg_ldg256(d + 8, ptr + 8);
     } else {
@@ -195,12 +195,12 @@ __device__ __forceinline__ void tg_load16(float (&d)[16], const float* ptr, long
     for (int j = 0; j < 16; ++j) d[j] = ptr[j * sn];
   }
 }
-__device__ __forceinline__ void tg_put16(float* ptr, long long sn, bool vec, bool rnd, const float (&v)[16]) {
+__device__ __forceinline__ void tg_put16(float* ptr, long long sn, bool vec, bool rnd, bool wide, const float (&v)[16]) {
   if (vec) {
     float w[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) w[j] = rnd ? round_tf32(v[j]) : v[j];
-    if ((reinterpret_cast<uintptr_t>(ptr) & 31) == 0) {
+    if (wide && (reinterpret_cast<uintptr_t>(ptr) & 31) == 0) {
       tg_stg256(ptr, w);
       tg_stg256(ptr + 8, w + 8);
     } else {
@@ -225,8 +225,10 @@ __device__ __forceinline__ void tg_put16(float* ptr, long long sn, bool vec, boo
 // warp-uniform test, so a plain bias+activation epilogue is ~5 instructions per element.  Same arithmetic, in the same
 // order, as tg_epi1.
 // `pre_bias`: the 16 per-column biases already in registers (persistent kernels whose warps keep the same columns).
+// `wide`: 256-bit accesses where the row pointer is 32-byte aligned.  Measured (r01, bench_tapgemm): +4..18 % on the
+// persistent kernel, -18 % on the weight-stationary kernel with 128-byte rows (N = 32), neutral for N = 64.
 __device__ __forceinline__ void tg_store16(const TgParams& p, const TgRow& r, int n, const uint32_t* acc,
-                                           const float* pre_bias = nullptr) {
+                                           const float* pre_bias = nullptr, bool wide = false) {
   if (!r.valid || n >= p.N) return;
   if (n + 15 >= p.N) {      // ragged tail of N: element-wise path with bounds checks
 #pragma unroll
@@ -271,7 +273,7 @@ __device__ __forceinline__ void tg_store16(const TgParams& p, const TgRow& r, in
   }
   if (p.res) {
     float rr[16];
-    tg_load16(rr, p.res + r.r_off + n * p.r_sn, p.r_sn, (p.vec4 & TG_VEC_RES) != 0);
+    tg_load16(rr, p.res + r.r_off + n * p.r_sn, p.r_sn, (p.vec4 & TG_VEC_RES) != 0, wide);
     if (p.res_op & 1) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] *= rr[j];
@@ -287,16 +289,16 @@ __device__ __forceinline__ void tg_store16(const TgParams& p, const TgRow& r, in
   }
   if (p.res2) {
     float rr[16];
-    tg_load16(rr, p.res2 + r.o_off + n * p.o_sn, p.o_sn, vec);
+    tg_load16(rr, p.res2 + r.o_off + n * p.o_sn, p.o_sn, vec, wide);
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] += rr[j];
   }
   tg_act_vec(v, p.act_post, p.act_post_p);
-  tg_put16(p.out + r.o_off + n * p.o_sn, p.o_sn, vec, (p.round_tf32 & 1) != 0, v);
+  tg_put16(p.out + r.o_off + n * p.o_sn, p.o_sn, vec, (p.round_tf32 & 1) != 0, wide, v);
   if (p.out2) {
     tg_act_vec(v, p.act2, p.act2_p);
     const long long sn2 = p.out2_own ? p.o2_sn : p.o_sn;
-    tg_put16(p.out2 + r.o2_off + n * sn2, sn2, p.out2_own ? (p.vec4 & TG_VEC_OUT2) != 0 : vec, (p.round_tf32 & 2) != 0, v);
+    tg_put16(p.out2 + r.o2_off + n * sn2, sn2, p.out2_own ? (p.vec4 & TG_VEC_OUT2) != 0 : vec, (p.round_tf32 & 2) != 0, wide, v);
   }
 }
 

@@ -262,8 +262,8 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           if (n0 + c0 >= p.N) break;                 // warp-uniform
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS + mh * BN + c0), v);
-          tg_store16(p, r, n0 + c0, v);
-          tg_store16(p, r, n0 + c0 + 16, v + 16);
+          tg_store16(p, r, n0 + c0, v, nullptr, true);
+          tg_store16(p, r, n0 + c0 + 16, v + 16, nullptr, true);
         }
       }
       // all TMEM reads of this accumulator stage are complete (tcgen05.wait::ld inside tmem_ld32)

@@ -305,7 +305,7 @@ tapgemm_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // registers hold the data: hand the accumulator back to the MMA warp before touching global memory
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         if (lane == 0) mbar_arrive(tempty_bar(acc));
-        tg_store16(p, r, n, v, pre_bias ? bias16 : nullptr);
+        tg_store16(p, r, n, v, pre_bias ? bias16 : nullptr, p.N > 32);
       }
     }
   }
