@@ -225,21 +225,10 @@ __device__ __forceinline__ void tg_put16(float* ptr, long long sn, bool vec, boo
 // warp-uniform test, so a plain bias+activation epilogue is ~5 instructions per element.  Same arithmetic, in the same
 // order, as tg_epi1.
 // `pre_bias`: the 16 per-column biases already in registers (persistent kernels whose warps keep the same columns).
-// Residual prefetch: the 16 residual values tg_store16 would read for (row r, columns n .. n+15), issued early — the
-// epilogue warps otherwise serialise "load residual (one DRAM latency) -> compute -> store" once per 16-column group,
-// which capped the residual-carrying layers (k2s2 conv-transposes, TDF output GEMMs, ResBlock second convs) at ~2.8 TB/s.
-// Returns false (nothing loaded) when there is no residual or tg_store16 will take its element-wise path.
-__device__ __forceinline__ bool tg_prefetch_res16(const TgParams& p, const TgRow& r, int n, float (&rr)[16], bool wide) {
-  if (!p.res || !r.valid || n + 15 >= p.N) return false;
-  tg_load16(rr, p.res + r.r_off + n * p.r_sn, p.r_sn, (p.vec4 & TG_VEC_RES) != 0, wide);
-  return true;
-}
-
 // `wide`: 256-bit accesses where the row pointer is 32-byte aligned.  Measured (r01, bench_tapgemm): +4..18 % on the
 // persistent kernel, -18 % on the weight-stationary kernel with 128-byte rows (N = 32), neutral for N = 64.
 __device__ __forceinline__ void tg_store16(const TgParams& p, const TgRow& r, int n, const uint32_t* acc,
-                                           const float* pre_bias = nullptr, bool wide = false,
-                                           const float* pre_res = nullptr) {
+                                           const float* pre_bias = nullptr, bool wide = false) {
   if (!r.valid || n >= p.N) return;
   if (n + 15 >= p.N) {      // ragged tail of N: element-wise path with bounds checks
 #pragma unroll
@@ -284,12 +273,7 @@ __device__ __forceinline__ void tg_store16(const TgParams& p, const TgRow& r, in
   }
   if (p.res) {
     float rr[16];
-    if (pre_res) {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) rr[j] = pre_res[j];
-    } else {
-      tg_load16(rr, p.res + r.r_off + n * p.r_sn, p.r_sn, (p.vec4 & TG_VEC_RES) != 0, wide);
-    }
+    tg_load16(rr, p.res + r.r_off + n * p.r_sn, p.r_sn, (p.vec4 & TG_VEC_RES) != 0, wide);
     if (p.res_op & 1) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] *= rr[j];

@@ -251,44 +251,20 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       tile_coords(tile, w0, h0, tb, n0);
       const int acc = it % NACC;
       const uint32_t use = (uint32_t)(it / NACC);
-      // residual of the first column group: requested before waiting for the accumulator, then one group ahead
-      float ra[16], rb[16];
-      bool pa = false, pb = false;
-      TgRow r0;
-      {
-        const int m = q * 32 + lane;
-        r0 = tg_row(p, tb, h0 + m / tbw, w0 + m % tbw);
-        const int c0 = cpar * 32;
-        if (p.res && c0 < BN && n0 + c0 < p.N) {
-          pa = tg_prefetch_res16(p, r0, n0 + c0, ra, true);
-          pb = tg_prefetch_res16(p, r0, n0 + c0 + 16, rb, true);
-        }
-      }
       mbar_wait(tfull_bar(acc), use & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
       for (int mh = 0; mh < MH; ++mh) {
         const int m = mh * 128 + q * 32 + lane;      // row inside the (tbw x tbh) box, w fastest
-        const TgRow r = mh == 0 ? r0 : tg_row(p, tb, h0 + m / tbw, w0 + m % tbw);
+        const TgRow r = tg_row(p, tb, h0 + m / tbw, w0 + m % tbw);
 #pragma unroll 1
         for (int c0 = cpar * 32; c0 < BN; c0 += 64) {
           if (n0 + c0 >= p.N) break;                 // warp-uniform
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS + mh * BN + c0), v);
-          float na[16], nb[16];
-          bool qa = false, qb = false;
-          const int c1 = c0 + 64;
-          if (mh == 0 && p.res && c1 < BN && n0 + c1 < p.N) {
-            qa = tg_prefetch_res16(p, r, n0 + c1, na, true);
-            qb = tg_prefetch_res16(p, r, n0 + c1 + 16, nb, true);
-          }
-          tg_store16(p, r, n0 + c0, v, nullptr, true, pa ? ra : nullptr);
-          tg_store16(p, r, n0 + c0 + 16, v + 16, nullptr, true, pb ? rb : nullptr);
-          pa = qa; pb = qb;
-#pragma unroll
-          for (int j = 0; j < 16; ++j) { ra[j] = na[j]; rb[j] = nb[j]; }
+          tg_store16(p, r, n0 + c0, v, nullptr, true);
+          tg_store16(p, r, n0 + c0 + 16, v + 16, nullptr, true);
         }
-        pa = pb = false;                               // second row half (256-row tiles): loads its residual in place
       }
       // all TMEM reads of this accumulator stage are complete (tcgen05.wait::ld inside tmem_ld32)
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

@@ -298,8 +298,6 @@ tapgemm_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const TgRow r = tg_row(p, tk.b, tk.h, tk.tw * 128 + q * 32 + lane);
         const int acc = ti & 1;
         const uint32_t use = (uint32_t)(ti >> 1);
-        float rres[16];
-        const bool have_res = tg_prefetch_res16(p, r, n, rres, p.N > 32);   // in flight while the MMAs of this tile finish
         mbar_wait(tfull_bar(acc), use & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         uint32_t v[16];
@@ -307,7 +305,7 @@ tapgemm_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // registers hold the data: hand the accumulator back to the MMA warp before touching global memory
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         if (lane == 0) mbar_arrive(tempty_bar(acc));
-        tg_store16(p, r, n, v, pre_bias ? bias16 : nullptr, p.N > 32, have_res ? rres : nullptr);
+        tg_store16(p, r, n, v, pre_bias ? bias16 : nullptr, p.N > 32);
       }
     }
   }
