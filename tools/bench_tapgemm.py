@@ -73,6 +73,7 @@ def main():
                 print(json.dumps(rec), flush=True)
                 f.write(json.dumps(rec) + "\n")
         main2d(f, args.only)
+        main_membound(f, args.only)
 
 
 def main2d(f, only=""):
@@ -92,6 +93,39 @@ def main2d(f, only=""):
             rec = dict(shape=name, backend=bname, ms=ms, tflops=fl / ms / 1e9, gbs=by / ms / 1e6, ws=op.ws_applicable())
             print(json.dumps(rec), flush=True)
             f.write(json.dumps(rec) + "\n")
+
+
+def main_membound(f, only=""):
+    """The residual-carrying, small-K layers of the MDX net (HBM-bound): k2s2 conv-transpose with the multiplicative skip,
+    and the TDF output GEMM with the transposed store + residual."""
+    if "us4" in only or not only:
+        B, H, W, Ci, Co = 2, 128, 1536, 96, 48
+        x = torch.randn(B, H, W, Ci, device="cuda")
+        w = torch.randn(4, Co, Ci, device="cuda") / Ci ** 0.5
+        b = torch.randn(Co, device="cuda")
+        sk = torch.randn(B, 2 * H, 2 * W, Co, device="cuda")
+        out = torch.empty(B, 2 * H, 2 * W, Co, device="cuda")
+        ops_ = tg.conv_transpose2d_k2s2(x, w, out, tg.Epi(bias=b, act_pre=tg.ACT_RELU, res=sk, res_mul=True, res_mapped=True))
+        ms = timeit(lambda: [o() for o in ops_])
+        by = 4.0 * (x.numel() * 2 + 2 * out.numel())
+        rec = dict(shape="mdx.us4 k2s2 c96->48", backend="auto", ms=ms, tflops=2.0 * B * H * W * Ci * Co * 4 / ms / 1e9, gbs=by / ms / 1e6)
+        print(json.dumps(rec), flush=True)
+        f.write(json.dumps(rec) + "\n")
+    if "tdf2" in only or not only:
+        BH, c, F_, Kb = 2 * 256, 48, 3072, 384
+        h = torch.randn(BH * c, Kb, device="cuda")
+        w2 = torch.randn(F_, Kb, device="cuda") / Kb ** 0.5
+        b2 = torch.randn(BH * c, device="cuda")
+        t = torch.randn(BH, F_, c, device="cuda")
+        out = torch.empty(BH, F_, c, device="cuda")
+        a2 = tg.View(h, (Kb, c, BH, 1, 1), (1, Kb, c * Kb, 0, 0))
+        op = tg.TapGemm(a2, tg.weights(w2), [(0, 0, 0, 0, 0)], (c, BH, 1), tg.Out(out, 0, F_ * c, 1, BH, c, sn=c),
+                        tg.Epi(bias=b2, bias_per_row=True, act_pre=tg.ACT_RELU, res=t, res_strides=(0, F_ * c, 1, c)), box=(16, 8))
+        ms = timeit(op)
+        by = 4.0 * (h.numel() + 2 * out.numel())
+        rec = dict(shape="mdx.tdf2 L0 (transposed store + residual)", backend="auto", ms=ms, tflops=2.0 * BH * c * Kb * F_ / ms / 1e9, gbs=by / ms / 1e6)
+        print(json.dumps(rec), flush=True)
+        f.write(json.dumps(rec) + "\n")
 
 
 if __name__ == "__main__":
