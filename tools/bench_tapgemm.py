@@ -105,12 +105,14 @@ def main_membound(f, only=""):
         b = torch.randn(Co, device="cuda")
         sk = torch.randn(B, 2 * H, 2 * W, Co, device="cuda")
         out = torch.empty(B, 2 * H, 2 * W, Co, device="cuda")
-        ops_ = tg.conv_transpose2d_k2s2(x, w, out, tg.Epi(bias=b, act_pre=tg.ACT_RELU, res=sk, res_mul=True, res_mapped=True))
-        ms = timeit(lambda: [o() for o in ops_])
-        by = 4.0 * (x.numel() * 2 + 2 * out.numel())
-        rec = dict(shape="mdx.us4 k2s2 c96->48", backend="auto", ms=ms, tflops=2.0 * B * H * W * Ci * Co * 4 / ms / 1e9, gbs=by / ms / 1e6)
-        print(json.dumps(rec), flush=True)
-        f.write(json.dumps(rec) + "\n")
+        for tag, epi in [("bias+relu+skip", tg.Epi(bias=b, act_pre=tg.ACT_RELU, res=sk, res_mul=True, res_mapped=True)),
+                         ("bias+relu", tg.Epi(bias=b, act_pre=tg.ACT_RELU)), ("plain", tg.Epi())]:
+            ops_ = tg.conv_transpose2d_k2s2(x, w, out, epi)
+            ms = timeit(lambda: [o() for o in ops_])
+            by = 4.0 * (x.numel() * 2 + out.numel() * (2 if epi.res is not None else 1))
+            rec = dict(shape=f"mdx.us4 k2s2 c96->48 [{tag}]", backend="auto", ms=ms, tflops=2.0 * B * H * W * Ci * Co * 4 / ms / 1e9, gbs=by / ms / 1e6)
+            print(json.dumps(rec), flush=True)
+            f.write(json.dumps(rec) + "\n")
     if "tdf2" in only or not only:
         BH, c, F_, Kb = 2 * 256, 48, 3072, 384
         h = torch.randn(BH * c, Kb, device="cuda")
