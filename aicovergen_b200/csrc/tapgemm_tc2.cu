@@ -111,7 +111,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 template <int BN, int STAGES, int MH>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-                   const __grid_constant__ TgParams p, int ntiles_n, int total_tiles, int tbw, int tbh) {
+                   const __grid_constant__ TgParams p, int ntiles_n, int total_tiles, int tbw, int tbh, int bias_floats) {
   constexpr int A_STAGE_BYTES = MH * TG_TILE_M * 128;
   constexpr int B_STAGE_BYTES = BN * 128;
   constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
@@ -128,6 +128,10 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  // per-column bias staged once per CTA (ncu r01e: the broadcast global bias loads in the epilogue cost 33 % of an
+  // HBM-bound layer: four dependent L1 round trips per 16 columns on warps that have nothing else to overlap them with)
+  float* bias_s = reinterpret_cast<float*>(smem_raw + (bar_base - smem_u32(smem_raw)) + 8 * (2 * STAGES + 6));
+  for (int i = threadIdx.x; i < bias_floats; i += NUM_THREADS) bias_s[i] = i < p.N ? __ldg(p.bias + i) : 0.f;
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform role index
   const int ntw = (p.OW + tbw - 1) / tbw;
@@ -262,8 +266,8 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           if (n0 + c0 >= p.N) break;                 // warp-uniform
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS + mh * BN + c0), v);
-          tg_store16(p, r, n0 + c0, v, nullptr, true);
-          tg_store16(p, r, n0 + c0 + 16, v + 16, nullptr, true);
+          tg_store16(p, r, n0 + c0, v, bias_floats ? bias_s + n0 + c0 : nullptr, true);
+          tg_store16(p, r, n0 + c0 + 16, v + 16, bias_floats ? bias_s + n0 + c0 + 16 : nullptr, true);
         }
       }
       // all TMEM reads of this accumulator stage are complete (tcgen05.wait::ld inside tmem_ld32)
@@ -283,14 +287,19 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 template <int BN, int STAGES, int MH>
 int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmW, const TgParams& p, int ntiles_n, int total_tiles,
                int grid, int tbw, int tbh, cudaStream_t stream) {
-  constexpr int smem = STAGES * (MH * TG_TILE_M * 128 + BN * 128) + 8 * (2 * STAGES + 6) + 1024;
-  static_assert(smem <= 227 * 1024, "shared memory budget");
-  static bool configured = false;
-  if (!configured) {
-    B200VC_CHECK_CUDA(cudaFuncSetAttribute(tapgemm_tc2_kernel<BN, STAGES, MH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
+  constexpr int smem_fixed = STAGES * (MH * TG_TILE_M * 128 + BN * 128) + 8 * (2 * STAGES + 6) + 1024;
+  static_assert(smem_fixed <= 227 * 1024, "shared memory budget");
+  // per-column bias in shared memory when it fits beside the operand ring (padded to whole n-tiles so every 16-column
+  // group the epilogue touches is readable)
+  const int want = (p.bias && !p.bias_per_row) ? ntiles_n * BN : 0;
+  const int bias_floats = (want > 0 && smem_fixed + want * 4 + 16 <= 227 * 1024) ? want : 0;
+  const int smem = smem_fixed + (bias_floats ? bias_floats * 4 + 16 : 0);
+  static int configured = 0;
+  if (configured < smem) {
+    B200VC_CHECK_CUDA(cudaFuncSetAttribute(tapgemm_tc2_kernel<BN, STAGES, MH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = 227 * 1024;
   }
-  tapgemm_tc2_kernel<BN, STAGES, MH><<<grid, NUM_THREADS, smem, stream>>>(tmA, tmW, p, ntiles_n, total_tiles, tbw, tbh);
+  tapgemm_tc2_kernel<BN, STAGES, MH><<<grid, NUM_THREADS, smem, stream>>>(tmA, tmW, p, ntiles_n, total_tiles, tbw, tbh, bias_floats);
   return kOk;
 }
 
