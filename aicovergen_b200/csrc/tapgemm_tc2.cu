@@ -3,8 +3,8 @@
 //   grid  = min(#tiles, #SMs) CTAs, each loops over output tiles (n-tile fastest so neighbouring CTAs share the A box in L2)
 //   warp 0 : TMA producer — the shared-memory ring keeps filling across tile boundaries
 //   warp 1 : TMEM allocator (2 x BN columns) + single-thread tcgen05.mma issuer; tcgen05.commit -> smem-empty / tmem-full
-//   warps 2-9 : epilogue — tcgen05.ld of accumulator stage `it & 1` while the MMA warp already fills the other stage;
-//               warp = (TMEM lane quarter, even/odd 32-column group), two warps per SM sub-partition, each thread
+//   warps 2-17 : epilogue — tcgen05.ld of accumulator stage `it & 1` while the MMA warp already fills the other stage;
+//               warp = (TMEM lane quarter, 32-column group mod 4), four warps per SM sub-partition, each thread
 //               finishing its row's columns in registers (tg_store16)
 //
 // Same descriptor, same epilogue semantics as tapgemm.cuh (scalar form tg_epi1).
@@ -20,7 +20,7 @@ int encode_map_f32(CUtensorMap* tm, const void* base, int rank, const cuuint64_t
 namespace {
 
 constexpr int KCHUNK = 32;
-constexpr int EPI_WARPS = 8;
+constexpr int EPI_WARPS = 16;                     // (TMEM lane quarter) x (32-column group mod 4): 4 warps per SM sub-partition
 constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -148,7 +148,7 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
     for (int a = 0; a < NACC; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), BN >= 64 ? EPI_WARPS : 4);   // BN == 32: only the first column group has work
+      mbar_init(tempty_bar(a), BN >= 128 ? EPI_WARPS : BN / 8);   // 4 warps per live 32-column group
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -247,7 +247,7 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int q = warp & 3;
-    const int cpar = (warp - 2) >> 2;              // this warp takes the 32-column groups with index % 2 == cpar
+    const int cpar = (warp - 2) >> 2;              // this warp takes the 32-column groups with index % 4 == cpar
     int it = 0;
     if (cpar * 32 < BN)
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -262,7 +262,7 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const int m = mh * 128 + q * 32 + lane;      // row inside the (tbw x tbh) box, w fastest
         const TgRow r = tg_row(p, tb, h0 + m / tbw, w0 + m % tbw);
 #pragma unroll 1
-        for (int c0 = cpar * 32; c0 < BN; c0 += 64) {
+        for (int c0 = cpar * 32; c0 < BN; c0 += 128) {
           if (n0 + c0 >= p.N) break;                 // warp-uniform
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS + mh * BN + c0), v);
