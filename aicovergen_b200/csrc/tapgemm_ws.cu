@@ -5,9 +5,9 @@
 // c=48 3x3 layers).  Here:
 //   * every CTA is persistent and first parks ALL weights of the layer in shared memory (ntaps x kchunks tiles of
 //     [Nr x 32] fp32, <= ~112 KB) — they are never fetched again;
-//   * per output tile (1 x 128 pixel strip) and 32-channel chunk, KH TMA boxes (one ring stage per input row) bring
-//     the strip WITH ITS HALO ([128 + (KW-1)*dil] pixels x 32 ch each); the kw taps are just row offsets of the UMMA
-//     A descriptor inside a row box (the 128-byte swizzle is a function of absolute shared-memory address bits, so shifting the start
+//   * per output tile (1 x 128 pixel strip) and 32-channel chunk ONE TMA box brings the strip WITH ITS HALO
+//     ([KH rows] x [128 + (KW-1)*dil] pixels x 32 ch); the taps are just row offsets of the UMMA A descriptor inside
+//     that box (the 128-byte swizzle is a function of absolute shared-memory address bits, so shifting the start
 //     address by whole 128-byte rows keeps TMA's layout and the descriptor's view consistent);
 //   * TMEM accumulators are double buffered so the epilogue of tile i overlaps the MMAs of tile i+1; SIXTEEN epilogue
 //     warps (4 per SM sub-partition: lane quarter x 16-column group) keep the register-resident epilogue off the
@@ -26,15 +26,13 @@ int encode_map_f32(CUtensorMap* tm, const void* base, int rank, const cuuint64_t
 namespace {
 
 constexpr int KCHUNK = 32;
-constexpr int MAX_STAGES = 8;
-constexpr int BAR_BYTES = 8 * (2 * MAX_STAGES + 6);
 constexpr int EPI_WARPS = 16;                      // (TMEM lane quarter) x (16-column group)
 constexpr int NUM_THREADS = 64 + EPI_WARPS * 32;   // warp0 TMA, warp1 MMA, warps 2..17 epilogue
 
 struct WsGeom {
   int KH, KW, dil_w, dil_h, pad_w, pad_h;
   int BWh;            // halo box width in pixels = 128 + (KW-1)*dil_w
-  int a_stage_bytes;  // one halo ROW (BWh pixels x 32 channels) = BWh * 128 rounded up to 1024
+  int a_stage_bytes;  // KH * BWh * 128 rounded up to 1024
   int b_tile_bytes;   // Nr * 128
   int Nr;             // MMA N (N rounded up to 16)
   int stages;
@@ -179,11 +177,11 @@ tapgemm_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t bar_base = a_base + g.stages * g.a_stage_bytes;
   auto a_stage = [&](int s) { return a_base + s * g.a_stage_bytes; };
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
-  const uint32_t w_bar = bar_base + 8u * (2 * MAX_STAGES);
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + 1 + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + 3 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_STAGES + 5);
+  auto empty_bar = [&](int s) { return bar_base + 8u * (4 + s); };
+  const uint32_t w_bar = bar_base + 8u * 8;
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (9 + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (11 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * 13;
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform role index
   const int ntw = (p.OW + 127) / 128;
@@ -223,24 +221,19 @@ tapgemm_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tma_load_3d(w_base + (uint32_t)((j * kchunks + kc) * g.b_tile_bytes), &tmW, w_bar, kc * KCHUNK, 0, j);
       }
       __syncwarp();
-      // One stage = one input row of the halo (BWh pixels x 32 channels).  Row granularity lets the ring refill while
-      // the taps of the later rows are still being multiplied: with whole (KH x BWh) boxes the MDX c=48 layers had only two
-      // 50 KB stages = one tile, and every tile exposed a full TMA round trip.
-      int s = 0;
-      uint32_t ph = 0;
-      const uint32_t a_tx = (uint32_t)(g.BWh * 128);
+      int it = 0;
+      const uint32_t a_tx = (uint32_t)(g.KH * g.BWh * 128);
       TileWalk tk;
       for (tk.init(blockIdx.x, gridDim.x, g.total_tiles, ntw, p.OH); tk.left > 0; tk.next(ntw, p.OH)) {
-        for (int kc = 0; kc < kchunks; ++kc) {
-          for (int kh = 0; kh < g.KH; ++kh) {
-            mbar_wait(empty_bar(s), ph ^ 1u);
-            if (elect_one()) {
-              mbar_expect_tx(full_bar(s), a_tx);
-              tma_load_5d(a_stage(s), &tmA, full_bar(s), kc * KCHUNK, tk.tw * 128 - g.pad_w, tk.h - g.pad_h + kh, tk.b, 0);
-            }
-            __syncwarp();
-            if (++s == g.stages) { s = 0; ph ^= 1u; }
+        for (int kc = 0; kc < kchunks; ++kc, ++it) {
+          const int s = it % g.stages;
+          const uint32_t ph = (it / g.stages) & 1;
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          if (elect_one()) {
+            mbar_expect_tx(full_bar(s), a_tx);
+            tma_load_5d(a_stage(s), &tmA, full_bar(s), kc * KCHUNK, tk.tw * 128 - g.pad_w, tk.h - g.pad_h, tk.b, 0);
           }
+          __syncwarp();
         }
       }
     }
@@ -252,43 +245,41 @@ tapgemm_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint32_t IDESC = make_idesc_tf32(128, g.Nr);
       mbar_wait(w_bar, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      int ti = 0, s = 0;
-      uint32_t ph = 0;
+      int it = 0, ti = 0;
       const int my_tiles = (int)blockIdx.x < g.total_tiles ? (g.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-      const uint64_t b_step = (uint64_t)((kchunks * g.b_tile_bytes) >> 4);
-      const uint64_t a_kw_step = (uint64_t)(g.dil_w * 8);                       // rows x 128 B >> 4
       for (; ti < my_tiles; ++ti) {
         const int acc = ti & 1;
         const uint32_t use = (uint32_t)(ti >> 1);
         mbar_wait(tempty_bar(acc), (use & 1u) ^ 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TM_COLS_PER_ACC);
-        uint32_t accum = 0u;
-        for (int kc = 0; kc < kchunks; ++kc) {
-          // descriptors differ only in their 14-bit start-address field: walk it with adds
+        for (int kc = 0; kc < kchunks; ++kc, ++it) {
+          const int s = it % g.stages;
+          const uint32_t ph = (it / g.stages) & 1;
+          mbar_wait(full_bar(s), ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          // descriptors differ only in their 14-bit start-address field: walk it with adds (this loop runs on one thread)
+          uint64_t adesc_row = make_smem_desc(a_stage(s));
           uint64_t bdesc = make_smem_desc(w_base + (uint32_t)(kc * g.b_tile_bytes));
+          const uint64_t b_step = (uint64_t)((kchunks * g.b_tile_bytes) >> 4);
+          const uint64_t a_kw_step = (uint64_t)(g.dil_w * 8), a_kh_step = (uint64_t)(g.BWh * 8);   // rows x 128 B >> 4
+          uint32_t accum = kc > 0 ? 1u : 0u;
           // short last k-chunk (Kc = 48 -> 32 + 16): only the K=8 steps that hold data (25 % fewer MMAs and operand reads)
           const int nk = (kc == kchunks - 1) ? (((p.Kc - kc * KCHUNK) + 7) >> 3) : KCHUNK / 8;
-          for (int kh = 0; kh < g.KH; ++kh) {
-            mbar_wait(full_bar(s), ph);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (elect_one()) {
-              uint64_t adesc = make_smem_desc(a_stage(s));
-              uint64_t bd = bdesc;
-              for (int kw = 0; kw < g.KW; ++kw, adesc += a_kw_step, bd += b_step) {
+          if (elect_one()) {
+            for (int kh = 0; kh < g.KH; ++kh, adesc_row += a_kh_step) {
+              uint64_t adesc = adesc_row;
+              for (int kw = 0; kw < g.KW; ++kw, adesc += a_kw_step, bdesc += b_step) {
                 for (int k = 0; k < nk; ++k) {
-                  umma_tf32(d_tmem, adesc + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), IDESC, accum);
+                  umma_tf32(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, accum);
                   accum = 1u;
                 }
               }
-              umma_commit(empty_bar(s));
-              if (kc == kchunks - 1 && kh == g.KH - 1) umma_commit(tfull_bar(acc));
             }
-            accum = 1u;
-            bdesc += b_step * (uint64_t)g.KW;
-            __syncwarp();
-            if (++s == g.stages) { s = 0; ph ^= 1u; }
+            umma_commit(empty_bar(s));
+            if (kc == kchunks - 1) umma_commit(tfull_bar(acc));
           }
+          __syncwarp();
         }
       }
     }
@@ -365,12 +356,12 @@ bool ws_geometry(const TgParams& p, WsGeom& g) {
   if (g.BWh > 256 || KH > 256) return false;
   g.Nr = (p.N + 15) & ~15;                 // MMA N and weight-tile rows (16 rows x 128 B = 2 KB granules: stays 1024-aligned)
   g.b_tile_bytes = g.Nr * 128;
-  g.a_stage_bytes = ((g.BWh * 128 + 1023) / 1024) * 1024;        // 1024-aligned row stages (swizzle atom = 8 rows x 128 B)
+  g.a_stage_bytes = ((KH * g.BWh * 128 + 1023) / 1024) * 1024;   // 1024-aligned stages (swizzle atom = 8 rows x 128 B)
   const int kchunks = (p.Kc + KCHUNK - 1) / KCHUNK;
   const int w_bytes = p.ntaps * kchunks * g.b_tile_bytes;
-  const int fixed = BAR_BYTES + 16 + 1024;
+  const int fixed = 8 * 14 + 16 + 1024;
   int stages = (SMEM_LIMIT - fixed - w_bytes) / g.a_stage_bytes;
-  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages > 4) stages = 4;
   if (stages < 2) return false;
   g.stages = stages;
   const long long tiles = (long long)((p.OW + 127) / 128) * p.OH * p.OB;
@@ -393,7 +384,7 @@ int tapgemm_ws_launch(const TgParams& p, cudaStream_t stream) {
   CUtensorMap tmA, tmW;
   {
     cuuint64_t dims[5], strides[4];
-    cuuint32_t box[5] = {KCHUNK, (cuuint32_t)g.BWh, 1, 1, 1};
+    cuuint32_t box[5] = {KCHUNK, (cuuint32_t)g.BWh, (cuuint32_t)g.KH, 1, 1};
     long long span = 1;
     for (int i = 0; i < 5; ++i) {
       dims[i] = (cuuint64_t)(p.a_dim[i] > 0 ? p.a_dim[i] : 1);
@@ -417,7 +408,7 @@ int tapgemm_ws_launch(const TgParams& p, cudaStream_t stream) {
     if (rc) return rc;
   }
   const int w_bytes = p.ntaps * kchunks * g.b_tile_bytes;
-  const int smem = w_bytes + g.stages * g.a_stage_bytes + BAR_BYTES + 16 + 1024;
+  const int smem = w_bytes + g.stages * g.a_stage_bytes + 8 * 14 + 16 + 1024;
   static int configured = 0;
   if (configured < smem) {
     B200VC_CHECK_CUDA(cudaFuncSetAttribute(tapgemm_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
