@@ -219,10 +219,18 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (elect_one()) {
           const uint64_t adesc = make_smem_desc(a_stage(s));
           const uint64_t bdesc = make_smem_desc(b_stage(s));
-          for (int k = 0; k < nk; ++k) {
-            // advance 8 tf32 = 32 bytes inside the swizzle atom: +2 in the (addr >> 4) field
-            umma_tf32(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, accum);
-            accum = 1u;
+          // advance 8 tf32 = 32 bytes inside the swizzle atom: +2 in the (addr >> 4) field
+          if (nk == KCHUNK / 8) {
+#pragma unroll
+            for (int k = 0; k < KCHUNK / 8; ++k) {
+              umma_tf32(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, accum);
+              accum = 1u;
+            }
+          } else {
+            for (int k = 0; k < nk; ++k) {
+              umma_tf32(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, accum);
+              accum = 1u;
+            }
           }
           umma_commit(empty_bar(s));   // frees this smem stage once the MMAs have read it
           if (chunk == nchunks - 1) umma_commit(tmem_full_bar);    // accumulator complete

@@ -228,11 +228,21 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           if (elect_one()) {
             const uint64_t adesc = make_smem_desc(a_stage(s));
             const uint64_t bdesc = make_smem_desc(b_stage(s));
-            for (int k = 0; k < nk; ++k) {
+            if (nk == KCHUNK / 8) {               // full chunk: straight-line issue
 #pragma unroll
-              for (int mh = 0; mh < MH; ++mh)       // 128 rows x 128 B = 16 KB further into the A box: +1024 in the (addr >> 4) field
-                umma_tf32(d_tmem + (uint32_t)(mh * BN), adesc + (uint64_t)(mh * 1024 + 2 * k), bdesc + (uint64_t)(2 * k), IDESC, accum);
-              accum = 1u;
+              for (int k = 0; k < KCHUNK / 8; ++k) {
+#pragma unroll
+                for (int mh = 0; mh < MH; ++mh)     // 128 rows x 128 B = 16 KB further into the A box: +1024 in the (addr >> 4) field
+                  umma_tf32(d_tmem + (uint32_t)(mh * BN), adesc + (uint64_t)(mh * 1024 + 2 * k), bdesc + (uint64_t)(2 * k), IDESC, accum);
+                accum = 1u;
+              }
+            } else {
+              for (int k = 0; k < nk; ++k) {
+#pragma unroll
+                for (int mh = 0; mh < MH; ++mh)
+                  umma_tf32(d_tmem + (uint32_t)(mh * BN), adesc + (uint64_t)(mh * 1024 + 2 * k), bdesc + (uint64_t)(2 * k), IDESC, accum);
+                accum = 1u;
+              }
             }
             umma_commit(empty_bar(s));
             if (chunk == nchunks - 1) umma_commit(tfull_bar(acc));
