@@ -162,6 +162,9 @@ struct TileWalk {
   }
 };
 
+// KW_T: the tap-grid width when it is one of the common kernel sizes (3 / 5 / 7 / 11), else 0 = run-time loop.  With
+// Cout <= 64 an MMA lasts 16-32 clk, so the single issuing lane is on the critical path and the tap loop must unroll.
+template <int KW_T>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tapgemm_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                   const __grid_constant__ TgParams p, const WsGeom g) {
@@ -269,7 +272,8 @@ tapgemm_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (elect_one()) {
             for (int kh = 0; kh < g.KH; ++kh, adesc_row += a_kh_step) {
               uint64_t adesc = adesc_row;
-              for (int kw = 0; kw < g.KW; ++kw, adesc += a_kw_step, bdesc += b_step) {
+#pragma unroll
+              for (int kw = 0; kw < (KW_T ? KW_T : g.KW); ++kw, adesc += a_kw_step, bdesc += b_step) {
                 if (nk == KCHUNK / 8) {       // full chunk: straight-line issue (a counted loop here costs the N<=32 layers 20 %)
 #pragma unroll
                   for (int k = 0; k < KCHUNK / 8; ++k) {
@@ -417,13 +421,23 @@ int tapgemm_ws_launch(const TgParams& p, cudaStream_t stream) {
   }
   const int w_bytes = p.ntaps * kchunks * g.b_tile_bytes;
   const int smem = w_bytes + g.stages * g.a_stage_bytes + 8 * 14 + 16 + 1024;
-  static int configured = 0;
-  if (configured < smem) {
-    B200VC_CHECK_CUDA(cudaFuncSetAttribute(tapgemm_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    configured = SMEM_LIMIT;
+  static bool configured = false;
+  if (!configured) {
+    B200VC_CHECK_CUDA(cudaFuncSetAttribute(tapgemm_ws_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    B200VC_CHECK_CUDA(cudaFuncSetAttribute(tapgemm_ws_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    B200VC_CHECK_CUDA(cudaFuncSetAttribute(tapgemm_ws_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    B200VC_CHECK_CUDA(cudaFuncSetAttribute(tapgemm_ws_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    B200VC_CHECK_CUDA(cudaFuncSetAttribute(tapgemm_ws_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    configured = true;
   }
   const int grid = g.total_tiles < num_sms_ws() ? g.total_tiles : num_sms_ws();
-  tapgemm_ws_kernel<<<grid, NUM_THREADS, smem, stream>>>(tmA, tmW, p, g);
+  switch (g.KW) {
+    case 3:  tapgemm_ws_kernel<3><<<grid, NUM_THREADS, smem, stream>>>(tmA, tmW, p, g); break;
+    case 5:  tapgemm_ws_kernel<5><<<grid, NUM_THREADS, smem, stream>>>(tmA, tmW, p, g); break;
+    case 7:  tapgemm_ws_kernel<7><<<grid, NUM_THREADS, smem, stream>>>(tmA, tmW, p, g); break;
+    case 11: tapgemm_ws_kernel<11><<<grid, NUM_THREADS, smem, stream>>>(tmA, tmW, p, g); break;
+    default: tapgemm_ws_kernel<0><<<grid, NUM_THREADS, smem, stream>>>(tmA, tmW, p, g); break;
+  }
   count_launch();
   B200VC_LAUNCH_CHECK();
   return kOk;
