@@ -74,3 +74,24 @@ def test_sharded_sum_equals_single_rank(world):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert np.array_equal(got, ref)
+
+
+def test_plan_cache_is_lru_and_holds_more_than_a_songs_segments():
+    """A 4-minute song cuts into 4 segments of different lengths (vc_infer_pipeline.py:516-545): the per-shape plan
+    cache must keep all of them across songs, and evict least-recently-used beyond its capacity."""
+    from aicovergen_b200.plans import PLAN_CACHE, PlanCache
+
+    assert PLAN_CACHE >= 5
+    built = []
+    cache = PlanCache()
+
+    def get(k):
+        return cache.get_or_build(k, lambda: built.append(k) or object())
+
+    for _ in range(3):                       # three "songs" with the same four segment lengths
+        for k in (6600, 6412, 7031, 5590):
+            get(k)
+    assert built == [6600, 6412, 7031, 5590]
+    for k in range(PLAN_CACHE):              # fill past capacity: the oldest entries go first
+        get(100 + k)
+    assert 6600 not in cache and len(cache) == PLAN_CACHE
