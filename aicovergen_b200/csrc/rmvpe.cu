@@ -116,6 +116,9 @@ bigru_kernel(const float* __restrict__ xp, const float* __restrict__ whh /*[2][3
   // prefetch x-projection for the first step
   int t = dir == 0 ? 0 : T - 1;
   float xv = (half == 0) ? __ldg(xp_d + (long long)t * xp_ld + wrow) : 0.f;
+  // x-projection of the n gate for the unit this thread finalises (threads 0..UPC-1), also fetched one step ahead:
+  // loaded inside the step it sat on the critical path of every one of the T sequential steps
+  float xn = (tid < GRU_UPC) ? __ldg(xp_d + (long long)t * xp_ld + 2 * GRU_H + rank * GRU_UPC + tid) : 0.f;
 
   for (int s = 0; s < T; ++s) {
     const int cur = s & 1, nxt = cur ^ 1;
@@ -123,6 +126,8 @@ bigru_kernel(const float* __restrict__ xp, const float* __restrict__ whh /*[2][3
     const int tn = dir == 0 ? s + 1 : T - 2 - s;
     float xv_next = 0.f;
     if (half == 0 && s + 1 < T) xv_next = __ldg(xp_d + (long long)tn * xp_ld + wrow);
+    float xn_next = 0.f;
+    if (tid < GRU_UPC && s + 1 < T) xn_next = __ldg(xp_d + (long long)tn * xp_ld + 2 * GRU_H + rank * GRU_UPC + tid);
 
     // partial dot product W_hh[row, half*128 : +128] . h[half*128 : +128]
     const float* h = &hbuf[cur][half * (GRU_H / 2)];
@@ -148,8 +153,6 @@ bigru_kernel(const float* __restrict__ xp, const float* __restrict__ whh /*[2][3
       // thread tid finalises unit rank*UPC + tid
       const int u = rank * GRU_UPC + tid;
       const float r = gate[tid], z = gate[GRU_UPC + tid], hpn = gate[2 * GRU_UPC + tid];
-      // x-projection of the n gate for this unit (row 2*UPC + tid belongs to thread 2*(2*UPC+tid))
-      const float xn = __ldg(xp_d + (long long)t * xp_ld + 2 * GRU_H + u);
       const float n = tanhf(xn + r * hpn);
       const float hprev = hbuf[cur][u];
       const float hnew = (1.f - z) * n + z * hprev;
@@ -161,6 +164,7 @@ bigru_kernel(const float* __restrict__ xp, const float* __restrict__ whh /*[2][3
       }
     }
     xv = xv_next;
+    xn = xn_next;
     cluster.sync();   // publishes hbuf[nxt] cluster-wide; also orders gate[] reuse
   }
 }
