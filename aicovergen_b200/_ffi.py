@@ -78,6 +78,7 @@ class TapGemmParams(C.Structure):
         ("act2_p", C.c_float),
         ("vec4", C.c_int32),
         ("round_tf32", C.c_int32),
+        ("dtype", C.c_int32),
         ("taps", Tap * MAX_TAPS),
     ]
 

@@ -17,6 +17,7 @@
 //   linears, mdx.py:77 (the ONNX TFC-TDF net).
 #pragma once
 #include "common.cuh"
+#include <cuda_fp16.h>
 #include "../../include/b200vc.h"
 
 namespace b200vc {
@@ -29,6 +30,18 @@ constexpr int TG_TILE_M = 128;
 //             v = act_post(v); out = v; out2 = act2(v)
 using TgTap = b200vc_tap;
 using TgParams = b200vc_tapgemm_params;
+
+// dtype bits (b200vc.h): which tensors hold IEEE fp16 instead of fp32
+constexpr int TG_DT_AB = 1, TG_DT_OUT = 2, TG_DT_OUT2 = 4, TG_DT_RES = 8, TG_DT_RES2 = 16;
+constexpr int TG_DT_EPI = TG_DT_OUT | TG_DT_OUT2 | TG_DT_RES | TG_DT_RES2;
+
+__device__ __forceinline__ float tg_ld(const float* base, long long idx, bool half) {
+  return half ? __half2float(reinterpret_cast<const __half*>(base)[idx]) : base[idx];
+}
+__device__ __forceinline__ void tg_st(float* base, long long idx, float v, bool half) {
+  if (half) reinterpret_cast<__half*>(base)[idx] = __float2half_rn(v);
+  else base[idx] = v;
+}
 
 // One GEMM row's addressing state.
 struct TgRow {
@@ -59,9 +72,9 @@ __device__ __forceinline__ float tg_epi1(const TgParams& p, const TgRow& r, int 
   if (p.bias) v += p.bias_per_row ? __ldg(p.bias + r.brow) : __ldg(p.bias + n);
   v = apply_act(v, p.act_pre, p.act_pre_p);
   if (p.row_scale) v *= __ldg(p.row_scale + r.brow);
-  if (p.res) { const float rr = p.res[r.r_off + n * p.r_sn]; v = (p.res_op & 1) ? v * rr : v + rr; }
+  if (p.res) { const float rr = tg_ld(p.res, r.r_off + n * p.r_sn, p.dtype & TG_DT_RES); v = (p.res_op & 1) ? v * rr : v + rr; }
   v *= p.scale;
-  if (p.res2) v += p.res2[r.o_off + n * p.o_sn];
+  if (p.res2) v += tg_ld(p.res2, r.o_off + n * p.o_sn, p.dtype & TG_DT_RES2);
   v = apply_act(v, p.act_post, p.act_post_p);
   return v;
 }
@@ -70,10 +83,10 @@ __device__ __forceinline__ float tg_epi1(const TgParams& p, const TgRow& r, int 
 __device__ __forceinline__ void tg_store1(const TgParams& p, const TgRow& r, int n, float acc) {
   if (!r.valid || n >= p.N) return;
   float v = tg_epi1(p, r, n, acc);
-  p.out[r.o_off + n * p.o_sn] = (p.round_tf32 & 1) ? round_tf32(v) : v;
+  tg_st(p.out, r.o_off + n * p.o_sn, (p.round_tf32 & 1) ? round_tf32(v) : v, p.dtype & TG_DT_OUT);
   if (p.out2) {
     float v2 = apply_act(v, p.act2, p.act2_p);
-    p.out2[r.o2_off + n * (p.out2_own ? p.o2_sn : p.o_sn)] = (p.round_tf32 & 2) ? round_tf32(v2) : v2;
+    tg_st(p.out2, r.o2_off + n * (p.out2_own ? p.o2_sn : p.o_sn), (p.round_tf32 & 2) ? round_tf32(v2) : v2, p.dtype & TG_DT_OUT2);
   }
 }
 
@@ -88,7 +101,7 @@ constexpr int TG_VEC_ALL = TG_VEC_OUT | TG_VEC_BIAS | TG_VEC_OUT2 | TG_VEC_RES;
 // Store 4 consecutive n (n % 4 == 0). Uses float4 when every epilogue tensor is channels-last + aligned and in range.
 __device__ __forceinline__ void tg_store4(const TgParams& p, const TgRow& r, int n, float4 acc) {
   if (!r.valid || n >= p.N) return;
-  if ((p.vec4 & TG_VEC_ALL) == TG_VEC_ALL && n + 3 < p.N) {
+  if ((p.vec4 & TG_VEC_ALL) == TG_VEC_ALL && n + 3 < p.N && !(p.dtype & TG_DT_EPI)) {
     float v[4] = {acc.x, acc.y, acc.z, acc.w};
     if (p.row_scale_pre) {
       const float rs = __ldg(p.row_scale_pre + r.brow);
@@ -195,6 +208,25 @@ __device__ __forceinline__ void tg_load16(float (&d)[16], const float* ptr, long
     for (int j = 0; j < 16; ++j) d[j] = ptr[j * sn];
   }
 }
+// fp16 tensors: 16 consecutive halfs are one 32-byte sector (two 16-byte vector accesses)
+__device__ __forceinline__ void tg_load16h(float (&d)[16], const __half* ptr, long long sn, bool vec) {
+  if (vec) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const uint4 t = reinterpret_cast<const uint4*>(ptr)[j];
+      const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+        d[8 * j + 2 * i] = f.x;
+        d[8 * j + 2 * i + 1] = f.y;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) d[j] = __half2float(ptr[j * sn]);
+  }
+}
 __device__ __forceinline__ void tg_put16(float* ptr, long long sn, bool vec, bool rnd, bool wide, const float (&v)[16]) {
   if (vec) {
     float w[16];
@@ -217,6 +249,23 @@ __device__ __forceinline__ void tg_put16(float* ptr, long long sn, bool vec, boo
 #pragma unroll
       for (int j = 0; j < 16; ++j) ptr[j * sn] = v[j];
     }
+  }
+}
+__device__ __forceinline__ void tg_put16h(__half* ptr, long long sn, bool vec, const float (&v)[16]) {
+  if (vec) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      uint32_t w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const __half2 h = __floats2half2_rn(v[8 * j + 2 * i], v[8 * j + 2 * i + 1]);
+        w[i] = *reinterpret_cast<const uint32_t*>(&h);
+      }
+      reinterpret_cast<uint4*>(ptr)[j] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) ptr[j * sn] = __float2half_rn(v[j]);
   }
 }
 
@@ -273,7 +322,8 @@ __device__ __forceinline__ void tg_store16(const TgParams& p, const TgRow& r, in
   }
   if (p.res) {
     float rr[16];
-    tg_load16(rr, p.res + r.r_off + n * p.r_sn, p.r_sn, (p.vec4 & TG_VEC_RES) != 0, wide);
+    if (p.dtype & TG_DT_RES) tg_load16h(rr, reinterpret_cast<const __half*>(p.res) + r.r_off + n * p.r_sn, p.r_sn, (p.vec4 & TG_VEC_RES) != 0);
+    else tg_load16(rr, p.res + r.r_off + n * p.r_sn, p.r_sn, (p.vec4 & TG_VEC_RES) != 0, wide);
     if (p.res_op & 1) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] *= rr[j];
@@ -289,16 +339,20 @@ __device__ __forceinline__ void tg_store16(const TgParams& p, const TgRow& r, in
   }
   if (p.res2) {
     float rr[16];
-    tg_load16(rr, p.res2 + r.o_off + n * p.o_sn, p.o_sn, vec, wide);
+    if (p.dtype & TG_DT_RES2) tg_load16h(rr, reinterpret_cast<const __half*>(p.res2) + r.o_off + n * p.o_sn, p.o_sn, vec);
+    else tg_load16(rr, p.res2 + r.o_off + n * p.o_sn, p.o_sn, vec, wide);
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] += rr[j];
   }
   tg_act_vec(v, p.act_post, p.act_post_p);
-  tg_put16(p.out + r.o_off + n * p.o_sn, p.o_sn, vec, (p.round_tf32 & 1) != 0, wide, v);
+  if (p.dtype & TG_DT_OUT) tg_put16h(reinterpret_cast<__half*>(p.out) + r.o_off + n * p.o_sn, p.o_sn, vec, v);
+  else tg_put16(p.out + r.o_off + n * p.o_sn, p.o_sn, vec, (p.round_tf32 & 1) != 0, wide, v);
   if (p.out2) {
     tg_act_vec(v, p.act2, p.act2_p);
     const long long sn2 = p.out2_own ? p.o2_sn : p.o_sn;
-    tg_put16(p.out2 + r.o2_off + n * sn2, sn2, p.out2_own ? (p.vec4 & TG_VEC_OUT2) != 0 : vec, (p.round_tf32 & 2) != 0, wide, v);
+    const bool vec2 = p.out2_own ? (p.vec4 & TG_VEC_OUT2) != 0 : vec;
+    if (p.dtype & TG_DT_OUT2) tg_put16h(reinterpret_cast<__half*>(p.out2) + r.o2_off + n * sn2, sn2, vec2, v);
+    else tg_put16(p.out2 + r.o2_off + n * sn2, sn2, vec2, (p.round_tf32 & 2) != 0, wide, v);
   }
 }
 

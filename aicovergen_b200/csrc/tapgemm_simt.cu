@@ -180,6 +180,7 @@ tapgemm_simt_kernel(const __grid_constant__ TgParams p) {
 }  // namespace
 
 int tapgemm_simt_launch(const TgParams& p, cudaStream_t stream) {
+  B200VC_REQUIRE(p.dtype == 0, "tapgemm_simt: the exact-fp32 kernel takes fp32 tensors only (dtype flags 0x%x)", p.dtype);
   const int ntw = ceil_div(p.OW, p.BW), nth = ceil_div(p.OH, p.BH);
   const long long tiles = (long long)ntw * nth * p.OB;
   B200VC_REQUIRE(tiles > 0 && tiles < (1ll << 31), "tapgemm: bad tile count %lld", tiles);

@@ -291,14 +291,14 @@ PFN_encodeTiled get_encode_fn() {
 }
 
 int encode_map(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims,
-               const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+               const cuuint64_t* strides_bytes, const cuuint32_t* box, bool half = false) {
   PFN_encodeTiled fn = get_encode_fn();
   if (!fn) {
     set_last_error("cuTensorMapEncodeTiled entry point unavailable");
     return kErrDriver;
   }
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base),
+  CUresult r = fn(tm, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base),
                   dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -338,21 +338,27 @@ int encode_map_f32(CUtensorMap* tm, const void* base, int rank, const cuuint64_t
                    const cuuint64_t* strides_bytes, const cuuint32_t* box) {
   return encode_map(tm, base, rank, dims, strides_bytes, box);
 }
+int encode_map_f16(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims,
+                   const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+  return encode_map(tm, base, rank, dims, strides_bytes, box, true);
+}
 
 // Whether a problem can go through the TMA/tcgen05 path (alignment rules of
 // cuTensorMapEncodeTiled); otherwise callers use the SIMT kernel.
 bool tapgemm_tc_supported(const TgParams& p) {
+  const int epb = (p.dtype & TG_DT_AB) ? 8 : 4;            // elements per 16 bytes
   if ((reinterpret_cast<uintptr_t>(p.A) & 15) || (reinterpret_cast<uintptr_t>(p.Wt) & 15)) return false;
   for (int i = 1; i < 5; ++i)
-    if (p.a_dim[i] > 1 && (p.a_stride[i] % 4 != 0)) return false;
+    if (p.a_dim[i] > 1 && (p.a_stride[i] % epb != 0)) return false;
   if (p.a_stride[0] != 1) return false;
-  if (p.ldw % 4 != 0 || (p.wstride % 4 != 0)) return false;
+  if (p.ldw % epb != 0 || (p.wstride % epb != 0)) return false;
   if (p.BW > 256 || p.BH > 256 || p.BW * p.BH != TG_TILE_M) return false;
   return true;
 }
 
 int tapgemm_tc_launch(const TgParams& p, cudaStream_t stream) {
   B200VC_REQUIRE(tapgemm_tc_supported(p), "tapgemm_tc: operand alignment not TMA-compatible");
+  B200VC_REQUIRE(!(p.dtype & TG_DT_AB), "tapgemm_tc: fp16 operands are handled by the persistent / weight-stationary kernels");
   const int ntw = ceil_div(p.OW, p.BW), nth = ceil_div(p.OH, p.BH);
   const long long tiles = (long long)ntw * nth * p.OB;
   B200VC_REQUIRE(tiles > 0 && tiles < (1ll << 31), "tapgemm_tc: bad tile count %lld", tiles);

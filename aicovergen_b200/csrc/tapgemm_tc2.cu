@@ -16,6 +16,8 @@ namespace b200vc {
 
 int encode_map_f32(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims,
                    const cuuint64_t* strides_bytes, const cuuint32_t* box);   // tapgemm_tc.cu
+int encode_map_f16(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims,
+                   const cuuint64_t* strides_bytes, const cuuint32_t* box);   // tapgemm_tc.cu
 
 namespace {
 
@@ -92,6 +94,25 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// fp16 operands (kind::f16): same shared-memory geometry (128-byte rows, 32-byte K steps), twice the K per step
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+template <bool F16>
+__device__ __forceinline__ void umma_any(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  if constexpr (F16) umma_f16(tmem_d, adesc, bdesc, idesc, acc);
+  else umma_tf32(tmem_d, adesc, bdesc, idesc, acc);
+}
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -108,10 +129,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 // MH = 128-row halves per tile.  MH == 2: one B tile feeds two MMAs (rows 0-127 and 128-255 of a 256-row A box), which
 // cuts the L2->SM operand bytes per FLOP by 1.3-1.5x — the persistent kernel runs at the L2 throughput cap
 // (~43 B/clk/SM, profiles/r01_ncu_kernels.md), so that ratio is its speed.
-template <int BN, int STAGES, int MH>
+template <int BN, int STAGES, int MH, bool F16>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                    const __grid_constant__ TgParams p, int ntiles_n, int total_tiles, int tbw, int tbh, int bias_floats) {
+  constexpr int KE = F16 ? 2 * KCHUNK : KCHUNK;                    // K elements per 128-byte chunk row
+  constexpr int ES = F16 ? 2 : 4;                                  // operand element size
   constexpr int A_STAGE_BYTES = MH * TG_TILE_M * 128;
   constexpr int B_STAGE_BYTES = BN * 128;
   constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
@@ -136,7 +159,7 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform role index
   const int ntw = (p.OW + tbw - 1) / tbw;
   const int nth = (p.OH + tbh - 1) / tbh;
-  const int kchunks = (p.Kc + KCHUNK - 1) / KCHUNK;
+  const int kchunks = (p.Kc + KE - 1) / KE;
   const int nchunks = p.ntaps * kchunks;
 
   if (warp == 0 && lane == 0) {
@@ -189,7 +212,7 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           const TgTap tap = p.taps[tap_i];
           const int cw = w0 + tap.dw, ch = h0 + tap.dh, cp = tap.dp, widx = tap.widx + wsel;
           int ca = tap.c_off;
-          for (int kc0 = 0; kc0 < p.Kc; kc0 += KCHUNK, ca += KCHUNK) {
+          for (int kc0 = 0; kc0 < p.Kc; kc0 += KE, ca += KE) {
             mbar_wait(empty_bar(s), ph ^ 1u);
             if (elect_one()) {
               mbar_expect_tx(full_bar(s), STAGE_BYTES);
@@ -217,9 +240,10 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         // instruction N = the live part of this n-tile rounded up to 16 (e.g. 48 for the MDX c=48 layers)
         const int n0_ = (tile % ntiles_n) * BN;
         const int nrem = p.N - n0_;
-        const uint32_t IDESC = make_idesc_tf32(128, nrem >= BN ? BN : ((nrem + 15) & ~15));
+        const int n_ins = nrem >= BN ? BN : ((nrem + 15) & ~15);
+        const uint32_t IDESC = F16 ? make_idesc_f16(128, n_ins) : make_idesc_tf32(128, n_ins);
         // the last k-chunk of a tap may be short (Kc = 48 -> 32 + 16): issue only the K=8 steps that hold data
-        const int klast = ((p.Kc - (kchunks - 1) * KCHUNK) + 7) >> 3;
+        const int klast = ((p.Kc - (kchunks - 1) * KE) * ES + 31) >> 5;      // 32-byte K steps that hold data
         uint32_t accum = 0u;
         for (int chunk = 0, kc = 0; chunk < nchunks; ++chunk) {
           mbar_wait(full_bar(s), ph);
@@ -233,14 +257,14 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               for (int k = 0; k < KCHUNK / 8; ++k) {
 #pragma unroll
                 for (int mh = 0; mh < MH; ++mh)     // 128 rows x 128 B = 16 KB further into the A box: +1024 in the (addr >> 4) field
-                  umma_tf32(d_tmem + (uint32_t)(mh * BN), adesc + (uint64_t)(mh * 1024 + 2 * k), bdesc + (uint64_t)(2 * k), IDESC, accum);
+                  umma_any<F16>(d_tmem + (uint32_t)(mh * BN), adesc + (uint64_t)(mh * 1024 + 2 * k), bdesc + (uint64_t)(2 * k), IDESC, accum);
                 accum = 1u;
               }
             } else {
               for (int k = 0; k < nk; ++k) {
 #pragma unroll
                 for (int mh = 0; mh < MH; ++mh)
-                  umma_tf32(d_tmem + (uint32_t)(mh * BN), adesc + (uint64_t)(mh * 1024 + 2 * k), bdesc + (uint64_t)(2 * k), IDESC, accum);
+                  umma_any<F16>(d_tmem + (uint32_t)(mh * BN), adesc + (uint64_t)(mh * 1024 + 2 * k), bdesc + (uint64_t)(2 * k), IDESC, accum);
                 accum = 1u;
               }
             }
@@ -294,7 +318,7 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   }
 }
 
-template <int BN, int STAGES, int MH>
+template <int BN, int STAGES, int MH, bool F16>
 int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmW, const TgParams& p, int ntiles_n, int total_tiles,
                int grid, int tbw, int tbh, cudaStream_t stream) {
   constexpr int smem_fixed = STAGES * (MH * TG_TILE_M * 128 + BN * 128) + 8 * (2 * STAGES + 6) + 1024;
@@ -306,10 +330,10 @@ int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmW, const TgParams& p
   const int smem = smem_fixed + (bias_floats ? bias_floats * 4 + 16 : 0);
   static int configured = 0;
   if (configured < smem) {
-    B200VC_CHECK_CUDA(cudaFuncSetAttribute(tapgemm_tc2_kernel<BN, STAGES, MH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B200VC_CHECK_CUDA(cudaFuncSetAttribute(tapgemm_tc2_kernel<BN, STAGES, MH, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = 227 * 1024;
   }
-  tapgemm_tc2_kernel<BN, STAGES, MH><<<grid, NUM_THREADS, smem, stream>>>(tmA, tmW, p, ntiles_n, total_tiles, tbw, tbh, bias_floats);
+  tapgemm_tc2_kernel<BN, STAGES, MH, F16><<<grid, NUM_THREADS, smem, stream>>>(tmA, tmW, p, ntiles_n, total_tiles, tbw, tbh, bias_floats);
   return kOk;
 }
 
@@ -337,7 +361,10 @@ int tapgemm_tc2_launch(const TgParams& p, cudaStream_t stream) {
   // kernel is bound by shared-memory bandwidth (TMA writes + UMMA operand reads share 128 B/clk/SM, and every MMA
   // re-reads its B slice), not by L2 — C256 k11 662 -> 608 TFLOP/s, 768->3072 linear 306 -> 221, C128 k7 486 -> 509.
   // Kept behind b200vc_tapgemm_set_rows256(1) (initial value: env B200VC_TC2_ROWS256) for experiments and tests.
-  const bool rows256 = g_rows256 != 0;
+  const bool f16 = (p.dtype & TG_DT_AB) != 0;
+  const unsigned long long es = f16 ? 2ull : 4ull;                 // operand element size
+  const int epb = f16 ? 8 : 4;                                       // elements per 16 bytes (TMA stride granule)
+  const bool rows256 = g_rows256 != 0 && !f16;
   int tbw = p.BW, tbh = p.BH, MH = 1;
   if (rows256) {
     const int bw2 = p.BH == 1 ? 2 * p.BW : p.BW, bh2 = p.BH == 1 ? 1 : 2 * p.BH;
@@ -355,20 +382,20 @@ int tapgemm_tc2_launch(const TgParams& p, cudaStream_t stream) {
   CUtensorMap tmA, tmW;
   {
     cuuint64_t dims[5], strides[4];
-    cuuint32_t box[5] = {KCHUNK, (cuuint32_t)tbw, (cuuint32_t)tbh, 1, 1};
+    cuuint32_t box[5] = {(cuuint32_t)(f16 ? 2 * KCHUNK : KCHUNK), (cuuint32_t)tbw, (cuuint32_t)tbh, 1, 1};
     long long span = 1;
     for (int i = 0; i < 5; ++i) {
       dims[i] = (cuuint64_t)(p.a_dim[i] > 0 ? p.a_dim[i] : 1);
       if (i > 0) {
         long long st = p.a_stride[i];
-        if (p.a_dim[i] <= 1) st = ((span + 3) / 4) * 4;
-        strides[i - 1] = (cuuint64_t)st * 4ull;
+        if (p.a_dim[i] <= 1) st = ((span + epb - 1) / epb) * epb;
+        strides[i - 1] = (cuuint64_t)st * es;
         span = st * (long long)dims[i];
       } else {
         span = (long long)dims[0];
       }
     }
-    int rc = encode_map_f32(&tmA, p.A, 5, dims, strides, box);
+    int rc = f16 ? encode_map_f16(&tmA, p.A, 5, dims, strides, box) : encode_map_f32(&tmA, p.A, 5, dims, strides, box);
     if (rc) return rc;
   }
   {
@@ -377,27 +404,34 @@ int tapgemm_tc2_launch(const TgParams& p, cudaStream_t stream) {
     const int nw = max_widx + 1 + (p.OB - 1) * p.w_batch_step;
     cuuint64_t dims[3] = {(cuuint64_t)p.Kc, (cuuint64_t)p.N, (cuuint64_t)nw};
     long long wst = p.wstride;
-    if (nw <= 1) wst = ((p.ldw * p.N + 3) / 4) * 4;
-    cuuint64_t strides[2] = {(cuuint64_t)p.ldw * 4ull, (cuuint64_t)wst * 4ull};
-    cuuint32_t box[3] = {KCHUNK, (cuuint32_t)BN, 1};
-    int rc = encode_map_f32(&tmW, p.Wt, 3, dims, strides, box);
+    if (nw <= 1) wst = ((p.ldw * p.N + epb - 1) / epb) * epb;
+    cuuint64_t strides[2] = {(cuuint64_t)p.ldw * es, (cuuint64_t)wst * es};
+    cuuint32_t box[3] = {(cuuint32_t)(f16 ? 2 * KCHUNK : KCHUNK), (cuuint32_t)BN, 1};
+    int rc = f16 ? encode_map_f16(&tmW, p.Wt, 3, dims, strides, box) : encode_map_f32(&tmW, p.Wt, 3, dims, strides, box);
     if (rc) return rc;
   }
   const int grid = (int)(total < num_sms() ? total : num_sms());
   int rc;
-  if (MH == 2) {
+  if (f16) {
     switch (BN) {
-      case 256: rc = launch_cfg<256, 3, 2>(tmA, tmW, p, ntiles_n, (int)total, grid, tbw, tbh, stream); break;
-      case 128: rc = launch_cfg<128, 4, 2>(tmA, tmW, p, ntiles_n, (int)total, grid, tbw, tbh, stream); break;
-      case 64:  rc = launch_cfg<64, 5, 2>(tmA, tmW, p, ntiles_n, (int)total, grid, tbw, tbh, stream); break;
-      default:  rc = launch_cfg<32, 6, 2>(tmA, tmW, p, ntiles_n, (int)total, grid, tbw, tbh, stream); break;
+      case 256: rc = launch_cfg<256, 4, 1, true>(tmA, tmW, p, ntiles_n, (int)total, grid, tbw, tbh, stream); break;
+      case 128: rc = launch_cfg<128, 6, 1, true>(tmA, tmW, p, ntiles_n, (int)total, grid, tbw, tbh, stream); break;
+      case 64:  rc = launch_cfg<64, 8, 1, true>(tmA, tmW, p, ntiles_n, (int)total, grid, tbw, tbh, stream); break;
+      default:  rc = launch_cfg<32, 8, 1, true>(tmA, tmW, p, ntiles_n, (int)total, grid, tbw, tbh, stream); break;
+    }
+  } else if (MH == 2) {
+    switch (BN) {
+      case 256: rc = launch_cfg<256, 3, 2, false>(tmA, tmW, p, ntiles_n, (int)total, grid, tbw, tbh, stream); break;
+      case 128: rc = launch_cfg<128, 4, 2, false>(tmA, tmW, p, ntiles_n, (int)total, grid, tbw, tbh, stream); break;
+      case 64:  rc = launch_cfg<64, 5, 2, false>(tmA, tmW, p, ntiles_n, (int)total, grid, tbw, tbh, stream); break;
+      default:  rc = launch_cfg<32, 6, 2, false>(tmA, tmW, p, ntiles_n, (int)total, grid, tbw, tbh, stream); break;
     }
   } else {
     switch (BN) {
-      case 256: rc = launch_cfg<256, 4, 1>(tmA, tmW, p, ntiles_n, (int)total, grid, tbw, tbh, stream); break;
-      case 128: rc = launch_cfg<128, 6, 1>(tmA, tmW, p, ntiles_n, (int)total, grid, tbw, tbh, stream); break;
-      case 64:  rc = launch_cfg<64, 8, 1>(tmA, tmW, p, ntiles_n, (int)total, grid, tbw, tbh, stream); break;
-      default:  rc = launch_cfg<32, 8, 1>(tmA, tmW, p, ntiles_n, (int)total, grid, tbw, tbh, stream); break;
+      case 256: rc = launch_cfg<256, 4, 1, false>(tmA, tmW, p, ntiles_n, (int)total, grid, tbw, tbh, stream); break;
+      case 128: rc = launch_cfg<128, 6, 1, false>(tmA, tmW, p, ntiles_n, (int)total, grid, tbw, tbh, stream); break;
+      case 64:  rc = launch_cfg<64, 8, 1, false>(tmA, tmW, p, ntiles_n, (int)total, grid, tbw, tbh, stream); break;
+      default:  rc = launch_cfg<32, 8, 1, false>(tmA, tmW, p, ntiles_n, (int)total, grid, tbw, tbh, stream); break;
     }
   }
   if (rc) return rc;

@@ -22,6 +22,8 @@ namespace b200vc {
 
 int encode_map_f32(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims,
                    const cuuint64_t* strides_bytes, const cuuint32_t* box);   // tapgemm_tc.cu
+int encode_map_f16(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims,
+                   const cuuint64_t* strides_bytes, const cuuint32_t* box);   // tapgemm_tc.cu
 
 namespace {
 
@@ -105,6 +107,19 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
+// fp16 operands (kind::f16): same shared-memory geometry, twice the K per 32-byte step
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -164,7 +179,7 @@ struct TileWalk {
 
 // KW_T: the tap-grid width when it is one of the common kernel sizes (3 / 5 / 7 / 11), else 0 = run-time loop.  With
 // Cout <= 64 an MMA lasts 16-32 clk, so the single issuing lane is on the critical path and the tap loop must unroll.
-template <int KW_T>
+template <int KW_T, bool F16>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tapgemm_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                   const __grid_constant__ TgParams p, const WsGeom g) {
@@ -173,7 +188,9 @@ tapgemm_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const int kchunks = (p.Kc + KCHUNK - 1) / KCHUNK;
+  constexpr int KE = F16 ? 2 * KCHUNK : KCHUNK;       // K elements per 128-byte chunk row
+  constexpr int ES = F16 ? 2 : 4;
+  const int kchunks = (p.Kc + KE - 1) / KE;
   const int w_bytes = p.ntaps * kchunks * g.b_tile_bytes;
   const uint32_t w_base = smem_base;                              // resident weights
   const uint32_t a_base = smem_base + w_bytes;                    // A halo ring (w_bytes is a multiple of 1024)
@@ -221,7 +238,7 @@ tapgemm_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         mbar_expect_tx(w_bar, (uint32_t)w_bytes);
         for (int j = 0; j < p.ntaps; ++j)
           for (int kc = 0; kc < kchunks; ++kc)
-            tma_load_3d(w_base + (uint32_t)((j * kchunks + kc) * g.b_tile_bytes), &tmW, w_bar, kc * KCHUNK, 0, j);
+            tma_load_3d(w_base + (uint32_t)((j * kchunks + kc) * g.b_tile_bytes), &tmW, w_bar, kc * KE, 0, j);
       }
       __syncwarp();
       int it = 0;
@@ -234,7 +251,7 @@ tapgemm_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           mbar_wait(empty_bar(s), ph ^ 1u);
           if (elect_one()) {
             mbar_expect_tx(full_bar(s), a_tx);
-            tma_load_5d(a_stage(s), &tmA, full_bar(s), kc * KCHUNK, tk.tw * 128 - g.pad_w, tk.h - g.pad_h, tk.b, 0);
+            tma_load_5d(a_stage(s), &tmA, full_bar(s), kc * KE, tk.tw * 128 - g.pad_w, tk.h - g.pad_h, tk.b, 0);
           }
           __syncwarp();
         }
@@ -245,7 +262,7 @@ tapgemm_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // The whole warp walks the loops (warp-uniform control flow keeps descriptors in uniform registers); one elected
     // lane issues the tcgen05 instructions.
     {
-      const uint32_t IDESC = make_idesc_tf32(128, g.Nr);
+      const uint32_t IDESC = F16 ? make_idesc_f16(128, g.Nr) : make_idesc_tf32(128, g.Nr);
       mbar_wait(w_bar, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       int it = 0, ti = 0;
@@ -268,7 +285,7 @@ tapgemm_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const uint64_t a_kw_step = (uint64_t)(g.dil_w * 8), a_kh_step = (uint64_t)(g.BWh * 8);   // rows x 128 B >> 4
           uint32_t accum = kc > 0 ? 1u : 0u;
           // short last k-chunk (Kc = 48 -> 32 + 16): only the K=8 steps that hold data (25 % fewer MMAs and operand reads)
-          const int nk = (kc == kchunks - 1) ? (((p.Kc - kc * KCHUNK) + 7) >> 3) : KCHUNK / 8;
+          const int nk = (kc == kchunks - 1) ? (((p.Kc - kc * KE) * ES + 31) >> 5) : KCHUNK / 8;
           if (elect_one()) {
             for (int kh = 0; kh < g.KH; ++kh, adesc_row += a_kh_step) {
               uint64_t adesc = adesc_row;
@@ -277,12 +294,14 @@ tapgemm_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 if (nk == KCHUNK / 8) {       // full chunk: straight-line issue (a counted loop here costs the N<=32 layers 20 %)
 #pragma unroll
                   for (int k = 0; k < KCHUNK / 8; ++k) {
-                    umma_tf32(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, accum);
+                    if constexpr (F16) umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, accum);
+                    else umma_tf32(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, accum);
                     accum = 1u;
                   }
                 } else {
                   for (int k = 0; k < nk; ++k) {
-                    umma_tf32(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, accum);
+                    if constexpr (F16) umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, accum);
+                    else umma_tf32(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, accum);
                     accum = 1u;
                   }
                 }
@@ -369,7 +388,8 @@ bool ws_geometry(const TgParams& p, WsGeom& g) {
   g.Nr = (p.N + 15) & ~15;                 // MMA N and weight-tile rows (16 rows x 128 B = 2 KB granules: stays 1024-aligned)
   g.b_tile_bytes = g.Nr * 128;
   g.a_stage_bytes = ((KH * g.BWh * 128 + 1023) / 1024) * 1024;   // 1024-aligned stages (swizzle atom = 8 rows x 128 B)
-  const int kchunks = (p.Kc + KCHUNK - 1) / KCHUNK;
+  const int ke = (p.dtype & TG_DT_AB) ? 2 * KCHUNK : KCHUNK;
+  const int kchunks = (p.Kc + ke - 1) / ke;
   const int w_bytes = p.ntaps * kchunks * g.b_tile_bytes;
   const int fixed = 8 * 14 + 16 + 1024;
   int stages = (SMEM_LIMIT - fixed - w_bytes) / g.a_stage_bytes;
@@ -389,55 +409,69 @@ bool tapgemm_ws_applicable(const TgParams& p) {
   return ws_geometry(p, g);
 }
 
+template <int KW_T, bool F16>
+static int ws_launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmW, const TgParams& p, const WsGeom& g, int grid, int smem,
+                         cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    B200VC_CHECK_CUDA(cudaFuncSetAttribute(tapgemm_ws_kernel<KW_T, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    configured = true;
+  }
+  tapgemm_ws_kernel<KW_T, F16><<<grid, NUM_THREADS, smem, stream>>>(tmA, tmW, p, g);
+  return kOk;
+}
+
+template <bool F16>
+static int ws_dispatch_kw(const CUtensorMap& tmA, const CUtensorMap& tmW, const TgParams& p, const WsGeom& g, int grid, int smem,
+                          cudaStream_t stream) {
+  switch (g.KW) {
+    case 3:  return ws_launch_cfg<3, F16>(tmA, tmW, p, g, grid, smem, stream);
+    case 5:  return ws_launch_cfg<5, F16>(tmA, tmW, p, g, grid, smem, stream);
+    case 7:  return ws_launch_cfg<7, F16>(tmA, tmW, p, g, grid, smem, stream);
+    case 11: return ws_launch_cfg<11, F16>(tmA, tmW, p, g, grid, smem, stream);
+    default: return ws_launch_cfg<0, F16>(tmA, tmW, p, g, grid, smem, stream);
+  }
+}
+
 int tapgemm_ws_launch(const TgParams& p, cudaStream_t stream) {
   WsGeom g;
   B200VC_REQUIRE(ws_geometry(p, g), "tapgemm_ws: descriptor is not a small-channel regular convolution");
-  const int kchunks = (p.Kc + KCHUNK - 1) / KCHUNK;
+  const bool f16 = (p.dtype & TG_DT_AB) != 0;
+  const unsigned long long es = f16 ? 2ull : 4ull;
+  const int epb = f16 ? 8 : 4;
+  const int ke = f16 ? 2 * KCHUNK : KCHUNK;
+  const int kchunks = (p.Kc + ke - 1) / ke;
   CUtensorMap tmA, tmW;
   {
     cuuint64_t dims[5], strides[4];
-    cuuint32_t box[5] = {KCHUNK, (cuuint32_t)g.BWh, (cuuint32_t)g.KH, 1, 1};
+    cuuint32_t box[5] = {(cuuint32_t)ke, (cuuint32_t)g.BWh, (cuuint32_t)g.KH, 1, 1};
     long long span = 1;
     for (int i = 0; i < 5; ++i) {
       dims[i] = (cuuint64_t)(p.a_dim[i] > 0 ? p.a_dim[i] : 1);
       if (i > 0) {
         long long st = p.a_stride[i];
-        if (p.a_dim[i] <= 1) st = ((span + 3) / 4) * 4;
-        strides[i - 1] = (cuuint64_t)st * 4ull;
+        if (p.a_dim[i] <= 1) st = ((span + epb - 1) / epb) * epb;
+        strides[i - 1] = (cuuint64_t)st * es;
         span = st * (long long)dims[i];
       } else {
         span = (long long)dims[0];
       }
     }
-    int rc = encode_map_f32(&tmA, p.A, 5, dims, strides, box);
+    int rc = f16 ? encode_map_f16(&tmA, p.A, 5, dims, strides, box) : encode_map_f32(&tmA, p.A, 5, dims, strides, box);
     if (rc) return rc;
   }
   {
     cuuint64_t dims[3] = {(cuuint64_t)p.Kc, (cuuint64_t)p.N, (cuuint64_t)p.ntaps};
-    cuuint64_t strides[2] = {(cuuint64_t)p.ldw * 4ull, (cuuint64_t)p.wstride * 4ull};
-    cuuint32_t box[3] = {KCHUNK, (cuuint32_t)g.Nr, 1};
-    int rc = encode_map_f32(&tmW, p.Wt, 3, dims, strides, box);
+    cuuint64_t strides[2] = {(cuuint64_t)p.ldw * es, (cuuint64_t)p.wstride * es};
+    cuuint32_t box[3] = {(cuuint32_t)ke, (cuuint32_t)g.Nr, 1};
+    int rc = f16 ? encode_map_f16(&tmW, p.Wt, 3, dims, strides, box) : encode_map_f32(&tmW, p.Wt, 3, dims, strides, box);
     if (rc) return rc;
   }
   const int w_bytes = p.ntaps * kchunks * g.b_tile_bytes;
   const int smem = w_bytes + g.stages * g.a_stage_bytes + 8 * 14 + 16 + 1024;
-  static bool configured = false;
-  if (!configured) {
-    B200VC_CHECK_CUDA(cudaFuncSetAttribute(tapgemm_ws_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    B200VC_CHECK_CUDA(cudaFuncSetAttribute(tapgemm_ws_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    B200VC_CHECK_CUDA(cudaFuncSetAttribute(tapgemm_ws_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    B200VC_CHECK_CUDA(cudaFuncSetAttribute(tapgemm_ws_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    B200VC_CHECK_CUDA(cudaFuncSetAttribute(tapgemm_ws_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    configured = true;
-  }
   const int grid = g.total_tiles < num_sms_ws() ? g.total_tiles : num_sms_ws();
-  switch (g.KW) {
-    case 3:  tapgemm_ws_kernel<3><<<grid, NUM_THREADS, smem, stream>>>(tmA, tmW, p, g); break;
-    case 5:  tapgemm_ws_kernel<5><<<grid, NUM_THREADS, smem, stream>>>(tmA, tmW, p, g); break;
-    case 7:  tapgemm_ws_kernel<7><<<grid, NUM_THREADS, smem, stream>>>(tmA, tmW, p, g); break;
-    case 11: tapgemm_ws_kernel<11><<<grid, NUM_THREADS, smem, stream>>>(tmA, tmW, p, g); break;
-    default: tapgemm_ws_kernel<0><<<grid, NUM_THREADS, smem, stream>>>(tmA, tmW, p, g); break;
-  }
+  int rc = f16 ? ws_dispatch_kw<true>(tmA, tmW, p, g, grid, smem, stream) : ws_dispatch_kw<false>(tmA, tmW, p, g, grid, smem, stream);
+  if (rc) return rc;
   count_launch();
   B200VC_LAUNCH_CHECK();
   return kOk;

@@ -43,12 +43,12 @@ class View:
     off: int = 0
 
     def ptr(self) -> int:
-        return self.t.data_ptr() + 4 * self.off
+        return self.t.data_ptr() + self.t.element_size() * self.off
 
 
 def view(x: torch.Tensor) -> View:
     """View of a channels-last tensor [W,C] / [H,W,C] / [B,H,W,C] (stride(-1) must be 1)."""
-    assert x.dtype == torch.float32 and x.stride(-1) == 1, (x.dtype, x.stride())
+    assert x.dtype in (torch.float32, torch.float16) and x.stride(-1) == 1, (x.dtype, x.stride())
     shp, st = list(x.shape), list(x.stride())
     while len(shp) < 4:
         shp.insert(0, 1)
@@ -69,12 +69,12 @@ class Weights:
     off: int = 0
 
     def ptr(self) -> int:
-        return self.t.data_ptr() + 4 * self.off
+        return self.t.data_ptr() + self.t.element_size() * self.off
 
 
 def weights(w: torch.Tensor) -> Weights:
     """Packed weights [ntaps, N, K] (or [N, K]) contiguous."""
-    assert w.dtype == torch.float32 and w.is_contiguous()
+    assert w.dtype in (torch.float32, torch.float16) and w.is_contiguous()
     if w.dim() == 2:
         w = w.unsqueeze(0)
     nt, N, K = w.shape
@@ -99,12 +99,12 @@ class Out:
     sn: int = 1
 
     def ptr(self) -> int:
-        return self.t.data_ptr() + 4 * self.off
+        return self.t.data_ptr() + self.t.element_size() * self.off
 
 
 def out_of(x: torch.Tensor, **kw) -> Out:
     """Output spec writing a channels-last tensor [W,N] / [H,W,N] / [B,H,W,N] (may be a column slice)."""
-    assert x.dtype == torch.float32 and x.stride(-1) == 1
+    assert x.dtype in (torch.float32, torch.float16) and x.stride(-1) == 1
     shp, st = list(x.shape), list(x.stride())
     while len(shp) < 4:
         shp.insert(0, 1)
@@ -198,7 +198,7 @@ class TapGemm:
         p.r_sb = p.r_sh = p.r_sw = 0
         if epi.res is not None:
             r = epi.res
-            assert r.dtype == torch.float32
+            assert r.dtype in (torch.float32, torch.float16)
             if epi.res_strides is not None:
                 p.r_sb, p.r_sh, p.r_sw, p.r_sn = (int(v_) for v_ in epi.res_strides)
             else:
@@ -213,7 +213,7 @@ class TapGemm:
         p.scale = float(epi.scale)
         if epi.res2 is not None:
             assert epi.res2.stride() == out.t.stride() or epi.res2.shape == out.t.shape
-            p.res2 = epi.res2.data_ptr() + 4 * out.off
+            p.res2 = epi.res2.data_ptr() + epi.res2.element_size() * out.off
             self._keep.append(epi.res2)
         p.act_post, p.act_post_p = epi.act_post, float(epi.act_post_p)
         p.out = out.ptr()
@@ -225,32 +225,47 @@ class TapGemm:
             self._keep.append(o2.t)
         elif epi.out2 is not None:
             assert epi.out2.stride() == out.t.stride()
-            p.out2 = epi.out2.data_ptr() + 4 * out.off
+            p.out2 = epi.out2.data_ptr() + epi.out2.element_size() * out.off
             self._keep.append(epi.out2)
         p.act2, p.act2_p = epi.act2, float(epi.act2_p)
         p.round_tf32 = (1 if epi.round_out else 0) | (2 if epi.round_out2 else 0)
         for i, (c_off, dw, dh, dp, widx) in enumerate(self.taps):
             t = p.taps[i]
             t.c_off, t.dw, t.dh, t.dp, t.widx = int(c_off), int(dw), int(dh), int(dp), int(widx)
-        # ---- vectorisation flags
+        # ---- element types: fp16 operands / epilogue tensors (tensor-core backends only; see b200vc.h `dtype`)
+        half = torch.float16
+        assert a.t.dtype == w.t.dtype, "A and W must have the same element type"
+        dt = 1 if a.t.dtype == half else 0
+        dt |= 2 if out.t.dtype == half else 0
+        o2t = epi.out2.t if isinstance(epi.out2, Out) else epi.out2
+        dt |= 4 if (o2t is not None and o2t.dtype == half) else 0
+        dt |= 8 if (epi.res is not None and epi.res.dtype == half) else 0
+        dt |= 16 if (epi.res2 is not None and epi.res2.dtype == half) else 0
+        p.dtype = dt
+        es_a = a.t.element_size()
+        es_o, es_o2 = out.t.element_size(), (o2t.element_size() if o2t is not None else 4)
+        es_r = epi.res.element_size() if epi.res is not None else 4
+        es_r2 = epi.res2.element_size() if epi.res2 is not None else 4
+        # ---- vectorisation flags (16-byte alignment of base pointers and of every stride, in bytes)
         v = 0
-        k_ok = (p.A or 0) % 16 == 0 and (p.Wt or 0) % 16 == 0 and p.ldw % 4 == 0 and p.wstride % 4 == 0
+        k_ok = dt == 0 and (p.A or 0) % 16 == 0 and (p.Wt or 0) % 16 == 0 and p.ldw % 4 == 0 and p.wstride % 4 == 0
         k_ok = k_ok and all(a.dims[i] <= 1 or a.strides[i] % 4 == 0 for i in range(1, 5))
         k_ok = k_ok and all(t[0] % 4 == 0 for t in self.taps)
         if k_ok:
             v |= 1
 
-        def al(ptr, *strides):
-            return (ptr or 0) % 16 == 0 and all(s_ % 4 == 0 for s_ in strides)
+        def al(ptr, es, *strides):
+            return (ptr or 0) % 16 == 0 and all((s_ * es) % 16 == 0 for s_ in strides)
 
         shared2 = p.out2 if not p.out2_own else 0
-        if p.o_sn == 1 and al(p.out, p.o_sb, p.o_sh, p.o_sw) and al(shared2) and al(p.res2):
+        if p.o_sn == 1 and al(p.out, es_o, p.o_sb, p.o_sh, p.o_sw) and al(shared2, es_o2, p.o_sb, p.o_sh, p.o_sw) and \
+                al(p.res2, es_r2, p.o_sb, p.o_sh, p.o_sw):
             v |= 2
-        if al(p.bias) or p.bias_per_row:
+        if al(p.bias, 4) or p.bias_per_row:
             v |= 4
-        if not p.out2_own or (p.o2_sn == 1 and al(p.out2, p.o2_sb, p.o2_sh, p.o2_sw)):
+        if not p.out2_own or (p.o2_sn == 1 and al(p.out2, es_o2, p.o2_sb, p.o2_sh, p.o2_sw)):
             v |= 8
-        if not p.res or (p.r_sn == 1 and al(p.res, p.r_sb, p.r_sh, p.r_sw)):
+        if not p.res or (p.r_sn == 1 and al(p.res, es_r, p.r_sb, p.r_sh, p.r_sw)):
             v |= 16
         p.vec4 = v
         self.params = p
@@ -273,6 +288,8 @@ class TapGemm:
     def __call__(self, stream: Optional[int] = None, backend: Optional[int] = None):
         be = self.backend if backend is None else backend
         if be in (BACKEND_TC, BACKEND_TC_V1, BACKEND_TC_TILE) and not self.tc_supported():
+            if self.params.dtype:
+                raise ValueError(f"tapgemm[{self.name}]: fp16 tensors need a TMA-addressable problem (tensor-core kernels only)")
             be = BACKEND_SIMT   # operand not TMA-addressable (e.g. C==1); still CUDA, still fp32-exact
         if stream is None:
             stream = torch.cuda.current_stream().cuda_stream

@@ -106,6 +106,11 @@ typedef struct b200vc_tapgemm_params {
                            loads; 2 = out/res2 (and a layout-sharing out2) channels-last + 16-byte aligned; 4 = per-column
                            bias float4-loadable; 8 = own-layout out2 channels-last + aligned; 16 = res likewise        */
   int32_t round_tf32;   /* bit0: round `out` to TF32 (RN), bit1: round `out2` — for tensors only consumed by TF32 GEMMs */
+  int32_t dtype;        /* element types (0 = everything fp32): bit0 A and W are IEEE fp16 (tcgen05 kind::f16, fp32
+                           accumulate; same 10-bit mantissa as TF32 at half the operand bytes) — tensor-core backends
+                           only; bit1 out, bit2 out2, bit3 res, bit4 res2 are fp16.  Pointers stay typed `float*` in
+                           this struct; offsets and strides are in ELEMENTS of the tensor's own type.
+                           EXPERIMENTAL in round 1: compiled and emulator-tested, not yet validated on a GPU. */
   b200vc_tap taps[B200VC_MAX_TAPS];
 } b200vc_tapgemm_params;
 

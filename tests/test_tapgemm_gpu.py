@@ -305,3 +305,46 @@ def test_persistent_256_row_tiles_conv2d():
     finally:
         _ffi.lib().b200vc_tapgemm_set_rows256(0)
     check(outs[1].cpu(), outs[0].cpu(), 2e-3, "persistent 256-row tiles conv2d")
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# fp16 operand storage (tcgen05 kind::f16) — EXPERIMENTAL: not part of the product path in round 1.
+# Run with B200VC_EXPERIMENTAL=1.
+# ------------------------------------------------------------------------------------------------------------------
+import os  # noqa: E402
+
+experimental = pytest.mark.skipif(os.environ.get("B200VC_EXPERIMENTAL") != "1", reason="experimental fp16 path (set B200VC_EXPERIMENTAL=1)")
+
+
+@experimental
+@pytest.mark.parametrize("backend", [tg.BACKEND_TC, tg.BACKEND_TC_V1])
+@pytest.mark.parametrize("T,Ci,Co,k,d", [(3000, 128, 128, 3, 1), (5000, 64, 64, 7, 3), (2500, 48, 96, 3, 1), (777, 768, 384, 1, 1)])
+def test_fp16_conv1d(backend, T, Ci, Co, k, d):
+    g = torch.Generator().manual_seed(T + Ci)
+    x = torch.randn(T, Ci, generator=g).half()
+    w = (torch.randn(Co, Ci, k, generator=g) / (Ci * k) ** 0.5).half()
+    b = torch.randn(Co, generator=g)
+    res = torch.randn(T, Co, generator=g).half()
+    ref = F.leaky_relu(F.conv1d(x.float().t()[None], w.float(), b, dilation=d, padding=(k * d - d) // 2)[0].t(), 0.1) + res.float()
+    xd, wd, bd, rd = dev(x, tg.pack_conv1d(w.float()).half(), b, res)
+    out = torch.full((T, Co), float("nan"), device="cuda", dtype=torch.float16)
+    out2 = torch.full((T, Co), float("nan"), device="cuda")
+    tg.conv1d(xd, wd, out, dilation=d, epi=tg.Epi(bias=bd, act_pre=tg.ACT_LRELU, act_pre_p=0.1, res=rd, out2=out2), backend=backend)()
+    torch.cuda.synchronize()
+    check(out2.cpu(), ref, 2e-3, f"fp16 conv1d fp32 out2 T={T} {Ci}->{Co}")
+    check(out.float().cpu(), ref, 3e-3, f"fp16 conv1d half out T={T} {Ci}->{Co}")
+
+
+@experimental
+@pytest.mark.parametrize("B,H,W,Ci,Co", [(1, 40, 256, 48, 48), (2, 21, 384, 48, 96), (1, 16, 128, 144, 144)])
+def test_fp16_conv2d(B, H, W, Ci, Co):
+    g = torch.Generator().manual_seed(H + W)
+    x = torch.randn(B, H, W, Ci, generator=g).half()
+    w = (torch.randn(Co, Ci, 3, 3, generator=g) / (Ci * 9) ** 0.5).half()
+    b = torch.randn(Co, generator=g)
+    ref = F.relu(F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, padding=1)).permute(0, 2, 3, 1).contiguous()
+    xd, wd, bd = dev(x, tg.pack_conv2d(w.float()).half(), b)
+    out = torch.full((B, H, W, Co), float("nan"), device="cuda", dtype=torch.float16)
+    tg.conv2d(xd, wd, out, 3, 3, (1, 1), tg.Epi(bias=bd, act_pre=tg.ACT_RELU))()
+    torch.cuda.synchronize()
+    check(out.float().cpu(), ref, 3e-3, f"fp16 conv2d {Ci}->{Co}")

@@ -219,3 +219,27 @@ def test_conv_transpose2d_k2s2_two_gemms_with_mapped_skip():
         emulate(op)
     ref = F.relu(F.conv_transpose2d(x.permute(0, 3, 1, 2), w, b, stride=2)).permute(0, 2, 3, 1) * sk
     close(out, ref)
+
+
+def test_fp16_tensors_descriptor_and_semantics():
+    """fp16 operands / outputs / residual (b200vc.h `dtype`): flags, element-unit offsets and the same epilogue
+    semantics, executed by the emulator on half tensors (the tcgen05 kind::f16 path itself needs a GPU)."""
+    g = torch.Generator().manual_seed(21)
+    B, H, W, Ci, Co = 1, 6, 40, 48, 32
+    x = torch.randn(B, H, W, Ci, generator=g).half()
+    w = (torch.randn(Co, Ci, 3, 3, generator=g) / (9 * Ci) ** 0.5)
+    b = torch.randn(Co, generator=g)
+    res = torch.randn(B, H, W, Co, generator=g).half()
+    out = torch.zeros(B, H, W, Co, dtype=torch.float16)
+    out2 = torch.zeros(B, H, W, Co)                                   # second output stays fp32
+    op = tg.conv2d(x, tg.pack_conv2d(w).half(), out, 3, 3, (1, 1), tg.Epi(bias=b, act_pre=tg.ACT_RELU, res=res, out2=out2))
+    assert op.params.dtype == 1 | 2 | 8
+    assert op.params.vec4 & 2 and op.params.vec4 & 16                 # 32 halfs per row = 64 bytes: still 16-byte aligned
+    emulate(op)
+    ref = F.relu(F.conv2d(x.float().permute(0, 3, 1, 2), w.half().float(), b, padding=1)).permute(0, 2, 3, 1) + res.float()
+    close(out.float(), ref, 2e-3)
+    close(out2, ref, 1e-5)
+    # a column slice of a wider half buffer: offsets are in elements of the tensor's own type
+    wide = torch.zeros(5, 96, dtype=torch.float16)
+    lin = tg.linear(torch.randn(5, 64, generator=g).half(), torch.randn(32, 64, generator=g).half(), wide[:, 64:])
+    assert lin.params.out == wide.data_ptr() + 2 * 64
