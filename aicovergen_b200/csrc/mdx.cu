@@ -1,6 +1,7 @@
 // MDX-Net pass helpers (src/mdx.py): chunk gathering with the pad_wave zero regions and the STFT reflect
 // padding fused, NHWC <-> NHCW tiled transposes around the TDF (frequency-axis linear) GEMMs, and the
 // iSTFT overlap-add + window-envelope normalisation + trim fused with the scatter into the song buffer.
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "../../include/b200vc.h"
 
@@ -36,7 +37,7 @@ __global__ void mdx_gather_chunks_kernel(const float* __restrict__ wave, long lo
 // per (pixel, 4-channel group) so every store instruction covers contiguous 16-byte pieces of one NHWC row.
 __global__ void mdx_first_conv_kernel(const float* __restrict__ spec, const float* __restrict__ w4,
                                       const float* __restrict__ bias, float* __restrict__ out, long long npix,
-                                      long long TF, int g4, int round_out) {
+                                      long long TF, int g4, int round_out, int out_half) {
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (idx >= npix * g4) return;
   const long long pix = idx / g4;
@@ -53,22 +54,35 @@ __global__ void mdx_first_conv_kernel(const float* __restrict__ spec, const floa
     a = fmaxf(a + __ldg(bias + cg * 4 + j), 0.f);
     v[j] = round_out ? round_tf32(a) : a;
   }
-  reinterpret_cast<float4*>(out)[idx] = make_float4(v[0], v[1], v[2], v[3]);
+  if (out_half) {      // fp16 activation storage: 4 channels = one 8-byte store
+    const __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+    reinterpret_cast<uint2*>(out)[idx] = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+  } else {
+    reinterpret_cast<float4*>(out)[idx] = make_float4(v[0], v[1], v[2], v[3]);
+  }
 }
 
 // Final 1x1 convolution (c -> 4 channels + bias): NHWC x[B][T][F][c] -> spec[B][2 ch][T][F][2 ri].  Read-bound: one
 // thread per pixel streams its c contiguous floats (float4) and keeps the four dot products in registers.
 __global__ void mdx_final_conv_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                                      float* __restrict__ spec, long long npix, long long TF, int c, int round_out) {
+                                      float* __restrict__ spec, long long npix, long long TF, int c, int round_out, int x_half) {
   extern __shared__ float ws[];            // [4][c]
   for (int i = threadIdx.x; i < 4 * c; i += blockDim.x) ws[i] = w[i];
   __syncthreads();
   const long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (pix >= npix) return;
   const float4* xp = reinterpret_cast<const float4*>(x + pix * c);
+  const uint2* xh = reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(x) + pix * c);
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
   for (int k = 0; k < c; k += 4) {
-    const float4 t = __ldg(xp + (k >> 2));
+    float4 t;
+    if (x_half) {
+      const uint2 u = __ldg(xh + (k >> 2));
+      const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+      t = make_float4(f0.x, f0.y, f1.x, f1.y);
+    } else {
+      t = __ldg(xp + (k >> 2));
+    }
     a0 = fmaf(t.x, ws[k], a0); a0 = fmaf(t.y, ws[k + 1], a0); a0 = fmaf(t.z, ws[k + 2], a0); a0 = fmaf(t.w, ws[k + 3], a0);
     a1 = fmaf(t.x, ws[c + k], a1); a1 = fmaf(t.y, ws[c + k + 1], a1); a1 = fmaf(t.z, ws[c + k + 2], a1); a1 = fmaf(t.w, ws[c + k + 3], a1);
     a2 = fmaf(t.x, ws[2 * c + k], a2); a2 = fmaf(t.y, ws[2 * c + k + 1], a2); a2 = fmaf(t.z, ws[2 * c + k + 2], a2); a2 = fmaf(t.w, ws[2 * c + k + 3], a2);
@@ -187,24 +201,24 @@ int b200vc_mdx_gather_chunks(const float* wave, int64_t n_song, const int64_t* s
 }
 
 int b200vc_mdx_first_conv(const float* spec, const float* w4, const float* bias, float* out, int B, int T, int F, int g,
-                          int round_out, void* stream) {
+                          int round_out, int out_half, void* stream) {
   B200VC_REQUIRE(spec && w4 && bias && out && B > 0 && T > 0 && F > 0 && g > 0 && g % 4 == 0, "mdx_first_conv: bad args (g=%d)", g);
   B200VC_REQUIRE(((uintptr_t)spec % 8 == 0) && ((uintptr_t)w4 % 16 == 0) && ((uintptr_t)out % 16 == 0), "mdx_first_conv: alignment");
   const long long npix = (long long)B * T * F;
   mdx_first_conv_kernel<<<blocks_for(npix * (g / 4), 256), 256, 0, (cudaStream_t)stream>>>(spec, w4, bias, out, npix, (long long)T * F,
-                                                                                          g / 4, round_out);
+                                                                                          g / 4, round_out, out_half);
   count_launch();
   B200VC_LAUNCH_CHECK();
   return kOk;
 }
 
 int b200vc_mdx_final_conv(const float* x, const float* w, const float* bias, float* spec, int B, int T, int F, int c,
-                          int round_out, void* stream) {
+                          int round_out, int x_half, void* stream) {
   B200VC_REQUIRE(x && w && bias && spec && B > 0 && T > 0 && F > 0 && c > 0 && c % 4 == 0 && c <= 2048, "mdx_final_conv: bad args (c=%d)", c);
   B200VC_REQUIRE(((uintptr_t)x % 16 == 0) && ((uintptr_t)spec % 8 == 0), "mdx_final_conv: alignment");
   const long long npix = (long long)B * T * F;
   mdx_final_conv_kernel<<<blocks_for(npix, 128), 128, 4 * c * sizeof(float), (cudaStream_t)stream>>>(x, w, bias, spec, npix,
-                                                                                                  (long long)T * F, c, round_out);
+                                                                                                  (long long)T * F, c, round_out, x_half);
   count_launch();
   B200VC_LAUNCH_CHECK();
   return kOk;

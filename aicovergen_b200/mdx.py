@@ -106,12 +106,19 @@ def _stft_gemm(padded, fwd, spec2, model: MDXModel, backend):
     return tg.TapGemm(a, tg.weights(fwd), [(0, 0, 0, 0, 0)], (T, 2, B), o, None, backend, name="mdx.stft")
 
 
+# fp16 storage of the U-Net's activations and GEMM weights (tcgen05 kind::f16, fp32 accumulate): the same 10-bit mantissa
+# as the TF32 path at half the shared-memory / L2 / HBM bytes per FLOP.  Only tensors that live inside the network's launch
+# plan change type; the spectrograms on either side stay fp32.
+MDX_FP16 = os.environ.get("B200VC_MDX_FP16", "0") == "1"
+
+
 class ConvTDFNetB200:
     """The TFC-TDF U-Net on device: stands where `ort.InferenceSession` stands in the reference (mdx.py:74-77)."""
 
     def __init__(self, sd: Dict[str, torch.Tensor], device, backend=tg.BACKEND_TC):
         self.device = torch.device(device)
         self.backend = backend
+        self.half = bool(MDX_FP16 and backend == tg.BACKEND_TC)
         meta = [int(v) for v in sd["_meta"]]
         (self.dim_f, self.dim_t, self.g, self.l, self.n, self.bn, self.k, self.dim_c) = meta
         self.W: Dict[str, torch.Tensor] = {}
@@ -120,6 +127,8 @@ class ConvTDFNetB200:
 
     def _dev(self, t, rnd=True):
         t = t.float().contiguous()
+        if rnd and self.half:
+            return t.half().to(self.device)          # GEMM weight in fp16 mode
         if rnd and self.backend == tg.BACKEND_TC:
             t = round_tf32(t)
         return t.to(self.device)
@@ -159,7 +168,7 @@ class ConvTDFNetB200:
         for i in range(self.n):
             self._conv_bn(sd, f"us.{i}.0", f"us.{i}.1", f"us{i}", tg.pack_convt2d, out_dim=1)
             self._tfc_tdf(sd, f"decoding_blocks.{i}", f"dec{i}")
-        self.W["final.w"] = self._dev(sd["final_conv.0.weight"].float()[:, :, 0, 0])   # [4, c]
+        self.W["final.w"] = self._dev(sd["final_conv.0.weight"].float()[:, :, 0, 0], False)   # [4, c] (row kernel: fp32)
         self.W["final.b"] = self._dev(sd["final_conv.0.bias"], False)
 
     def plan(self, B: int) -> "_NetPlan":
@@ -189,6 +198,7 @@ class _NetPlan:
         dev, W, be = net.device, net.W, net.backend
         R = be == tg.BACKEND_TC
         f32 = dict(device=dev, dtype=torch.float32)
+        act = dict(device=dev, dtype=torch.float16 if net.half else torch.float32)   # activations inside the plan
         T, F, g, l, n, bnf = net.dim_t, net.dim_f, net.g, net.l, net.n, net.bn
         self.B = B
         steps: List = []
@@ -196,7 +206,7 @@ class _NetPlan:
         self.spec_in = torch.empty(B, 2, T, 2 * F, **f32)
         self.spec_out = torch.empty(B, 2, T, 2 * F, **f32)
         max_elems = B * T * F * g
-        pool = [torch.empty(max_elems, **f32) for _ in range(3)]       # t1, t2, xt scratch shared by all levels
+        pool = [torch.empty(max_elems, **act) for _ in range(3)]       # t1, t2, xt scratch shared by all levels
 
         def buf(slot, *shape):
             nel = 1
@@ -228,7 +238,7 @@ class _NetPlan:
                 cur = dst
             t = cur
             rows, Kb = B * Hh * c, Ww // bnf
-            h = torch.empty(rows, Kb, **f32)
+            h = torch.empty(rows, Kb, **act)
             s1, b1 = rep(W[key + ".s1"], B * Hh), rep(W[key + ".b1"], B * Hh)
             s2, b2 = rep(W[key + ".s2"], B * Hh), rep(W[key + ".b2"], B * Hh)
             add(tg.linear(xt.view(rows, Ww), W[key + ".w1"], h,
@@ -245,29 +255,29 @@ class _NetPlan:
                            be, box=(bw, 128 // bw), name=f"{key}.tdf2"))
 
         # ---- first conv (1x1, 4 -> g) reading [B, ch, T, F, ri]: pointwise, write-bound -> its own row kernel
-        x = torch.empty(B, T, F, g, **f32)
+        x = torch.empty(B, T, F, g, **act)
         add(lambda x=x: ops.mdx_first_conv(self.spec_in, W["first.w4"], W["first.b"], x, R))
         Hh, Ww, c = T, F, g
         skips = []
         for i in range(n):
-            y = torch.empty(B, Hh, Ww, c, **f32)
+            y = torch.empty(B, Hh, Ww, c, **act)
             tfc_tdf(x, f"enc{i}", Hh, Ww, c, y)
             skips.append((y, Hh, Ww, c))
-            x = torch.empty(B, Hh // 2, Ww // 2, c + g, **f32)
+            x = torch.empty(B, Hh // 2, Ww // 2, c + g, **act)
             add(tg.conv2d_k2s2(y, W[f"ds{i}.w"], x, Epi(bias=W[f"ds{i}.b"], act_pre=tg.ACT_RELU, round_out=R), be, name=f"ds{i}"))
             Hh, Ww, c = Hh // 2, Ww // 2, c + g
-        y = torch.empty(B, Hh, Ww, c, **f32)
+        y = torch.empty(B, Hh, Ww, c, **act)
         tfc_tdf(x, "mid", Hh, Ww, c, y)
         x = y
         for i in range(n):
             sk, Hs, Ws, cs = skips[-1 - i]
-            u = torch.empty(B, Hs, Ws, cs, **f32)
+            u = torch.empty(B, Hs, Ws, cs, **act)
             for op in tg.conv_transpose2d_k2s2(x, W[f"us{i}.w"], u,
                                                Epi(bias=W[f"us{i}.b"], act_pre=tg.ACT_RELU, res=sk, res_mul=True, res_mapped=True, round_out=R),
                                                be, name=f"us{i}"):
                 add(op)
             Hh, Ww, c = Hs, Ws, cs
-            y = torch.empty(B, Hh, Ww, c, **f32)
+            y = torch.empty(B, Hh, Ww, c, **act)
             tfc_tdf(u, f"dec{i}", Hh, Ww, c, y)
             x = y
         # ---- final conv (1x1, g -> 4) writing [B, ch, T, F, ri]: pointwise, read-bound -> its own row kernel

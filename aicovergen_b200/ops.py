@@ -225,24 +225,24 @@ def mdx_gather_chunks(wave, src_start, lo, hi, out, chunk, half, sign, round_out
                                                    B, chunk, half, float(sign), int(round_out), _s()), "mdx_gather_chunks")
 
 
-_ffi.declare("b200vc_mdx_first_conv", [_P, _P, _P, _P, _i32, _i32, _i32, _i32, _i32, _P])
-_ffi.declare("b200vc_mdx_final_conv", [_P, _P, _P, _P, _i32, _i32, _i32, _i32, _i32, _P])
+_ffi.declare("b200vc_mdx_first_conv", [_P, _P, _P, _P, _i32, _i32, _i32, _i32, _i32, _i32, _P])
+_ffi.declare("b200vc_mdx_final_conv", [_P, _P, _P, _P, _i32, _i32, _i32, _i32, _i32, _i32, _P])
 
 
 def mdx_first_conv(spec, w4, bias, out, round_out=False):
     """spec [B,2,T,2F] (f, ri interleaved) -> out [B,T,F,g] = relu(W4 . (ch0re, ch0im, ch1re, ch1im) + bias)."""
     B, T, F, g = out.shape
     assert spec.shape == (B, 2, T, 2 * F) and spec.is_contiguous() and out.is_contiguous() and w4.shape == (g, 4)
-    _ffi.check(_ffi.lib().b200vc_mdx_first_conv(_p(_f32c(spec)), _p(w4), _p(bias), _p(out), B, T, F, g, int(round_out), _s()),
-               "mdx_first_conv")
+    _ffi.check(_ffi.lib().b200vc_mdx_first_conv(_p(_f32c(spec)), _p(w4), _p(bias), _p(out), B, T, F, g, int(round_out),
+                                                int(out.dtype == torch.float16), _s()), "mdx_first_conv")
 
 
 def mdx_final_conv(x, w, bias, spec, round_out=False):
     """x [B,T,F,c] -> spec [B,2,T,2F] = W[4,c] . x + bias (rows of W: ch0re, ch0im, ch1re, ch1im)."""
     B, T, F, c = x.shape
     assert spec.shape == (B, 2, T, 2 * F) and spec.is_contiguous() and x.is_contiguous() and w.shape == (4, c)
-    _ffi.check(_ffi.lib().b200vc_mdx_final_conv(_p(_f32c(x)), _p(w), _p(bias), _p(spec), B, T, F, c, int(round_out), _s()),
-               "mdx_final_conv")
+    _ffi.check(_ffi.lib().b200vc_mdx_final_conv(_p(x), _p(w), _p(bias), _p(spec), B, T, F, c, int(round_out),
+                                                int(x.dtype == torch.float16), _s()), "mdx_final_conv")
 
 
 def nhwc_to_nhcw(x, scale, out, round_out=False):

@@ -248,9 +248,9 @@ int b200vc_mdx_gather_chunks(const float* wave, int64_t n_song, const int64_t* s
  * first: spec[B][2][T][F][2] (ch, ri) -> out[B][T][F][g] = relu(W4[g][4] . (ch0re, ch0im, ch1re, ch1im) + bias)  (BN folded)
  * final: x[B][T][F][c] -> spec[B][2][T][F][2] = W[4][c] . x + bias                                                  */
 int b200vc_mdx_first_conv(const float* spec, const float* w4, const float* bias, float* out, int B, int T, int F, int g,
-                          int round_out, void* stream);
+                          int round_out, int out_half /* out holds fp16 */, void* stream);
 int b200vc_mdx_final_conv(const float* x, const float* w, const float* bias, float* spec, int B, int T, int F, int c,
-                          int round_out, void* stream);
+                          int round_out, int x_half /* x holds fp16 */, void* stream);
 
 /* x [R,W,C] -> out [R,C,W] * scale[c] and back with a fused residual add: the layout change around the
  * frequency-axis Linear layers (TDF) of the MDX-Net graph executed at mdx.py:77. */
