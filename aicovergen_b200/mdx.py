@@ -152,7 +152,14 @@ class ConvTDFNetB200:
         s1, b1 = self._bn(sd, f"{p}.tdf.1")
         s2, b2 = self._bn(sd, f"{p}.tdf.4")
         W = self.W
-        W[key + ".w1"], W[key + ".w2"] = self._dev(sd[f"{p}.tdf.0.weight"]), self._dev(sd[f"{p}.tdf.3.weight"])
+        w1, w2 = sd[f"{p}.tdf.0.weight"], sd[f"{p}.tdf.3.weight"]
+        W[key + ".w1"] = self._dev(w1)
+        # fp16 mode: the second TDF GEMM reads K = F/bn elements per row; TMA needs 16-byte row pitches, so when F/bn is not
+        # a multiple of 8 (the bottleneck block: 12) that one GEMM keeps fp32/TF32 operands (its input h is then fp32 too)
+        if self.half and w2.shape[1] % 8 != 0:
+            W[key + ".w2"] = round_tf32(w2.float().contiguous()).to(self.device)
+        else:
+            W[key + ".w2"] = self._dev(w2)
         W[key + ".s1"], W[key + ".b1"] = self._dev(s1, False), self._dev(b1, False)
         W[key + ".s2"], W[key + ".b2"] = self._dev(s2, False), self._dev(b2, False)
 
@@ -238,7 +245,7 @@ class _NetPlan:
                 cur = dst
             t = cur
             rows, Kb = B * Hh * c, Ww // bnf
-            h = torch.empty(rows, Kb, **act)
+            h = torch.empty(rows, Kb, device=dev, dtype=W[key + ".w2"].dtype)     # follows the operand type of the GEMM that reads it
             s1, b1 = rep(W[key + ".s1"], B * Hh), rep(W[key + ".b1"], B * Hh)
             s2, b2 = rep(W[key + ".s2"], B * Hh), rep(W[key + ".b2"], B * Hh)
             add(tg.linear(xt.view(rows, Ww), W[key + ".w1"], h,
