@@ -120,3 +120,26 @@ def test_first_and_final_conv_row_kernels():
     so = torch.empty(B, 2, T, 2 * Fq, device="cuda")
     ops.mdx_final_conv(out, wf.cuda(), bf.cuda(), so)
     assert (so.cpu() - ref_spec).abs().max() < 1e-4
+
+
+@pytest.mark.skipif(__import__("os").environ.get("B200VC_EXPERIMENTAL") != "1",
+                    reason="experimental fp16 activation storage (set B200VC_EXPERIMENTAL=1)")
+@pytest.mark.parametrize("cfg", [dict(dim_f=256, dim_t=32, g=8, n=3), dict(dim_f=3072, dim_t=256, g=48, n=5)])
+def test_convtdfnet_parity_fp16_storage(cfg, monkeypatch):
+    """The U-Net with fp16 activation / weight storage (tcgen05 kind::f16, fp32 accumulate): same tolerance as the TF32 path
+    (both carry 10 mantissa bits).  Opt-in until validated on a GPU."""
+    import aicovergen_b200.mdx as bm
+    from oracle import mdx as om
+
+    monkeypatch.setattr(bm, "MDX_FP16", True)
+    sd = make_mdx_state_dict(**cfg)
+    B = 2 if cfg["dim_f"] < 1000 else 1
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(B, 4, cfg["dim_f"], cfg["dim_t"], generator=g) * 3.0
+    ref = om.convtdfnet(sd, x)
+    net = bm.ConvTDFNetB200(sd, "cuda:0", tg.BACKEND_TC)
+    assert net.half
+    got = torch.from_numpy(net.run(None, {"input": x.numpy()})[0])
+    e = rel_rms(got, ref)
+    print(f"[mdx net fp16 storage {cfg['dim_f']}x{cfg['dim_t']}] rel rms err {e:.3e}")
+    assert torch.isfinite(got).all() and e < 8e-3
