@@ -331,3 +331,43 @@ def make_mdx_state_dict(dim_f: int = 3072, dim_t: int = 256, g: int = 48, l: int
     sd["final_conv.0.bias"] = gen.normal((dim_c,), 0.02)
     sd["_meta"] = torch.tensor([dim_f, dim_t, g, l, n, bn, k, dim_c])
     return sd
+
+
+def calibrate_mdx_batchnorm(sd: Dict[str, torch.Tensor], x: torch.Tensor, eps: float = 1e-5) -> Dict[str, torch.Tensor]:
+    """Gives a synthetic ConvTDFNet the activation statistics of a TRAINED one: one forward pass over `x`
+    ([B,4,dim_f,dim_t] spectrogram-like input) sets every BatchNorm's running_mean / running_var to the statistics of
+    its own input (what training converges to), so each normalised layer emits O(1) values and the multiplicative skips
+    stay bounded (the default synthetic checkpoints reach 1e5..1e10 at full size: harmless in fp32/TF32, beyond fp16).
+    Returns a NEW state dict; weights, affine parameters and `_meta` are untouched.  Plain torch on the CPU — a weight
+    generator for tests/bench, not part of the inference path."""
+    import torch.nn.functional as F
+
+    out = {k_: v.clone() for k_, v in sd.items()}
+    dim_f, dim_t, g, l, n, bnf, k, dim_c = [int(v) for v in sd["_meta"]]
+
+    def bn_fit(name, t):
+        mean = t.mean(dim=(0, 2, 3))
+        var = t.var(dim=(0, 2, 3), unbiased=False)
+        out[name + ".running_mean"], out[name + ".running_var"] = mean, var.clamp_min(1e-6)
+        return F.batch_norm(t, mean, var.clamp_min(1e-6), out[name + ".weight"], out[name + ".bias"], False, 0.0, eps)
+
+    def tfc_tdf(p, t):
+        for j in range(l):
+            t = F.relu(bn_fit(f"{p}.tfc.H.{j}.1", F.conv2d(t, out[f"{p}.tfc.H.{j}.0.weight"], out[f"{p}.tfc.H.{j}.0.bias"], padding=1)))
+        h = F.relu(bn_fit(f"{p}.tdf.1", F.linear(t, out[f"{p}.tdf.0.weight"])))
+        h = F.relu(bn_fit(f"{p}.tdf.4", F.linear(h, out[f"{p}.tdf.3.weight"])))
+        return t + h
+
+    with torch.no_grad():
+        t = F.relu(bn_fit("first_conv.1", F.conv2d(x.float(), out["first_conv.0.weight"], out["first_conv.0.bias"]))).transpose(-1, -2)
+        skips = []
+        for i in range(n):
+            t = tfc_tdf(f"encoding_blocks.{i}", t)
+            skips.append(t)
+            t = F.relu(bn_fit(f"ds.{i}.1", F.conv2d(t, out[f"ds.{i}.0.weight"], out[f"ds.{i}.0.bias"], stride=2)))
+        t = tfc_tdf("bottleneck_block", t)
+        for i in range(n):
+            t = F.relu(bn_fit(f"us.{i}.1", F.conv_transpose2d(t, out[f"us.{i}.0.weight"], out[f"us.{i}.0.bias"], stride=2)))
+            t = t * skips[-i - 1]
+            t = tfc_tdf(f"decoding_blocks.{i}", t)
+    return out

@@ -79,3 +79,24 @@ def test_full_size_fp16_plan_is_tma_addressable(geom, monkeypatch):
         if op.params.dtype & 1:
             assert op.tc_supported(), op.name
     assert all(name.endswith("tdf2") for name in fp32_ops) and len(fp32_ops) <= 3, fp32_ops
+
+
+def test_calibrated_batchnorm_keeps_stored_activations_in_fp16_range(monkeypatch):
+    """synthetic.calibrate_mdx_batchnorm gives a synthetic net the activation statistics of a trained one: outputs stay
+    O(1), the fp16-storage plan (emulated) then matches the oracle as closely as the TF32 path does."""
+    from aicovergen_b200.synthetic import calibrate_mdx_batchnorm
+
+    cfg = dict(dim_f=64, dim_t=16, g=8, l=2, n=2, bn=4)
+    g = torch.Generator().manual_seed(11)
+    sd = calibrate_mdx_batchnorm(make_mdx_state_dict(**cfg), torch.randn(2, 4, 64, 16, generator=g) * 30.0)
+    x = torch.randn(2, 4, 64, 16, generator=g) * 30.0                 # another draw of the same (large) scale
+    ref = om.convtdfnet(sd, x)
+    assert float(ref.abs().max()) < 50.0
+    monkeypatch.setattr(bm, "MDX_FP16", True)
+    net = bm.ConvTDFNetB200(sd, "cpu", tg.BACKEND_TC)
+    got, gemms = _run_plan_on_cpu(net, x, monkeypatch)
+    err = float((got - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt())
+    assert torch.isfinite(got).all() and err < 8e-3, err
+    for op in gemms:                                                  # every stored fp16 tensor stayed finite and small
+        if op.params.dtype & 2:
+            assert float(op.out.t.float().abs().max()) < 1e3, op.name

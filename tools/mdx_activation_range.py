@@ -20,6 +20,7 @@ ap.add_argument("--g", type=int, default=48)
 ap.add_argument("--n-fft", type=int, default=7680)
 ap.add_argument("--scale", type=float, default=3.0, help="std of the random spectrogram (tests use 3.0)")
 ap.add_argument("--real-stft", action="store_true", help="feed the STFT of a full-scale synthetic song chunk instead of noise")
+ap.add_argument("--calibrate", action="store_true", help="fit the BatchNorm statistics first (synthetic.calibrate_mdx_batchnorm)")
 args = ap.parse_args()
 
 sd = make_mdx_state_dict(dim_f=args.dim_f, dim_t=args.dim_t, g=args.g)
@@ -33,6 +34,15 @@ if args.real_stft:
     x = mp.stft(song[None, :, 44100:44100 + mp.chunk_size])
 else:
     x = torch.randn(1, 4, dim_f, dim_t, generator=torch.Generator().manual_seed(1)) * args.scale
+if args.calibrate:
+    from aicovergen_b200.synthetic import calibrate_mdx_batchnorm
+    if args.real_stft:   # calibrate on a chunk of a DIFFERENT synthetic song (seed 1), evaluate on seed 0
+        other = torch.from_numpy(bench.synth_song(30.0, 1))
+        other = other / other.abs().max()
+        calib_in = mp.stft(other[None, :, 2 * 44100:2 * 44100 + mp.chunk_size])
+    else:                # a different noise draw of the same scale
+        calib_in = torch.randn(1, 4, dim_f, dim_t, generator=torch.Generator().manual_seed(7)) * float(x.std())
+    sd = calibrate_mdx_batchnorm(sd, calib_in)
 rec = {}
 
 
