@@ -279,7 +279,7 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..17) =====================
     const int q = warp & 3;
     const int cpar = (warp - 2) >> 2;              // this warp takes the 32-column groups with index % 4 == cpar
     int it = 0;

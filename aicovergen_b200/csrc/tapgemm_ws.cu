@@ -315,7 +315,7 @@ tapgemm_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..17) =====================
     const int q = warp & 3;                         // TMEM lane quarter this warp may read
     const int n = ((warp - 2) >> 2) * 16;           // its 16-column group
     if (n < p.N) {
