@@ -111,6 +111,20 @@ def build_engine(device: str, rank_seed: int = 0):
                                            make_rmvpe_state_dict, make_rvc_checkpoint)
 
     mdx_w = [make_mdx_state_dict(dim_f=s["dim_f"], dim_t=s["dim_t"], seed=2024 + i) for i, s in enumerate(MDX_STAGES)]
+    if os.environ.get("B200VC_MDX_CALIBRATED") == "1":
+        # opt-in (round 2): BatchNorm statistics fitted on the spectrogram of a seeded song chunk, as training would leave
+        # them, so the fp16-storage mode of the U-Net (B200VC_MDX_FP16=1) stays inside fp16's range
+        from aicovergen_b200.synthetic import calibrate_mdx_batchnorm
+        cal_song = torch.from_numpy(synth_song(12.0, 4242))
+        cal_song = cal_song / cal_song.abs().max()
+        for i, st in enumerate(MDX_STAGES):
+            hop = 1024
+            chunk = hop * (st["dim_t"] - 1)
+            seg = cal_song[:, 44100:44100 + chunk]
+            z = torch.stft(seg, n_fft=st["n_fft"], hop_length=hop, window=torch.hann_window(st["n_fft"]), center=True,
+                           return_complex=True)
+            z = torch.view_as_real(z).permute(0, 3, 1, 2)[:, :, :st["dim_f"]]                    # [ch, ri, F, T]
+            mdx_w[i] = calibrate_mdx_batchnorm(mdx_w[i], z.reshape(1, 4, st["dim_f"], st["dim_t"]))
     hsd, rsd, cpt = make_hubert_state_dict(), make_rmvpe_state_dict(), make_rvc_checkpoint("40k", "v2")
     eng = CoverEngine(mdx_w, hsd, rsd, cpt, index=None, device=device)
     # IVF index (README's IVF2237 example: 87 243 x 768) from HuBERT features of a seeded clip
