@@ -1,6 +1,7 @@
 // Coalesced fp32 row/elementwise kernels around the tap-GEMMs: normalisation, softmax
 // (+ VITS relative-position terms), gates, gathers, NSF sine source, conv_post.
 // All HBM-bound; one pass over the data each, float4 where rows allow.
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "../../include/b200vc.h"
 
@@ -271,9 +272,15 @@ __global__ void conv1d_from1_kernel(const float* __restrict__ src, long long n_s
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       v[i] = apply_act(v[i], act2, act2_p);
-      if (round_out2) v[i] = round_tf32(v[i]);
+      if (round_out2 & 1) v[i] = round_tf32(v[i]);
     }
-    *reinterpret_cast<float4*>(out2 + o) = make_float4(v[0], v[1], v[2], v[3]);
+    if (round_out2 & 2) {      // bit1: out2 holds fp16 (4 channels = one 8-byte store)
+      const __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(out2) + o) =
+          make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+    } else {
+      *reinterpret_cast<float4*>(out2 + o) = make_float4(v[0], v[1], v[2], v[3]);
+    }
   }
 }
 
@@ -310,7 +317,8 @@ __global__ void act_kernel(const float* __restrict__ x, float* __restrict__ out,
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n) return;
   const float v = apply_act(x[e], act, p);
-  out[e] = round_out ? round_tf32(v) : v;
+  if (round_out & 2) reinterpret_cast<__half*>(out)[e] = __float2half_rn(v);      // bit1: `out` holds fp16
+  else out[e] = (round_out & 1) ? round_tf32(v) : v;
 }
 
 

@@ -111,7 +111,8 @@ def axpby(a, b, out, alpha=1.0, beta=1.0):
 
 def act(x, out, code, p=0.0, round_out=False):
     assert x.is_contiguous() and out.is_contiguous()
-    _ffi.check(_ffi.lib().b200vc_act(_p(_f32c(x)), _p(out), x.numel(), code, p, int(round_out), _s()), "act")
+    flags = 2 if out.dtype == torch.float16 else int(round_out)          # bit1: `out` holds fp16
+    _ffi.check(_ffi.lib().b200vc_act(_p(_f32c(x)), _p(out), x.numel(), code, p, flags, _s()), "act")
 
 
 def nsf_source(f0, noise, har, scratch, upp, sr, lin_w, lin_b):
@@ -132,7 +133,8 @@ def conv1d_from1(src, w, out, stride, src_off, bias=None, res=None, out2=None, a
     assert res is None or (res.shape == out.shape and res.is_contiguous())
     assert out2 is None or (out2.shape == out.shape and out2.is_contiguous())
     _ffi.check(_ffi.lib().b200vc_conv1d_from1(_p(_f32c(src)), src.numel(), _p(w), _p(bias), _p(res), _p(out), _p(out2), T, Cc,
-                                              w.shape[1], int(stride), int(src_off), int(act2), float(act2_p), int(round_out2), _s()),
+                                              w.shape[1], int(stride), int(src_off), int(act2), float(act2_p),
+                                              2 if (out2 is not None and out2.dtype == torch.float16) else int(round_out2), _s()),
                "conv1d_from1")
 
 

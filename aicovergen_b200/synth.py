@@ -39,6 +39,11 @@ def round_tf32(t: torch.Tensor) -> torch.Tensor:
     return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
 
 
+# opt-in (round 2): fp16 storage of the vocoder's GEMM-only tensors (the leaky-ReLU copies and the ResBlock mid tensor) and of
+# the ResBlock weights — tcgen05 kind::f16, fp32 accumulate, the residual streams stay fp32.  Validated at the GEMM level only.
+SYNTH_FP16 = __import__("os").environ.get("B200VC_SYNTH_FP16", "0") == "1"
+
+
 class SynthesizerB200:
     def __init__(self, cpt: dict, device="cuda:0", backend: int = tg.BACKEND_TC):
         cfg = cpt["config"]
@@ -54,6 +59,7 @@ class SynthesizerB200:
         self.version = cpt.get("version", "v1")
         self.device = torch.device(device)
         self.backend = backend
+        self.half_rb = bool(SYNTH_FP16 and backend == tg.BACKEND_TC)
         self.window = 10
         self._plans = PlanCache()
         self._cond_cache: Dict[int, dict] = {}
@@ -138,7 +144,8 @@ class SynthesizerB200:
                 for m in range(len(self.rb_d[j])):
                     for c in (1, 2):
                         q = f"dec.resblocks.{n}.convs{c}.{m}"
-                        W[f"rb{n}.c{c}.{m}.w"] = self._dev(tg.pack_conv1d(fold_weight_norm(sd, q)))
+                        wq = tg.pack_conv1d(fold_weight_norm(sd, q))
+                        W[f"rb{n}.c{c}.{m}.w"] = wq.float().contiguous().half().to(self.device) if self.half_rb else self._dev(wq)
                         W[f"rb{n}.c{c}.{m}.b"] = self._dev(sd[q + ".bias"], False)
         W["post.w"] = self._dev(sd["dec.conv_post.weight"][0].t().contiguous(), False)   # [k, C]
         W["emb_g"] = self._dev(sd["emb_g.weight"], False)
@@ -298,11 +305,12 @@ class _Plan:
             add(lambda: ops.nsf_source(self.f0, self.noise_src, har, self.cum, m.upp, m.sr, m.lin_w, m.lin_b))
         max_elems = max(Ts[i + 1] * Cs[i] for i in range(nst))
         pool = [torch.empty(max_elems, **f32) for _ in range(9)]
+        hpool = {s_: torch.empty(max_elems, device=dev, dtype=torch.float16) for s_ in (1, 2, 4, 5)} if m.half_rb else {}
         prev = xl0
         nk = len(m.rb_k)
         for i in range(nst):
             T, Cc = Ts[i + 1], Cs[i]
-            bufs = [pool[s][:T * Cc].view(T, Cc) for s in range(9)]
+            bufs = [(hpool[s] if s in hpool else pool[s])[:T * Cc].view(T, Cc) for s in range(9)]   # slots 1,2,4,5 = xsl, tb, xal, xbl
             sum_slot = 7 if i % 2 == 0 else 8
             xb_slot = 8 if i % 2 == 0 else 7     # the other parity slot is free inside this stage
             xs, xsl, tb, xa, xal, xbl = bufs[0], bufs[1], bufs[2], bufs[3], bufs[4], bufs[5]

@@ -174,7 +174,7 @@ int b200vc_nsf_source(const float* f0, const float* noise, float* har, double* s
 
 /* Strided Conv1d from ONE input channel as a write-bound row kernel:
  *   out[t,c] = res[t,c] + bias[c] + sum_j w[c,j] * src[src_off + t*stride + j]   (zero outside [0,n_src)); out2 = act2(out)
- * res, bias, out2 may be NULL; res may alias out.  Replaces Conv1d(1, C, k, stride) at infer_pack/models.py:477-486,505-506
+ * res, bias, out2 may be NULL; res may alias out.  round_out2: bit0 = round out2 to TF32, bit1 = out2 holds IEEE fp16.  Replaces Conv1d(1, C, k, stride) at infer_pack/models.py:477-486,505-506
  * (NSF noise_convs) and HuBERT's first feature-extractor convolution. */
 int b200vc_conv1d_from1(const float* src, int64_t n_src, const float* w, const float* bias, const float* res, float* out,
                         float* out2, int64_t T, int C, int K, int stride, int64_t src_off, int act2, float act2_p,

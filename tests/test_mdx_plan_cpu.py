@@ -100,3 +100,23 @@ def test_calibrated_batchnorm_keeps_stored_activations_in_fp16_range(monkeypatch
     for op in gemms:                                                  # every stored fp16 tensor stayed finite and small
         if op.params.dtype & 2:
             assert float(op.out.t.float().abs().max()) < 1e3, op.name
+
+
+def test_vocoder_fp16_resblock_plan_is_tma_addressable(monkeypatch):
+    """Opt-in fp16 storage of the vocoder's GEMM-only tensors (B200VC_SYNTH_FP16): descriptors only — every ResBlock
+    convolution carries fp16 operands, the right mix of fp16 / fp32 outputs, and satisfies the TMA alignment rules."""
+    import aicovergen_b200.synth as bs
+    from aicovergen_b200.synthetic import make_rvc_checkpoint
+
+    monkeypatch.setattr(bs, "SYNTH_FP16", True)
+    m = bs.SynthesizerB200(make_rvc_checkpoint("40k", "v2"), "cpu")
+    assert m.half_rb
+    pl = bs._Plan(m, 157)
+    gemms = [st for st in pl.steps if isinstance(st, tg.TapGemm)]
+    half = [op for op in gemms if op.params.dtype & 1]
+    assert len(half) == 72 and all(op.name.startswith("rb") for op in half)      # 4 stages x 3 blocks x 3 dilations x 2 convs
+    assert all(op.tc_supported() for op in half)
+    assert {op.params.dtype for op in half} == {1, 3, 5}    # out fp32 / out fp16 (mid tensor) / out fp32 + fp16 activated copy
+    monkeypatch.setattr(bs, "SYNTH_FP16", False)
+    m32 = bs.SynthesizerB200(make_rvc_checkpoint("40k", "v2"), "cpu")
+    assert not any(st.params.dtype for st in bs._Plan(m32, 157).steps if isinstance(st, tg.TapGemm))

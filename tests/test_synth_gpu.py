@@ -78,3 +78,27 @@ def test_conv1d_from1_row_kernel(C, K, stride, pad):
     want = ref + res
     assert (out.cpu() - want).abs().max() < 1e-4
     assert (out2.cpu() - F.leaky_relu(want, 0.1)).abs().max() < 1e-4
+
+
+@pytest.mark.skipif(__import__("os").environ.get("B200VC_EXPERIMENTAL") != "1",
+                    reason="experimental fp16 storage of the vocoder's GEMM-only tensors (set B200VC_EXPERIMENTAL=1)")
+def test_synth_infer_parity_fp16_resblocks(monkeypatch):
+    """Same parity bar as the TF32 path (waveform abs RMS <= 1e-3) with the ResBlock operands stored in fp16."""
+    import aicovergen_b200.synth as bs
+    from oracle import synth as osynth
+
+    monkeypatch.setattr(bs, "SYNTH_FP16", True)
+    P = 157
+    cpt = make_rvc_checkpoint("40k", "v2", seed=1234)
+    phone, pitch, pitchf = _inputs(P, P)
+    sid = torch.tensor([0])
+    nz, ns = osynth.draw_noise(7, P, 192, 400)
+    ref = osynth.infer(cpt, phone, pitch, pitchf, sid, nz, ns)
+    net = bs.SynthesizerB200(cpt, "cuda:0")
+    assert net.half_rb
+    o = net.infer(phone.cuda(), torch.tensor([P]).cuda(), pitch.cuda(), pitchf.cuda(), sid.cuda(),
+                  noise_z=nz.cuda(), noise_src=ns.cuda())[0]
+    torch.cuda.synchronize()
+    e_abs = rms(o.cpu() - ref)
+    print(f"[synth fp16 resblocks P={P}] waveform: abs rms err {e_abs:.3e} (ref rms {rms(ref):.3e})")
+    assert torch.isfinite(o).all() and e_abs < 1e-3, e_abs
