@@ -52,3 +52,21 @@ def test_sass_contains_blackwell_tensor_and_tma_instructions():
     sass = subprocess.run([cuobjdump, "-sass", str(obj)], capture_output=True, text=True).stdout
     for mnem in ("UTCHMMA", "UTMALDG", "LDTM"):
         assert mnem in sass, mnem
+
+
+def test_committed_bench_line_carries_the_contract_keys():
+    """The last bench line committed under profiles/ has every key the driver's contract names (bench.py docstring)."""
+    import json
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    b = json.load(open(os.path.join(root, "profiles", "r01_bench_final.json")))
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert k in b, k
+    assert b["config"]["workload"] and b["gpu_launches"] > 0 and b["higher_is_better"] is True and b["scaling"] == "weak"
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(b["e2e"]) and b["e2e"]["h2d_bytes_per_step"] > 0
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(b["roofline"]) and b["roofline"]["bound"] in ("hbm", "tensor")
+    assert {"value", "unit", "cores", "kind", "sample"} <= set(b["cpu_baseline"]) and b["cpu_baseline"]["kind"] in ("port", "reference")
+    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(b["clocks"])
+    assert not set(b["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
