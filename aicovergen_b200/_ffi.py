@@ -152,5 +152,23 @@ def check(rc: int, what: str = "b200vc"):
         raise RuntimeError(f"{what} failed (rc={rc}): {msg}")
 
 
+def on_device(fn):
+    """Decorator for the public methods of the operator objects: run with the object's own CUDA device current.
+    Every C-ABI launch goes to `torch.cuda.current_stream()` of the CURRENT device and the kernels / TMA descriptors are
+    created on the current device, so an operator built for cuda:k must not run while cuda:0 is current."""
+    import functools
+
+    import torch
+
+    @functools.wraps(fn)
+    def wrapper(self, *a, **k):
+        dev = torch.device(self.device)
+        if dev.type != "cuda" or dev.index is None or dev.index == torch.cuda.current_device():
+            return fn(self, *a, **k)
+        with torch.cuda.device(dev):
+            return fn(self, *a, **k)
+    return wrapper
+
+
 def launch_count() -> int:
     return int(lib().b200vc_launch_count())

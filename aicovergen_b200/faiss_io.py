@@ -8,12 +8,13 @@ Layout restated from the published faiss serialisation (faiss/impl/index_write.c
     u64 nlist | u64 nprobe
     quantiser    : u32 "IxF2"/"IxFI"/"IxFl" | index header | u64 n_floats | f32[n_floats]      (nlist x d centroids)
     direct map   : u8 type | u64 n | i64[n]  (| u64 n_pairs | (i64,i64)[n_pairs] when type == 2, hashtable)
-    u64 code_size (= 4 d)
+    (NO code_size field here: "IwFl" is fourcc + ivf header + inverted lists, the reader derives code_size = 4 d;
+     only the quantising IVF types - IwSq, IwPQ ... - and the legacy "IvFl" layout carry one)
     inverted lists: u32 "ilar" | u64 nlist | u64 code_size | u32 "full" | u64 nlist | u64 sizes[nlist]
                                                           (or u32 "sprs" | u64 2k | (u64 list, u64 size)[k])
                     then per non-empty list: codes u8[size*code_size] | ids i64[size]
-`parity unpinned`: no faiss build and no index file exist in this environment; the writer below produces the same
-layout so that the reader is exercised by a round trip (tests/test_formats_cpu.py).
+`parity unpinned`: no faiss build and no index file exist in this environment; tests/test_formats_cpu.py parses a
+byte string assembled field by field from the layout above (independently of the writer below) besides the round trip.
 """
 from __future__ import annotations
 
@@ -98,15 +99,13 @@ def read_ivfflat(path: str) -> IvfFlatData:
         if dm_type == 2:
             npairs = _rd(f, "Q")
             _read_array(f, "<i8", 2 * npairs)
-        code_size = _rd(f, "Q")
-        if code_size != 4 * d:
-            raise FaissFormatError(f"{path}: code_size {code_size} != 4*d")
+        code_size = 4 * d                      # IndexIVFFlat: not stored, ivfl->code_size = d * sizeof(float)
         il = _fourcc(f)
         if il != "ilar":
             raise FaissFormatError(f"{path}: inverted lists {il!r} are not ArrayInvertedLists ('ilar')")
         il_nlist, il_cs = _rd(f, "Q"), _rd(f, "Q")
         if il_nlist != nlist or il_cs != code_size:
-            raise FaissFormatError(f"{path}: inverted-list header mismatch")
+            raise FaissFormatError(f"{path}: inverted-list header mismatch (nlist {il_nlist} vs {nlist}, code_size {il_cs} vs 4*d = {code_size})")
         kind = _fourcc(f)
         sizes = np.zeros(nlist, dtype=np.int64)
         if kind == "full":
@@ -169,7 +168,6 @@ def write_ivfflat(path: str, centroids: np.ndarray, vectors: np.ndarray, list_of
         f.write(struct.pack("<Q", nlist * d))
         f.write(centroids.tobytes())
         f.write(struct.pack("<BQ", 0, 0))                       # no direct map
-        f.write(struct.pack("<Q", 4 * d))
         f.write(b"ilar")
         f.write(struct.pack("<QQ", nlist, 4 * d))
         if int((sizes > 0).sum()) > nlist // 2:

@@ -13,7 +13,7 @@ from typing import Dict, List, Optional
 
 import torch
 
-from . import ops
+from . import _ffi, ops
 from . import tapgemm as tg
 from .plans import PlanCache
 from .synth import round_tf32
@@ -76,6 +76,7 @@ class HubertB200:
         self.W = W
 
     # ------------------------------------------------------------------ plug point
+    @_ffi.on_device
     @torch.no_grad()
     def extract_features(self, source: torch.Tensor, padding_mask: Optional[torch.Tensor] = None,
                          mask: bool = False, output_layer: Optional[int] = None):
@@ -90,6 +91,7 @@ class HubertB200:
         plan = self._plans.get_or_build(key, lambda: _HubertPlan(self, L, nl))
         return plan.run(source), padding_mask
 
+    @_ffi.on_device
     @torch.no_grad()
     def final_proj(self, x: torch.Tensor) -> torch.Tensor:
         """Linear 768 -> 256 used by v1 voice models (vc_infer_pipeline.py:406)."""

@@ -12,7 +12,7 @@ from typing import Optional, Tuple
 import numpy as np
 import torch
 
-from . import ops
+from . import _ffi, ops
 from . import tapgemm as tg
 from .tapgemm import Epi
 
@@ -22,6 +22,10 @@ class IvfIndexB200:
         """centroids [nlist, d], vectors [ntotal, d] in insertion (id) order.  `list_of` [ntotal]: the inverted list of
         every vector as stored in an index file; when absent vectors go to their nearest centroid (what faiss' add does)."""
         self.device = torch.device(device)
+        with torch.cuda.device(self.device):      # the list assignment below launches kernels (see _ffi.on_device)
+            self._build(centroids, vectors, list_of)
+
+    def _build(self, centroids, vectors, list_of):
         cent = torch.from_numpy(np.ascontiguousarray(centroids, dtype=np.float32))
         vecs = torch.from_numpy(np.ascontiguousarray(vectors, dtype=np.float32))
         self.ntotal, self.d = int(vecs.shape[0]), int(vecs.shape[1])
@@ -45,6 +49,7 @@ class IvfIndexB200:
     def reconstruct_n(self, i0: int, n: int) -> np.ndarray:
         return self._host_vectors[i0:i0 + n].copy()
 
+    @_ffi.on_device
     def search(self, x: np.ndarray, k: int = 8) -> Tuple[np.ndarray, np.ndarray]:
         """(squared-L2 [T,k], ids [T,k]); only k=8 is on the RVC path."""
         if k != 8:
@@ -72,6 +77,7 @@ class IvfIndexB200:
         assign = self._coarse(q)
         ops.ivf_scan_blend(q, assign, self.offsets, self.ids, self.vecs_sorted, out, rate, D, I)
 
+    @_ffi.on_device
     @torch.no_grad()
     def search_blend(self, feats: torch.Tensor, index_rate: float) -> torch.Tensor:
         """feats [T, d] (device, fp32) -> index_rate * weighted-NN reconstruction + (1-index_rate) * feats."""

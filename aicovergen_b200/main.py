@@ -25,7 +25,7 @@ import numpy as np
 import torch
 from scipy.io import wavfile
 
-from . import ops
+from . import _ffi, ops
 from .mdx import MDX, MDXModel, run_mdx, run_mdx_arrays, run_mdx_device, _read_wav_44k, _write_wav_pcm16
 from .rvc import Config, get_vc, load_hubert, rvc_infer
 
@@ -41,6 +41,9 @@ MDX_STAGES = (
     dict(name="UVR_MDXNET_KARA_2", dim_f=2048, dim_t=256, n_fft=5120, stem="Instrumental", compensate=1.035),
     dict(name="Reverb_HQ_By_FoxJoy", dim_f=3072, dim_t=512, n_fft=6144, stem="Other", compensate=1.035),
 )
+
+
+SUPPORTED_F0_METHODS = ("rmvpe",)
 
 
 def db_gain(db: float) -> float:
@@ -71,6 +74,7 @@ class CoverEngine:
         self.vc.model_rmvpe = RMVPEB200(rmvpe_sd, device=device)
         self.index_path = index or ""
 
+    @_ffi.on_device
     @torch.no_grad()
     def separate(self, song_dev: torch.Tensor) -> Dict[str, torch.Tensor]:
         """The three MDX passes of preprocess_song on a device tensor [2,N] float32 @44.1k -> stems (device tensors)."""
@@ -79,37 +83,47 @@ class CoverEngine:
         _, dereverb = run_mdx_device(self.mdx[2], main_vocals, denoise=True)
         return dict(vocals=vocals, instrumental=instrumental, backup=backup, main=main_vocals, dereverb=dereverb)
 
+    @_ffi.on_device
     @torch.no_grad()
     def convert(self, vocals_44k: torch.Tensor, pitch_change=0, index_rate=0.5, filter_radius=3, rms_mix_rate=0.25,
-                protect=0.33, f0_method="rmvpe") -> np.ndarray:
-        """load_audio (mono 16 kHz, on device) + VC.pipeline. Returns int16 @ tgt_sr (host, like the reference)."""
+                protect=0.33, f0_method="rmvpe", crepe_hop_length=128, return_device=False):
+        """load_audio (mono 16 kHz, on device) + VC.pipeline. Returns int16 @ tgt_sr: a host array like the reference, or
+        (return_device=True) the same samples as a device tensor, without the D2H."""
         n16 = int(vocals_44k.shape[1] * 16000 // 44100)
         mono = torch.empty(n16, device=self.device)
         ops.resample_sinc_mono(vocals_44k.contiguous(), mono, 44100, 16000)
         times = [0, 0, 0]
-        return self.vc.pipeline(self.hubert, self.net_g, 0, mono, "array", times, pitch_change, f0_method, self.index_path,
-                                index_rate, self.cpt.get("f0", 1), filter_radius, self.tgt_sr, 0, rms_mix_rate,
-                                self.cpt.get("version", "v1"), protect, 128)
+        self.vc.return_device = bool(return_device)
+        try:
+            return self.vc.pipeline(self.hubert, self.net_g, 0, mono, "array", times, pitch_change, f0_method, self.index_path,
+                                    index_rate, self.cpt.get("f0", 1), filter_radius, self.tgt_sr, 0, rms_mix_rate,
+                                    self.cpt.get("version", "v1"), protect, crepe_hop_length)
+        finally:
+            self.vc.return_device = False
 
+    @_ffi.on_device
     @torch.no_grad()
-    def mix(self, ai_vocals_i16: np.ndarray, backup: torch.Tensor, instrumental: torch.Tensor, main_gain=0, backup_gain=0,
+    def mix(self, ai_vocals_i16, backup: torch.Tensor, instrumental: torch.Tensor, main_gain=0, backup_gain=0,
             inst_gain=0) -> torch.Tensor:
-        dev_i16 = getattr(self.vc, "last_output_device", None)
-        if dev_i16 is not None and dev_i16.numel() == ai_vocals_i16.size and dev_i16.device == torch.device(self.device):
-            a = dev_i16.float() / 32768.0       # the utterance VC.pipeline just produced is still in HBM: no H2D
+        """ai_vocals_i16: the int16 utterance at tgt_sr, host array or device tensor (exactly what the caller passes is
+        mixed; nothing is substituted)."""
+        if isinstance(ai_vocals_i16, torch.Tensor):
+            a = ai_vocals_i16.to(self.device).float() / 32768.0
         else:
-            a = torch.from_numpy(ai_vocals_i16.astype(np.float32) / 32768.0).to(self.device)
+            a = torch.from_numpy(np.asarray(ai_vocals_i16).astype(np.float32) / 32768.0).to(self.device)
         out = torch.empty_like(backup)
         ops.mix3(a, self.tgt_sr, backup.contiguous(), instrumental.contiguous(), out, 44100, db_gain(-4 + main_gain),
                  db_gain(-6 + backup_gain), db_gain(-7 + inst_gain))
         return out
 
-    def cover_device(self, song_dev: torch.Tensor, **kw) -> torch.Tensor:
-        """song already in HBM -> cover in HBM."""
+    @_ffi.on_device
+    def cover_device(self, song_dev: torch.Tensor, main_gain=0, backup_gain=0, inst_gain=0, **convert_kw) -> torch.Tensor:
+        """song already in HBM -> cover in HBM (the converted utterance is handed to the mix as a device tensor)."""
         stems = self.separate(song_dev)
-        ai = self.convert(stems["dereverb"], **kw)
-        return self.mix(ai, stems["backup"], stems["instrumental"])
+        ai = self.convert(stems["dereverb"], return_device=True, **convert_kw)
+        return self.mix(ai, stems["backup"], stems["instrumental"], main_gain, backup_gain, inst_gain)
 
+    @_ffi.on_device
     def cover(self, song: np.ndarray, **kw) -> np.ndarray:
         """Host array in, host array out (H2D of the song and D2H of the cover included)."""
         dev = torch.from_numpy(np.ascontiguousarray(song, dtype=np.float32)).to(self.device, non_blocking=True)
@@ -248,11 +262,16 @@ def song_cover_pipeline(song_input, voice_model, pitch_change, keep_files, is_we
     try:
         if not song_input or not voice_model:
             raise_exception("Ensure that the song input field and voice model field is filled.", is_webui)
+        # options this build does not implement are refused BEFORE any separation / conversion work is done
+        if str(song_input).startswith("https://") or str(song_input).startswith("http://"):
+            raise_exception("YouTube input is out of scope for the B200 build; pass a local file.", is_webui)
+        if pitch_change_all != 0:
+            raise_exception("pitch_change_all needs sox (out of scope for the B200 build).", is_webui)
+        if f0_method not in SUPPORTED_F0_METHODS:
+            raise_exception(f"f0_method {f0_method!r}: the B200 build runs {SUPPORTED_F0_METHODS}.", is_webui)
         display_progress("[~] Starting AI Cover Generation Pipeline...", 0, is_webui, progress)
         with open(os.path.join(mdxnet_models_dir, "model_data.json")) as infile:
             mdx_model_params = json.load(infile)
-        if str(song_input).startswith("https://"):
-            raise_exception("YouTube input is out of scope for the B200 build; pass a local file.", is_webui)
         input_type = "local"
         song_input = song_input.strip('"')
         if not os.path.exists(song_input):
@@ -283,8 +302,6 @@ def song_cover_pipeline(song_input, voice_model, pitch_change, keep_files, is_we
                          filter_radius, rms_mix_rate, protect, crepe_hop_length, is_webui)
         display_progress("[~] Applying audio effects to Vocals...", 0.8, is_webui, progress)
         ai_vocals_mixed_path = add_audio_effects(ai_vocals_path, reverb_rm_size, reverb_wet, reverb_dry, reverb_damping)
-        if pitch_change_all != 0:
-            raise_exception("pitch_change_all needs sox (out of scope for the B200 build).", is_webui)
         display_progress("[~] Combining AI Vocals and Instrumentals...", 0.9, is_webui, progress)
         combine_audio([ai_vocals_mixed_path, backup_vocals_path, instrumentals_path], ai_cover_path, main_gain, backup_gain,
                       inst_gain, output_format)

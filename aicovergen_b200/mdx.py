@@ -24,7 +24,7 @@ import numpy as np
 import torch
 from scipy.io import wavfile
 
-from . import ops
+from . import _ffi, ops
 from . import tapgemm as tg
 from .synth import round_tf32
 from .tapgemm import Epi
@@ -68,6 +68,7 @@ class MDXModel:
             self._dft[rnd] = (conv(fwd).to(self.device), conv(inv).to(self.device), env.float().to(self.device))
         return self._dft[rnd]
 
+    @_ffi.on_device
     def stft(self, x: torch.Tensor) -> torch.Tensor:
         """[B,2,chunk] -> [B,4,dim_f,dim_t] (L.re, L.im, R.re, R.im) like mdx.py:37-43 (API path, not the hot path)."""
         B = x.reshape(-1, 2, self.chunk_size).shape[0]
@@ -82,6 +83,7 @@ class MDXModel:
         s = spec2.view(B, 2, self.dim_t, self.dim_f, 2).permute(0, 1, 4, 3, 2)       # [B, ch, ri, F, T]
         return s.reshape(B, 4, self.dim_f, self.dim_t).contiguous()
 
+    @_ffi.on_device
     def istft(self, x: torch.Tensor, freq_pad=None) -> torch.Tensor:
         """[B,4,dim_f,dim_t] -> [B,2,chunk] like mdx.py:45-54 (API path)."""
         B = x.shape[0]
@@ -181,12 +183,16 @@ class ConvTDFNetB200:
     def plan(self, B: int) -> "_NetPlan":
         pl = self._plans.get(B)
         if pl is None:
-            self._plans.clear()
+            # a batch plan is large (~20 GB at B=11): keep the newest one, plus the B == 1 plan of the ort.run API path
+            if B != 1:
+                for k in [k for k in self._plans if k != 1]:
+                    del self._plans[k]
             pl = _NetPlan(self, B)
             self._plans[B] = pl
         return pl
 
     # onnxruntime-compatible call (host arrays; API path used by MDX.process): input [B,4,dim_f,dim_t]
+    @_ffi.on_device
     def run(self, _outputs, feed):
         x = torch.from_numpy(np.ascontiguousarray(feed["input"], dtype=np.float32)).to(self.device)
         B = x.shape[0]
@@ -398,6 +404,7 @@ class MDX:
         m = self.model
         return chunk_descriptors(n, m.n_fft, m.chunk_size, mt_threads, self.DEFAULT_MARGIN_SIZE)
 
+    @_ffi.on_device
     def _process_device(self, wave_dev: torch.Tensor, out_dev: torch.Tensor, sign: float, coef: float, accumulate: bool,
                         mt_threads: int, shard=(0, 1)):
         """Run this rank's share of the chunks of `sign * wave` through STFT -> net -> iSTFT and add coef * result into
@@ -415,13 +422,13 @@ class MDX:
         R = self.backend == tg.BACKEND_TC
         fwd, inv, env = m.dft(R)
         pl = self.ort.plan(B)
-        if self._io is None or self._io[0] != B:
+        if self._io is None or self._io[0] is not pl:      # keyed on the plan itself: a rebuilt plan owns new spec buffers
             half = m.n_fft // 2
             padded = torch.empty(B, 2, m.chunk_size + m.n_fft, device=dev)
             frames = torch.empty(B, 2, m.dim_t, m.n_fft, device=dev)
             stft = _stft_gemm(padded, fwd, pl.spec_in, m, self.backend)
             istft = tg.linear(pl.spec_out.view(-1, 2 * m.dim_f), inv, frames.view(-1, m.n_fft), None, self.backend, name="mdx.istft")
-            self._io = (B, padded, frames, stft, istft)
+            self._io = (pl, padded, frames, stft, istft)
         _, padded, frames, stft, istft = self._io
         trim = m.n_fft // 2
         for s in range(0, nchunks, B):
@@ -443,6 +450,7 @@ class MDX:
             if self.prog is not None:
                 self.prog.update(e - s)
 
+    @_ffi.on_device
     def process_wave(self, wave: np.ndarray, mt_threads=1):
         """np [2,N] -> np [2,N] like mdx.py:201-235 (the thread count only decides the segment split here)."""
         w = torch.from_numpy(np.ascontiguousarray(wave, dtype=np.float32)).to(self.device)
@@ -490,6 +498,11 @@ def _write_wav_pcm16(path, data_T, sr):
 def run_mdx_device(mdx_sess: MDX, wave_dev: torch.Tensor, denoise=False, m_threads=2, group=None):
     """The arithmetic of run_mdx (mdx.py:257-280) on a device tensor [2,N]: returns (main, inverse) device tensors.
     NB the reference normalises `wave` in place by its peak and reuses the normalised array for the inverse stem."""
+    with torch.cuda.device(mdx_sess.device):
+        return _run_mdx_device(mdx_sess, wave_dev, denoise, m_threads, group)
+
+
+def _run_mdx_device(mdx_sess: MDX, wave_dev: torch.Tensor, denoise, m_threads, group):
     model = mdx_sess.model
     peak = float(torch.maximum(wave_dev.max(), wave_dev.min().abs()).item())       # max(np.max(w), abs(np.min(w)))
     w = (wave_dev / peak).contiguous()

@@ -58,6 +58,8 @@ def _p(t: Optional[torch.Tensor]):
 
 def _f32c(t: torch.Tensor):
     assert t.is_cuda and t.dtype == torch.float32, (t.device, t.dtype)
+    # launches go to the current device's stream (see _ffi.on_device): refuse cross-device calls instead of faulting
+    assert t.device.index == torch.cuda.current_device(), f"tensor on {t.device} but cuda:{torch.cuda.current_device()} is current"
     return t
 
 

@@ -15,7 +15,7 @@ from typing import Dict, List, Optional
 import numpy as np
 import torch
 
-from . import ops
+from . import _ffi, ops
 from . import tapgemm as tg
 from .plans import PlanCache
 from .tapgemm import Epi
@@ -126,6 +126,7 @@ class RMVPEB200:
     def _plan(self, n_samples: int) -> "_RmvpePlan":
         return self._plans.get_or_build(n_samples, lambda: _RmvpePlan(self, n_samples))
 
+    @_ffi.on_device
     @torch.no_grad()
     def salience_from_audio(self, audio: torch.Tensor) -> torch.Tensor:
         """Device tensor [n_frames, 360] (rmvpe.py:370-373)."""
@@ -133,6 +134,7 @@ class RMVPEB200:
         pl.run(audio)
         return pl.sal[:pl.n_frames]
 
+    @_ffi.on_device
     @torch.no_grad()
     def infer_from_audio_device(self, audio: torch.Tensor, thred: float = 0.03) -> torch.Tensor:
         """f0 [n_frames] float64 on the device (no host sync)."""
@@ -141,6 +143,7 @@ class RMVPEB200:
         ops.rmvpe_decode(pl.sal, pl.f0, pl.n_frames, thred)
         return pl.f0
 
+    @_ffi.on_device
     def infer_from_audio(self, audio: np.ndarray, thred: float = 0.03) -> np.ndarray:
         """Reference signature (rmvpe.py:366-383): np.ndarray[N] -> np.ndarray[1 + N//160] (float64 Hz, 0 = unvoiced)."""
         if isinstance(audio, torch.Tensor):

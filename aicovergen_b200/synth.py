@@ -17,7 +17,7 @@ from typing import Dict, List, Optional, Tuple
 import numpy as np
 import torch
 
-from . import ops
+from . import _ffi, ops
 from . import tapgemm as tg
 from .plans import PlanCache
 from .tapgemm import Epi
@@ -178,6 +178,7 @@ class SynthesizerB200:
         return out
 
     # ------------------------------------------------------------------ public plug point
+    @_ffi.on_device
     @torch.no_grad()
     def infer(self, phone, phone_lengths, pitch=None, nsff0=None, sid=None, max_len=None,
               noise_z: Optional[torch.Tensor] = None, noise_src: Optional[torch.Tensor] = None):

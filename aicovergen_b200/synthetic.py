@@ -333,7 +333,8 @@ def make_mdx_state_dict(dim_f: int = 3072, dim_t: int = 256, g: int = 48, l: int
     return sd
 
 
-def calibrate_mdx_batchnorm(sd: Dict[str, torch.Tensor], x: torch.Tensor, eps: float = 1e-5) -> Dict[str, torch.Tensor]:
+def calibrate_mdx_batchnorm(sd: Dict[str, torch.Tensor], x: torch.Tensor, eps: float = 1e-5,
+                            out_gain: float = 0.0) -> Dict[str, torch.Tensor]:
     """Gives a synthetic ConvTDFNet the activation statistics of a TRAINED one: one forward pass over `x`
     ([B,4,dim_f,dim_t] spectrogram-like input) sets every BatchNorm's running_mean / running_var to the statistics of
     its own input (what training converges to), so each normalised layer emits O(1) values and the multiplicative skips
@@ -370,4 +371,163 @@ def calibrate_mdx_batchnorm(sd: Dict[str, torch.Tensor], x: torch.Tensor, eps: f
             t = F.relu(bn_fit(f"us.{i}.1", F.conv_transpose2d(t, out[f"us.{i}.0.weight"], out[f"us.{i}.0.bias"], stride=2)))
             t = t * skips[-i - 1]
             t = tfc_tdf(f"decoding_blocks.{i}", t)
+        if out_gain > 0:
+            # a separator's output spectrogram has the level of its input: rescale the final 1x1 conv accordingly
+            y = F.conv2d(t.transpose(-1, -2), out["final_conv.0.weight"], out["final_conv.0.bias"])
+            sc = out_gain * x.float().pow(2).mean().sqrt() / y.pow(2).mean().sqrt().clamp_min(1e-12)
+            out["final_conv.0.weight"] = out["final_conv.0.weight"] * sc
+            out["final_conv.0.bias"] = out["final_conv.0.bias"] * sc
     return out
+
+
+def calibrate_rmvpe(sd: Dict[str, torch.Tensor], audio: torch.Tensor, peak_sigma_bins: float = 1.3,
+                    logit_gain: float = 4.0, logit_bias: float = -5.2, voicing_sigma: float = 2.0,
+                    eps: float = 1e-5) -> Dict[str, torch.Tensor]:
+    """Gives a synthetic rmvpe checkpoint the two properties of a TRAINED one that the F0 decode relies on:
+      * every BatchNorm's running statistics equal the statistics of its own input on a calibration clip (what training
+        converges to), so activations stay O(1) through the ~70 convolutions instead of drifting with depth;
+      * the salience head emits ONE smooth peak per frame over neighbouring 20-cent bins (a trained rmvpe's output is a
+        narrow bump around the pitch, rmvpe.py:385-409 decodes it with a +-4-bin local average): `fc.1.weight` rows are
+        made smooth across bins (Gaussian, `peak_sigma_bins`) and scaled so that 3 sigma of the per-bin logits is
+        `logit_gain` around `logit_bias` (most bins ~0), plus a per-frame "voicing" term common to all bins (std
+        `voicing_sigma`) so that frames split into clearly voiced (peak 0.3 .. 0.99) and unvoiced (max <= 0.03) ones —
+        the `protect` / f0 == 0 branches of VC.pipeline need both.  With a smooth peak an argmax flip between adjacent
+        near-equal bins moves the decoded f0 by a fraction of a cent, as it does for real weights.
+    `audio` [N] float32 @16 kHz.  Plain torch on the CPU: a weight generator for tests / bench, not an inference path.
+    Returns a NEW state dict with the same keys."""
+    import torch.nn.functional as F
+
+    from .rmvpe import HOP, N_FFT, N_MELS, mel_basis
+
+    out = {k_: v.clone() for k_, v in sd.items()}
+
+    def bn_fit(name, t):
+        mean = t.mean(dim=(0, 2, 3))
+        var = t.var(dim=(0, 2, 3), unbiased=False).clamp_min(1e-6)
+        out[name + ".running_mean"], out[name + ".running_var"] = mean, var
+        return F.batch_norm(t, mean, var, out[name + ".weight"], out[name + ".bias"], False, 0.0, eps)
+
+    def block(p, x):
+        y = F.relu(bn_fit(p + "conv.1", F.conv2d(x, out[p + "conv.0.weight"], padding=1)))
+        y = F.relu(bn_fit(p + "conv.4", F.conv2d(y, out[p + "conv.3.weight"], padding=1)))
+        if p + "shortcut.weight" in out:
+            return y + F.conv2d(x, out[p + "shortcut.weight"], out[p + "shortcut.bias"])
+        return y + x
+
+    n_enc = 1 + max(int(k_.split(".")[3]) for k_ in sd if k_.startswith("unet.encoder.layers."))
+    n_blocks = 1 + max(int(k_.split(".")[5]) for k_ in sd if k_.startswith("unet.encoder.layers.0.conv."))
+    n_inter = 1 + max(int(k_.split(".")[3]) for k_ in sd if k_.startswith("unet.intermediate.layers."))
+    with torch.no_grad():
+        a = audio.float().reshape(1, -1)
+        spec = torch.stft(a, N_FFT, HOP, N_FFT, torch.hann_window(N_FFT), center=True, return_complex=True).abs()
+        mel = torch.log(torch.clamp(torch.from_numpy(mel_basis()) @ spec, min=1e-5))            # [1, 128, n]
+        n = mel.shape[-1]
+        mel = F.pad(mel, (0, 32 * ((n - 1) // 32 + 1) - n), mode="reflect")
+        x = bn_fit("unet.encoder.bn", mel.transpose(-1, -2).unsqueeze(1))
+        skips = []
+        for i in range(n_enc):
+            for b in range(n_blocks):
+                x = block(f"unet.encoder.layers.{i}.conv.{b}.", x)
+            skips.append(x)
+            x = F.avg_pool2d(x, 2)
+        for i in range(n_inter):
+            for b in range(n_blocks):
+                x = block(f"unet.intermediate.layers.{i}.conv.{b}.", x)
+        for i in range(n_enc):
+            p = f"unet.decoder.layers.{i}."
+            x = F.relu(bn_fit(p + "conv1.1", F.conv_transpose2d(x, out[p + "conv1.0.weight"], stride=2, padding=1, output_padding=1)))
+            x = torch.cat((x, skips[-1 - i]), dim=1)
+            for b in range(n_blocks):
+                x = block(p + f"conv2.{b}.", x)
+        x = F.conv2d(x, out["cnn.weight"], out["cnn.bias"], padding=1)
+        x = x.transpose(1, 2).flatten(-2)
+        # standardise the GRU input so the gates work in their active range
+        mu, sdv = x.mean(), x.std().clamp_min(1e-6)
+        out["cnn.weight"] = out["cnn.weight"] / sdv
+        out["cnn.bias"] = (out["cnn.bias"] - mu) / sdv
+        x = (x - mu) / sdv
+        Hh = out["fc.0.gru.weight_hh_l0"].shape[1]
+        gru = torch.nn.GRU(x.shape[-1], Hh, num_layers=1, batch_first=True, bidirectional=True)
+        gru.load_state_dict({k_[len("fc.0.gru."):]: v for k_, v in out.items() if k_.startswith("fc.0.gru.")})
+        h = gru.eval()(x)[0][0]                                                                   # [T, 2H]
+        # smooth-across-bins head: W = G W0 with a Gaussian G over the 360 pitch bins, logits standardised on the clip
+        w0 = out["fc.1.weight"]
+        nb = w0.shape[0]
+        k = torch.arange(nb, dtype=torch.float32)
+        G = torch.exp(-0.5 * ((k[:, None] - k[None, :]) / peak_sigma_bins) ** 2)
+        G = G / G.sum(1, keepdim=True)
+        w = G @ w0
+        z = h @ w.t()
+        w = w * (logit_gain / 3.0 / z.std().clamp_min(1e-6))           # 3 sigma of the logits ~ logit_gain
+        wv = w0[nb // 2:nb // 2 + 8].mean(0)                            # a direction of the GRU output: per-frame voicing term
+        wv = wv * (voicing_sigma / (h @ wv).std().clamp_min(1e-6))
+        w = w + wv[None, :]
+        out["fc.1.weight"] = w
+        out["fc.1.bias"] = torch.full((nb,), float(logit_bias)) - (h @ w.t()).mean(0)
+    return out
+
+
+_TRAINED_LIKE_CACHE: Dict[tuple, Dict[str, torch.Tensor]] = {}
+
+
+def calibration_clip(seconds: float = 6.0, sr: int = 16000, seed: int = 11) -> torch.Tensor:
+    """Seeded vocal-like clip (harmonic stack with vibrato + unvoiced bursts + noise floor) used to fit the statistics."""
+    g = torch.Generator().manual_seed(seed)
+    n = int(seconds * sr)
+    t = torch.arange(n, dtype=torch.float64) / sr
+    f0 = 220.0 * 2 ** (0.5 * torch.sin(2 * math.pi * 0.23 * t)) * 2 ** (30 / 1200 * torch.sin(2 * math.pi * 5.5 * t))
+    ph = 2 * math.pi * torch.cumsum(f0, 0) / sr
+    x = sum(torch.sin(k * ph) / k for k in range(1, 9))
+    noise = torch.randn(n, generator=g, dtype=torch.float64)
+    x = torch.where((t % 2.0) > 1.7, 0.7 * noise, x) + 0.05 * noise
+    return (0.5 * x / x.abs().max()).float()
+
+
+def make_rmvpe_trained_like(seed: int = 4321) -> Dict[str, torch.Tensor]:
+    """make_rmvpe_state_dict + calibrate_rmvpe on the seeded calibration clip (cached per process)."""
+    key = ("rmvpe", seed)
+    if key not in _TRAINED_LIKE_CACHE:
+        _TRAINED_LIKE_CACHE[key] = calibrate_rmvpe(make_rmvpe_state_dict(seed), calibration_clip())
+    return _TRAINED_LIKE_CACHE[key]
+
+
+def calibration_song(seconds: float = 3.0, sr: int = 44100, seed: int = 4242) -> torch.Tensor:
+    """Seeded stereo test song [2, n] (pink-ish bed + chord tones + a vocal-like line), peak-normalised."""
+    g = torch.Generator().manual_seed(seed)
+    n = int(seconds * sr)
+    t = torch.arange(n, dtype=torch.float64) / sr
+    f0 = 220.0 * 2 ** (0.5 * torch.sin(2 * math.pi * 0.2 * t))
+    ph = 2 * math.pi * torch.cumsum(f0, 0) / sr
+    vocal = sum(torch.sin(k * ph) / k for k in range(1, 9))
+    out = []
+    for ch in range(2):
+        white = torch.randn(n, generator=g, dtype=torch.float64)
+        spec = torch.fft.rfft(white)
+        spec = spec / torch.sqrt(torch.arange(spec.numel(), dtype=torch.float64).clamp_min(1.0))
+        bed = torch.fft.irfft(spec, n)
+        bed = bed * (0.25 / bed.abs().max())
+        chord = sum(torch.sin(2 * math.pi * f * (1 + 0.002 * ch) * t + ch) for f in (130.8, 164.8, 196.0))
+        out.append(bed + 0.15 * chord + 0.35 * vocal * (1.0 - 0.1 * ch))
+    x = torch.stack(out)
+    return (x / x.abs().max()).float()
+
+
+def make_mdx_trained_like(dim_f: int = 3072, dim_t: int = 256, n_fft: int = 7680, seed: int = 2024, cal_frames: int = 64,
+                          **kw) -> Dict[str, torch.Tensor]:
+    """make_mdx_state_dict + calibrate_mdx_batchnorm on the STFT of the seeded calibration song (the BatchNorm statistics a
+    trained network would carry), cached per process.  The calibration runs on `cal_frames` time frames (the statistics
+    are per channel over batch x time x frequency, and the TDF linears act along frequency only), which keeps it to a few
+    seconds of CPU time at the full 3072-bin geometry."""
+    key = ("mdx", dim_f, dim_t, n_fft, seed, cal_frames, tuple(sorted(kw.items())))
+    if key not in _TRAINED_LIKE_CACHE:
+        sd = make_mdx_state_dict(dim_f=dim_f, dim_t=dim_t, seed=seed, **kw)
+        n_lvl = int(sd["_meta"][4])
+        T = max(cal_frames, 2 ** n_lvl)
+        T = min(T, dim_t)
+        hop = 1024
+        song = calibration_song(max(3.0, (hop * (T - 1) + n_fft) / 44100.0 + 1.5))
+        seg = song[:, 22050:22050 + hop * (T - 1)]
+        z = torch.stft(seg, n_fft=n_fft, hop_length=hop, window=torch.hann_window(n_fft), center=True, return_complex=True)
+        z = torch.view_as_real(z).permute(0, 3, 1, 2)[:, :, :dim_f]                 # [ch, ri, F, T]
+        _TRAINED_LIKE_CACHE[key] = calibrate_mdx_batchnorm(sd, z.reshape(1, 4, dim_f, T), out_gain=0.05)
+    return _TRAINED_LIKE_CACHE[key]

@@ -180,6 +180,9 @@ class TapGemm:
         p.o_sb, p.o_sh, p.o_sw, p.o_sn = int(out.sb), int(out.sh), int(out.sw), int(out.sn)
         p.r_sn = 1
         self._keep = [a.t, w.t, out.t]
+        if a.t.is_cuda:     # launches use the current device's stream (see _ffi.on_device); CPU tensors = descriptor emulator tests
+            assert a.t.device == w.t.device == out.t.device and a.t.device.index == torch.cuda.current_device(), \
+                f"tapgemm[{name}]: operands on {a.t.device}/{w.t.device}/{out.t.device}, current device cuda:{torch.cuda.current_device()}"
         # ---- epilogue
         if epi.row_scale_pre is not None:
             assert epi.row_scale_pre.dtype == torch.float32 and epi.row_scale_pre.is_contiguous()

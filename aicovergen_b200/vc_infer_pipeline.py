@@ -22,36 +22,11 @@ import numpy as np
 import torch
 from scipy import signal
 
-from . import ops
+from . import _ffi, ops
 from .index import IvfIndexB200, read_index
 
 # 5th-order Butterworth high-pass at 48 Hz for 16 kHz input (vc_infer_pipeline.py:22)
 bh, ah = signal.butter(N=5, Wn=48, btype="high", fs=16000)
-
-
-def _frame_rms(y: np.ndarray, frame_length: int, hop_length: int) -> np.ndarray:
-    """librosa.feature.rms(y=..., frame_length, hop_length) of librosa 0.9.1 (center=True, reflect padding) -> [1, n]."""
-    pad = frame_length // 2
-    yp = np.pad(y, (pad, pad), mode="reflect")
-    n = 1 + (len(yp) - frame_length) // hop_length
-    sq = np.abs(yp) ** 2
-    csum = np.concatenate(([0.0], np.cumsum(sq, dtype=np.float64)))
-    starts = hop_length * np.arange(n)
-    power = (csum[starts + frame_length] - csum[starts]) / frame_length
-    return np.sqrt(np.maximum(power, 0.0)).astype(y.dtype if y.dtype in (np.float32, np.float64) else np.float64)[None, :]
-
-
-def change_rms(data1, sr1, data2, sr2, rate):
-    """Match the output loudness envelope to the input's (vc_infer_pipeline.py:41-60). data2 is scaled in place."""
-    import torch.nn.functional as F
-
-    rms1 = _frame_rms(data1, sr1 // 2 * 2, sr1 // 2)
-    rms2 = _frame_rms(data2, sr2 // 2 * 2, sr2 // 2)
-    rms1 = F.interpolate(torch.from_numpy(rms1).unsqueeze(0), size=data2.shape[0], mode="linear").squeeze()
-    rms2 = F.interpolate(torch.from_numpy(rms2).unsqueeze(0), size=data2.shape[0], mode="linear").squeeze()
-    rms2 = torch.max(rms2, torch.zeros_like(rms2) + 1e-6)
-    data2 *= (torch.pow(rms1, torch.tensor(1 - rate)) * torch.pow(rms2, torch.tensor(rate - 1))).numpy()
-    return data2
 
 
 class VC(object):
@@ -70,6 +45,7 @@ class VC(object):
         self._noise_gen: Optional[torch.Generator] = None
         self.keep_float = False      # tests: keep the float waveform before/after the RMS mix
         self.exact_hpf = False       # True: scipy.signal.filtfilt on the host (the reference's exact ba-form numerics)
+        self.return_device = False   # extension: pipeline() returns the int16 utterance as a device tensor (no D2H)
 
     # ------------------------------------------------------------------ extension for parity tests
     def set_noise_seed(self, seed: Optional[int]):
@@ -183,6 +159,7 @@ class VC(object):
                 opt_ts.append(t - self.t_query + int(torch.argmin(seg).item()))   # argmin returns the first minimum
         return opt_ts
 
+    @_ffi.on_device
     def pipeline(self, model, net_g, sid, audio, input_audio_path, times, f0_up_key, f0_method, file_index,
                  index_rate, if_f0, filter_radius, tgt_sr, resample_sr, rms_mix_rate, version, protect,
                  crepe_hop_length, f0_file=None):
@@ -194,8 +171,13 @@ class VC(object):
                     self._index_cache = (key, read_index(file_index, self.device))
                 index = self._index_cache[1]
                 big_npy = index._host_vectors            # what reconstruct_n(0, ntotal) returns, without the copy
-            except Exception:
+            except Exception as e:
+                # the reference continues without an index on a failed read (:508-510); say so loudly — a silently
+                # disabled index changes the timbre of every conversion
                 traceback.print_exc()
+                import warnings
+                warnings.warn(f"b200vc: feature index {file_index!r} could not be loaded ({e}); continuing WITHOUT "
+                              f"index retrieval (index_rate={index_rate} ignored)", RuntimeWarning)
                 index = big_npy = None
         else:
             index = big_npy = None
@@ -265,7 +247,7 @@ class VC(object):
         if self.keep_float:
             self.last_float_mixed = audio_dev.cpu().numpy()
         out_i16 = ops.to_int16_peak_guard(audio_dev)
-        self.last_output_device = out_i16        # the same samples still in HBM (CoverEngine.mix reads them here)
-        audio_opt = out_i16.cpu().numpy()         # the single D2H of the converted utterance
         del pitch, pitchf, sid
-        return audio_opt
+        if self.return_device:
+            return out_i16                        # CoverEngine: the mix reads the utterance from HBM
+        return out_i16.cpu().numpy()              # the single D2H of the converted utterance

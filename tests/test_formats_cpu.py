@@ -43,6 +43,42 @@ def test_ivfflat_byte_layout_matches_faiss_headers(tmp_path):
     assert b.find(b"ilar") > 0 and b.find(b"full") > b.find(b"ilar")
 
 
+def test_ivfflat_hand_assembled_faiss_bytes(tmp_path):
+    """A file assembled field by field from faiss 1.7.x's serialisation (index_write.cpp: fourcc "IwFl" + write_ivf_header
+    + write_InvertedLists; NO code_size between the direct map and "ilar" for IndexIVFFlat), without the repo's writer:
+    d=2, nlist=3 (list 1 empty -> exercises skipping), ntotal=4 added in id order, maintained direct map (type 1: Array)."""
+    d, nlist = 2, 3
+    cent = np.array([[0, 0], [10, 10], [5, 5]], dtype="<f4")
+    vec = np.array([[0.1, 0], [5, 5.2], [0, 0.3], [4.9, 5]], dtype="<f4")      # ids 0..3 -> lists 0, 2, 0, 2
+    hdr = lambda n: struct.pack("<i", d) + struct.pack("<q", n) + struct.pack("<qq", 1 << 20, 1 << 20) + b"\x01" + struct.pack("<i", 1)
+    b = b"IwFl" + hdr(4) + struct.pack("<QQ", nlist, 1)
+    b += b"IxF2" + hdr(nlist) + struct.pack("<Q", nlist * d) + cent.tobytes()
+    # direct map, type Array: entry id -> (list_no << 32 | offset)
+    dm = np.array([(0 << 32) | 0, (2 << 32) | 0, (0 << 32) | 1, (2 << 32) | 1], dtype="<i8")
+    b += b"\x01" + struct.pack("<Q", 4) + dm.tobytes()
+    b += b"ilar" + struct.pack("<QQ", nlist, 4 * d) + b"full" + struct.pack("<Q", nlist) + np.array([2, 0, 2], dtype="<u8").tobytes()
+    b += vec[[0, 2]].tobytes() + np.array([0, 2], dtype="<i8").tobytes()
+    b += vec[[1, 3]].tobytes() + np.array([1, 3], dtype="<i8").tobytes()
+    assert len(b) == 4 + 33 + 16 + 4 + 33 + 8 + 24 + 1 + 8 + 32 + 4 + 16 + 4 + 8 + 24 + 2 * (16 + 16)
+    p = tmp_path / "added_IVF3_Flat_nprobe_1_hand.index"
+    p.write_bytes(b)
+    data = faiss_io.read_ivfflat(str(p))
+    assert (data.d, data.nlist, data.nprobe, data.metric, data.ids_sequential) == (2, 3, 1, faiss_io.METRIC_L2, True)
+    np.testing.assert_array_equal(data.centroids, cent)
+    np.testing.assert_array_equal(data.vectors, vec)
+    np.testing.assert_array_equal(data.list_of, [0, 2, 0, 2])
+    # the legacy layout with a u64 code_size before "ilar" must be rejected, not misparsed
+    bad = b.replace(b"ilar", struct.pack("<Q", 4 * d) + b"ilar")
+    p.write_bytes(bad)
+    with pytest.raises(faiss_io.FaissFormatError):
+        faiss_io.read_ivfflat(str(p))
+    # and the writer emits exactly these bytes for the same index without a direct map
+    q = tmp_path / "w.index"
+    faiss_io.write_ivfflat(str(q), cent, vec, np.array([0, 2, 0, 2]))
+    want = b.replace(b"\x01" + struct.pack("<Q", 4) + dm.tobytes(), b"\x00" + struct.pack("<Q", 0))
+    assert q.read_bytes() == want
+
+
 def test_rejects_other_index_types(tmp_path):
     p = tmp_path / "x.index"
     p.write_bytes(b"IxF2" + b"\0" * 64)
