@@ -47,7 +47,8 @@ __global__ void logmel_affine_reflect_kernel(const float* __restrict__ x, float*
   int t = (int)(e / C);
   const int c = (int)(e % C);
   if (t >= rows) t = 2 * (rows - 1) - t;
-  out[e] = a * logf(fmaxf(x[(long long)t * C + c], clampv)) + b;
+  const float v = x[(long long)t * C + c];
+  out[e] = a * (clampv < 0.f ? v : logf(fmaxf(v, clampv))) + b;     // clampv < 0: x already holds log-mel (RMVPE.mel2hidden)
 }
 
 // NHWC 2x2 average pool, input may be a channel slice (pixel pitch ldi)

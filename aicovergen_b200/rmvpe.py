@@ -136,6 +136,29 @@ class RMVPEB200:
 
     @_ffi.on_device
     @torch.no_grad()
+    def mel2hidden(self, mel: torch.Tensor) -> torch.Tensor:
+        """Reference signature (rmvpe.py:350-357): log-mel [1,128,n] (or [128,n]) -> salience [1,n,360] (device tensor)."""
+        m2 = mel.reshape(N_MELS, -1)
+        n = int(m2.shape[1])
+        pl = self._plan((n - 1) * HOP)
+        pl.run_from_logmel(m2.t().to(self.device).float().contiguous())
+        return pl.sal[:n].unsqueeze(0)
+
+    def decode(self, hidden, thred: float = 0.03) -> np.ndarray:
+        """Reference signature (rmvpe.py:359-364): salience [n,360] (numpy or tensor) -> f0 [n] float64."""
+        with torch.cuda.device(self.device):
+            h = torch.as_tensor(hidden).to(self.device).float().contiguous()
+            n = int(h.shape[0])
+            cents = torch.empty(n, device=self.device, dtype=torch.float64)
+            f0d = torch.empty(n, device=self.device, dtype=torch.float64)
+            ops.rmvpe_decode(h, f0d, n, thred, cents=cents)
+            c = cents.cpu().numpy()
+        f0 = 10 * (2 ** (c / 1200))
+        f0[f0 == 10] = 0
+        return f0
+
+    @_ffi.on_device
+    @torch.no_grad()
     def infer_from_audio_device(self, audio: torch.Tensor, thred: float = 0.03) -> torch.Tensor:
         """f0 [n_frames] float64 on the device (no host sync)."""
         pl = self._plan(int(audio.numel()))
@@ -185,7 +208,9 @@ class _RmvpePlan:
         melp = torch.empty(nf, N_MELS, **f32)
         add(tg.linear(mag, W["mel"], melp, None, be, name="mel"))
         img = torch.empty(1, T, N_MELS, 1, **f32)        # NHWC: H = frames, W = mel bins, C = 1
-        add(lambda: ops.logmel_affine_reflect(melp, img.view(T, N_MELS), nf, 1e-5, m.bn_a, m.bn_b))
+        self.n_front = len(steps)                        # steps before this one build `melp` from audio
+        self.melp, self.mel_is_log = melp, False
+        add(lambda: ops.logmel_affine_reflect(melp, img.view(T, N_MELS), nf, -1.0 if self.mel_is_log else 1e-5, m.bn_a, m.bn_b))
 
         def block(x, key, out, cin, cout, H_, W_):
             t1 = torch.empty(1, H_, W_, cout, **f32)
@@ -246,5 +271,14 @@ class _RmvpePlan:
 
     def run(self, audio: torch.Tensor):
         self.audio.copy_(audio.reshape(-1))
+        self.mel_is_log = False
         for st in self.steps:
             st()
+
+    def run_from_logmel(self, mel_t: torch.Tensor):
+        """mel_t [n_frames, 128] log-mel (what MelSpectrogram.forward returns, transposed): skips the front-end."""
+        self.melp.copy_(mel_t)
+        self.mel_is_log = True
+        for st in self.steps[self.n_front:]:
+            st()
+        self.mel_is_log = False

@@ -57,8 +57,10 @@ class VC(object):
             return None, None
         g = self._noise_gen
         nz = torch.randn(1, net_g.inter, P, generator=g)
-        _ = torch.rand(1, 1, generator=g)
-        ns = torch.randn(1, P * net_g.upp, 1, generator=g) if net_g.f0 else None
+        ns = None
+        if net_g.f0:                     # the *_nono models draw randn_like(m_p) only (models.py:847-853)
+            _ = torch.rand(1, 1, generator=g)
+            ns = torch.randn(1, P * net_g.upp, 1, generator=g)
         dev = self.device
         return nz.to(dev), (None if ns is None else ns.to(dev))
 

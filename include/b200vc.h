@@ -192,7 +192,7 @@ int b200vc_reflect_pad_1d(const float* in, float* out, int64_t N, int64_t pad, v
 /* mag[t,k] = |spec[t,k] + i spec[t,nb+k]| with zero-filled row tail up to ldm (rmvpe.py:314) */
 int b200vc_magnitude(const float* spec, float* mag, int64_t rows, int nb, int64_t lds, int64_t ldm, void* stream);
 
-/* out[t,c] = a*log(max(x[t,c],clampv))+b for t<rows, reflect-padded to rows_total rows
+/* out[t,c] = a*log(max(x[t,c],clampv))+b (clampv < 0: a*x[t,c]+b, x already log-mel) for t<rows, reflect-padded to rows_total rows
  * (rmvpe.py:324 ; the scalar BatchNorm2d(1) of Encoder.bn, rmvpe.py:74,92 ; F.pad reflect, rmvpe.py:353-355) */
 int b200vc_logmel_affine_reflect(const float* x, float* out, int rows, int rows_total, int C, float clampv,
                                  float a, float b, void* stream);

@@ -46,3 +46,44 @@ def librosa_rms(y, frame_length, hop_length):
     x = yp[idx]
     power = np.mean(np.abs(x) ** 2, axis=0, keepdims=True)
     return np.sqrt(power)
+
+
+def resample_sinc_mono(x, n_out, rate_in, rate_out, zero_crossings=16):
+    """Checker for the device INGEST STAND-IN b200vc_resample_sinc_mono (the reference shells out to ffmpeg
+    `-ac 1 -ar 16000`, my_utils.py:13-17 — not restated): channel mean, Hann-windowed sinc, cutoff at the lower Nyquist.
+    float64 accumulation; x [channels, n_in] -> [n_out]."""
+    x = np.asarray(x, dtype=np.float64)
+    mono = x.mean(0)
+    n_in = mono.shape[0]
+    ratio = float(rate_in) / float(rate_out)
+    scale = 1.0 / ratio if ratio > 1.0 else 1.0
+    halfw = zero_crossings / scale
+    out = np.zeros(n_out)
+    kk = np.arange(-int(np.ceil(halfw)) - 1, int(np.ceil(halfw)) + 2)
+    for s in range(0, n_out, 65536):
+        m = np.arange(s, min(s + 65536, n_out))
+        center = m * ratio
+        k = np.floor(center)[:, None].astype(np.int64) + kk[None, :]
+        d = k - center[:, None]
+        ok = (np.abs(d) <= halfw) & (k >= 0) & (k < n_in)
+        a = d * scale
+        sinc = np.sinc(a)
+        win = 0.5 + 0.5 * np.cos(np.pi * d / halfw)
+        v = mono[np.clip(k, 0, n_in - 1)]
+        out[m] = (np.where(ok, v * sinc * win, 0.0)).sum(1) * scale
+    return out.astype(np.float32)
+
+
+def mix3(a_mono, rate_a, b, c, rate, ga, gb, gc):
+    """Checker for the device MIX STAND-IN b200vc_mix3 (gain-and-sum in place of pydub's overlay, main.py:229-233):
+    out[ch, n] = ga * lerp(a_mono, n * rate_a / rate) + gb * b[ch, n] + gc * c[ch, n]."""
+    n = b.shape[1]
+    pos = np.arange(n, dtype=np.float64) * (float(rate_a) / float(rate))
+    i0 = pos.astype(np.int64)
+    fr = (pos - i0).astype(np.float32)
+    a = np.asarray(a_mono, dtype=np.float32)
+    na = a.shape[0]
+    a0 = np.where(i0 < na, a[np.clip(i0, 0, na - 1)], 0.0)
+    a1 = a[np.clip(i0 + 1, 0, na - 1)]
+    av = np.where(i0 + 1 < na, a0 * (1.0 - fr) + a1 * fr, a0).astype(np.float32)
+    return (ga * av[None, :] + gb * b + gc * c).astype(np.float32)

@@ -86,16 +86,18 @@ def vc_segment(hubert_sd, cpt, audio0, pitch, pitchf, index, big_npy, index_rate
     # draw order inside net_g.infer: randn_like(m_p), rand(1,1), randn_like(sine)  (models.py:748,337,368)
     P = feats.shape[1]
     nz = torch.randn(1, cfg[2], P)
-    _ = torch.rand(1, 1)
-    ns = torch.randn(1, P * upp, 1)
+    ns = None
+    if has_f0:                       # the *_nono models draw randn_like(m_p) only (models.py:847-853)
+        _ = torch.rand(1, 1)
+        ns = torch.randn(1, P * upp, 1)
     o = osyn.infer(cpt, feats, pitch, pitchf, torch.tensor([0]), nz, ns)
     return o[0, 0].float().numpy()
 
 
 def pipeline(hubert_sd, cpt, rmvpe_sd, audio: np.ndarray, index: Optional[IvfFlatIndex] = None, f0_up_key=0,
              index_rate=0.5, rms_mix_rate=0.25, protect=0.33, version="v2", x_pad=3, x_query=10, x_center=60,
-             x_max=65, seed: Optional[int] = None, return_all=False):
-    """VC.pipeline with f0_method='rmvpe', if_f0=1, resample_sr=0, no f0 file."""
+             x_max=65, seed: Optional[int] = None, return_all=False, if_f0: int = 1):
+    """VC.pipeline with f0_method='rmvpe', resample_sr=0, no f0 file (if_f0=0: the no-pitch models, :548-603)."""
     tgt_sr = cpt["config"][-1]
     sr, window = 16000, 160
     t_pad, t_pad_tgt = sr * x_pad, tgt_sr * x_pad
@@ -107,23 +109,23 @@ def pipeline(hubert_sd, cpt, rmvpe_sd, audio: np.ndarray, index: Optional[IvfFla
     opt_ts = cut_points(audio, window, t_max, t_center, t_query)
     audio_pad = np.pad(audio, (t_pad, t_pad), mode="reflect")
     p_len = audio_pad.shape[0] // window
-    f0 = ormv.infer_from_audio(rmvpe_sd, audio_pad, 0.03)
-    pitch, pitchf = ormv.coarse_pitch(f0, f0_up_key)
-    pitch, pitchf = pitch[:p_len], pitchf[:p_len]
-    pitch_t = torch.tensor(pitch).unsqueeze(0).long()
-    pitchf_t = torch.tensor(pitchf).unsqueeze(0).float()
+    f0 = pitch = pitchf = None
+    if if_f0 == 1:
+        f0 = ormv.infer_from_audio(rmvpe_sd, audio_pad, 0.03)
+        pitch, pitchf = ormv.coarse_pitch(f0, f0_up_key)
+        pitch, pitchf = pitch[:p_len], pitchf[:p_len]
+        pitch_t = torch.tensor(pitch).unsqueeze(0).long()
+        pitchf_t = torch.tensor(pitchf).unsqueeze(0).float()
+    sl = (lambda a, b: (pitch_t[:, a:b], pitchf_t[:, a:b])) if if_f0 == 1 else (lambda a, b: (None, None))
     if seed is not None:
         torch.manual_seed(seed)
     s, t, outs = 0, None, []
     for t in opt_ts:
         t = t // window * window
-        outs.append(vc_segment(hubert_sd, cpt, audio_pad[s: t + t_pad2 + window],
-                               pitch_t[:, s // window: (t + t_pad2) // window],
-                               pitchf_t[:, s // window: (t + t_pad2) // window],
+        outs.append(vc_segment(hubert_sd, cpt, audio_pad[s: t + t_pad2 + window], *sl(s // window, (t + t_pad2) // window),
                                index, big_npy, index_rate, version, protect)[t_pad_tgt: -t_pad_tgt])
         s = t
-    outs.append(vc_segment(hubert_sd, cpt, audio_pad[t:], pitch_t[:, t // window:] if t is not None else pitch_t,
-                           pitchf_t[:, t // window:] if t is not None else pitchf_t,
+    outs.append(vc_segment(hubert_sd, cpt, audio_pad[t:], *sl(t // window if t is not None else 0, None),
                            index, big_npy, index_rate, version, protect)[t_pad_tgt: -t_pad_tgt])
     audio_opt = np.concatenate(outs)
     float_out = audio_opt.copy()

@@ -159,20 +159,23 @@ def resblock1(sd: SD, p: str, x, k: int, dil):
 def generator(sd: SD, z, f0, g, cfg, noise):
     up_r, up_k, rb_k, rb_d, sr = cfg[12], cfg[14], cfg[10], cfg[11], cfg[17]
     upp = int(np.prod(up_r))
-    sine = sine_source(f0, upp, sr, noise)
-    har = torch.tanh(F.linear(sine, sd["dec.m_source.l_linear.weight"], sd["dec.m_source.l_linear.bias"])).transpose(1, 2)
+    nsf = f0 is not None          # f0=None: the plain `Generator` of the *_nono models (models.py:188-250), no source branch
+    if nsf:
+        sine = sine_source(f0, upp, sr, noise)
+        har = torch.tanh(F.linear(sine, sd["dec.m_source.l_linear.weight"], sd["dec.m_source.l_linear.bias"])).transpose(1, 2)
     x = F.conv1d(z, sd["dec.conv_pre.weight"], sd["dec.conv_pre.bias"], padding=3)
     x = x + F.conv1d(g, sd["dec.cond.weight"], sd["dec.cond.bias"])
     nk = len(rb_k)
     for i, (u, k) in enumerate(zip(up_r, up_k)):
         x = F.leaky_relu(x, 0.1)
         x = F.conv_transpose1d(x, wn_weight(sd, f"dec.ups.{i}"), sd[f"dec.ups.{i}.bias"], stride=u, padding=(k - u) // 2)
-        if i + 1 < len(up_r):
-            s = int(np.prod(up_r[i + 1:]))
-            xs = F.conv1d(har, sd[f"dec.noise_convs.{i}.weight"], sd[f"dec.noise_convs.{i}.bias"], stride=s, padding=s // 2)
-        else:
-            xs = F.conv1d(har, sd[f"dec.noise_convs.{i}.weight"], sd[f"dec.noise_convs.{i}.bias"])
-        x = x + xs
+        if nsf:
+            if i + 1 < len(up_r):
+                s = int(np.prod(up_r[i + 1:]))
+                xs = F.conv1d(har, sd[f"dec.noise_convs.{i}.weight"], sd[f"dec.noise_convs.{i}.bias"], stride=s, padding=s // 2)
+            else:
+                xs = F.conv1d(har, sd[f"dec.noise_convs.{i}.weight"], sd[f"dec.noise_convs.{i}.bias"])
+            x = x + xs
         acc = None
         for j in range(nk):
             r = resblock1(sd, f"dec.resblocks.{i * nk + j}.", x, rb_k[j], rb_d[j])
@@ -184,7 +187,8 @@ def generator(sd: SD, z, f0, g, cfg, noise):
 
 
 def infer(cpt: dict, phone, pitch, nsff0, sid, noise_z, noise_src, return_all: bool = False):
-    """SynthesizerTrnMs{256,768}NSFsid.infer (models.py:745-751).
+    """SynthesizerTrnMs{256,768}NSFsid.infer (models.py:634-640, 745-751) and, with pitch = nsff0 = None, the
+    `_nono` variants (models.py:847-853, 949-955: no pitch embedding, plain HiFi-GAN `Generator`).
     phone [1,P,768|256] f32, pitch [1,P] i64, nsff0 [1,P] f32, sid [1] i64,
     noise_z [1,192,P] (the randn_like of line 748), noise_src [1,P*upp,1] (line 368). -> [1,1,P*upp]."""
     sd = {k: v.float() if v.is_floating_point() else v for k, v in cpt["weight"].items()}

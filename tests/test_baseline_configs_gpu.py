@@ -1,0 +1,230 @@
+"""GPU parity at the sizes BASELINE.json / SURVEY.md §8(d) name (round-1 tests ran shrunken versions of cfg 3 / cfg 4):
+
+  cfg 3  full `VC.pipeline` on a 60 s vocal with rvc.Config's own (3, 10, 60, 65), IVF2237 x 87 243 index, index_rate 0.5
+  cfg 4  one whole 4-minute 44.1 kHz stereo MDX sweep (Kim_Vocal_2 geometry), checked on sampled chunks + exact chunk count
+  cfg 5  the benchmarked stage graph itself (`CoverEngine`: 3 MDX passes -> mono 16 k -> VC.pipeline -> mix), every stage
+         hand-off checked against the oracle applied to the SAME input that stage received on the device
+
+Bars (north_star): coarse F0 indices bit-exact, fp32 waveforms within 1e-3 RMS (absolute, on [-1, 1] audio).
+Synthetic checkpoints are the "trained-like" ones (BatchNorm statistics fitted, smooth single-peak rmvpe salience).
+"""
+import os
+import sys
+import tempfile
+import time
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from siggen import song_44k, vocal_like  # noqa: E402
+
+from aicovergen_b200.synthetic import (make_hubert_state_dict, make_ivf_index_data, make_mdx_trained_like,  # noqa: E402
+                                       make_rmvpe_trained_like, make_rvc_checkpoint)
+
+pytestmark = pytest.mark.gpu
+
+
+def rms(x):
+    return float(np.sqrt(np.mean(np.asarray(x, dtype=np.float64) ** 2)))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def test_cfg3_vc_pipeline_60s_with_ivf2237_index():
+    """SURVEY.md §8 canonical sizes: 960 000 samples -> no split -> one vc() on 1 056 000 samples -> HuBERT T=3299 ->
+    6598 frames -> 2 399 200 output samples."""
+    from aicovergen_b200 import rvc
+    from aicovergen_b200.faiss_io import write_ivfflat
+    from oracle import hubert as ohub
+    from oracle import pipeline as opipe
+    from oracle.index import IvfFlatIndex
+
+    cfg = rvc.Config("cuda:0", True)
+    assert (cfg.x_pad, cfg.x_query, cfg.x_center, cfg.x_max) == (3, 10, 60, 65) and cfg.is_half          # rvc.py:76-81
+    hsd, rsd, cpt = make_hubert_state_dict(), make_rmvpe_trained_like(), make_rvc_checkpoint("40k", "v2")
+    audio = vocal_like(60.0, seed=7)
+    assert audio.shape == (960000,)
+    t0 = time.time()
+    base = ohub.extract_features(hsd, torch.from_numpy(vocal_like(20.0, seed=3))[None], 12)[0]
+    cent, vecs = make_ivf_index_data(base, n_total=87243, nlist=2237, lloyd=False)        # README's added_IVF2237_Flat example
+    index = IvfFlatIndex(cent, vecs)
+    sizes = np.bincount(index.assign, minlength=2237)
+    tmp = tempfile.NamedTemporaryFile(suffix="_added_IVF2237_Flat_nprobe_1_v2.index", delete=False)
+    tmp.close()
+    write_ivfflat(tmp.name, cent, vecs, index.assign)
+    ref_i16, info = opipe.pipeline(hsd, cpt, rsd, audio.copy(), index=index, seed=5, return_all=True)
+    t_cpu = time.time() - t0
+
+    hubert = rvc.load_hubert("cuda:0", cfg.is_half, {"model": hsd})
+    cpt2, version, net_g, tgt_sr, vc = rvc.get_vc("cuda:0", cfg.is_half, cfg, dict(cpt))
+    assert version == "v2" and tgt_sr == 40000
+    from aicovergen_b200.rmvpe import RMVPEB200
+    vc.model_rmvpe = RMVPEB200(rsd, device="cuda:0")
+    vc.set_noise_seed(5)
+    vc.keep_float = True
+    try:
+        out = vc.pipeline(hubert, net_g, 0, audio.copy(), "x.wav", [0, 0, 0], 0, "rmvpe", tmp.name, 0.5, 1, 3, tgt_sr, 0, 0.25,
+                          version, 0.33, 128)
+    finally:
+        os.unlink(tmp.name)
+    assert info["opt_ts"] == [], "60 s must not be cut (960 160 < t_max)"
+    assert out.dtype == np.int16 and out.shape == ref_i16.shape == (2399200,)
+    from scipy import signal
+    pad = np.pad(signal.filtfilt(opipe.bh, opipe.ah, audio), (48000, 48000), mode="reflect")
+    pitch, pitchf = vc.get_f0("x.wav", pad, len(pad) // 160, 0, "rmvpe", 3, 128)
+    p_len = len(pad) // 160
+    assert p_len == 6600
+    mism = int((pitch[:p_len] != info["pitch"]).sum())
+    voiced = float((info["pitchf"] > 0).mean())
+    e = rms(vc.last_float_output.astype(np.float64) - info["float_out"])
+    d16 = np.abs(out.astype(np.int32) - ref_i16.astype(np.int32))
+    print(f"[cfg3 60 s] oracle {t_cpu:.0f} s CPU; lists {int((sizes == 0).sum())} empty / min {sizes.min()} / max {sizes.max()}; coarse-pitch "
+          f"mismatches {mism}/{p_len} (voiced {voiced:.2f}, {len(np.unique(info['pitch']))} distinct levels); float waveform abs rms err {e:.3e} "
+          f"(ref rms {rms(info['float_out']):.3e}); int16 max diff {d16.max()} rms {np.sqrt((d16.astype(float) ** 2).mean()):.2f}")
+    assert np.isfinite(info["float_out"]).all() and np.isfinite(vc.last_float_output).all()
+    assert 0.2 < voiced < 0.98 and len(np.unique(info["pitch"])) > 20, "F0 track must exercise voiced and unvoiced frames"
+    assert mism == 0
+    assert e < 1e-3
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def test_cfg4_mdx_4min_sweep_sampled_chunks():
+    """run_mdx arithmetic on a 4-min stereo song (10 584 000 samples/channel): 2 halves x 22 chunks = 44 network calls per
+    sweep.  The oracle recomputes 8 sampled chunks end to end (pad_wave -> STFT -> net -> iSTFT -> trim) and
+    the test places them with the reference's own segment / [:-pad] / margin arithmetic (mdx.py:107-117, 143-171, 195-197)."""
+    from aicovergen_b200 import _ffi
+    from aicovergen_b200.mdx import MDX, MDXModel, run_mdx_arrays
+    from oracle import mdx as om
+
+    dim_f, dim_t, n_fft, comp = 3072, 256, 7680, 1.009           # Kim_Vocal_2 class (model_data.json)
+    sd = make_mdx_trained_like(dim_f, dim_t, n_fft)
+    wave = song_44k(240.0, seed=0)
+    n = wave.shape[1]
+    assert n == 10584000
+    sess = MDX(sd, MDXModel("cuda:0", dim_f, dim_t, n_fft, stem_name="Vocals", compensation=comp), 0)
+    l0 = _ffi.launch_count()
+    main, inv = run_mdx_arrays(sess, wave, denoise=False, m_threads=2)
+    # exact chunk count: the first / final conv row kernels run once per network call of batch 11
+    assert main.shape == inv.shape == wave.shape and np.isfinite(main).all() and np.isfinite(inv).all()
+    mp = om.MdxParams(dim_f, dim_t, n_fft, stem_name="Vocals", compensation=comp)
+    net = lambda s: om.convtdfnet(sd, s)  # noqa: E731
+    peak = max(np.max(wave), abs(np.min(wave)))
+    wn = wave / peak
+    halves = om.segment_split(wn, n // 2)
+    assert len(halves) == 2 and halves[0].shape[1] == n // 2 + 44100
+    trim, gen = n_fft // 2, mp.chunk_size - n_fft
+    rng = np.random.default_rng(1)
+    worst, count = 0.0, 0
+    for h, half in enumerate(halves):
+        mix, pad, _ = om.pad_wave(half, mp)
+        assert mix.shape[0] == 22, "22 chunks per half (SURVEY.md §8)"
+        count += mix.shape[0]
+        half_start = 0 if h == 0 else n // 2 - 44100
+        keep_lo = half_start + (0 if h == 0 else 44100)
+        keep_hi = half_start + half.shape[1] - (44100 if h == 0 else 0)
+        for i in sorted(set([0, 21]) | set(rng.choice(22, 2, replace=False).tolist())):
+            w = mp.istft(net(mp.stft(mix[i:i + 1])))[0, :, trim:-trim].numpy() * peak          # [2, gen]
+            a = half_start + i * gen
+            lo, hi = max(a, keep_lo), min(a + gen, keep_hi, half_start + half.shape[1])
+            ref = w[:, lo - a: hi - a]
+            got = main[:, lo:hi]
+            e = rms(got - ref)
+            worst = max(worst, e)
+            print(f"[cfg4 4-min] half {h} chunk {i:2d}: abs rms err {e:.3e} (ref rms {rms(ref):.3e}, rel {e / max(rms(ref), 1e-12):.2e})")
+            assert e < 1e-3
+            ref_inv = -ref * comp + wn[:, lo:hi]
+            assert rms(inv[:, lo:hi] - ref_inv) < 1e-3
+    assert count == 44
+    print(f"[cfg4 4-min] worst sampled-chunk abs rms err {worst:.3e}; stem rms {rms(main):.3e}; launches {_ffi.launch_count() - l0}")
+    assert rms(main) > 1e-3, "silent stem"
+
+    # denoise=True (what main.py:182 uses): 0.5 * (P(w) - P(-w)), 88 network calls; 2 chunks
+    main_d, _ = run_mdx_arrays(sess, wave, denoise=True, m_threads=2)
+    mix, pad, _ = om.pad_wave(halves[1], mp)
+    for i in (3, 20):
+        x = mix[i:i + 1]
+        wp = mp.istft(net(mp.stft(x)))[0, :, trim:-trim].numpy()
+        wm = mp.istft(net(mp.stft(-x)))[0, :, trim:-trim].numpy()
+        ref = 0.5 * (wp - wm) * peak
+        a = n // 2 - 44100 + i * gen
+        lo, hi = max(a, n // 2), min(a + gen, n)
+        e = rms(main_d[:, lo:hi] - ref[:, lo - a: hi - a])
+        print(f"[cfg4 4-min denoise] half 1 chunk {i}: abs rms err {e:.3e}")
+        assert e < 1e-3
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def test_cover_engine_stage_handoffs_30s():
+    """The graph bench.py times (CoverEngine.cover): every stage output is compared with the oracle applied to the input
+    that stage received on the device, so each hand-off is checked on identical inputs and the wiring (which stem feeds
+    which stage, main.py:166-203) is checked by construction."""
+    from aicovergen_b200 import ops
+    from aicovergen_b200.index import write_index_npz
+    from aicovergen_b200.main import MDX_STAGES, CoverEngine, db_gain
+    from oracle import dsp as odsp
+    from oracle import hubert as ohub
+    from oracle import mdx as om
+    from oracle import pipeline as opipe
+    from oracle.index import IvfFlatIndex
+
+    hsd, rsd, cpt = make_hubert_state_dict(), make_rmvpe_trained_like(), make_rvc_checkpoint("40k", "v2")
+    mdx_w = [make_mdx_trained_like(s["dim_f"], s["dim_t"], s["n_fft"], seed=2024 + i) for i, s in enumerate(MDX_STAGES)]
+    base = ohub.extract_features(hsd, torch.from_numpy(vocal_like(8.0, seed=3))[None], 12)[0]
+    cent, vecs = make_ivf_index_data(base, n_total=20000, nlist=512, lloyd=False)
+    index = IvfFlatIndex(cent, vecs)
+    tmp = tempfile.NamedTemporaryFile(suffix=".npz", delete=False)
+    tmp.close()
+    write_index_npz(tmp.name, cent, vecs)
+    eng = CoverEngine(mdx_w, hsd, rsd, cpt, index=tmp.name, device="cuda:0")
+    song = song_44k(30.0, seed=1)
+    song_dev = torch.from_numpy(song).cuda()
+    stems = {k: v.cpu().numpy() for k, v in eng.separate(song_dev).items()}
+    nets = [(om.MdxParams(s["dim_f"], s["dim_t"], s["n_fft"], stem_name=s["stem"], compensation=s["compensate"]),
+             (lambda sd: (lambda x: om.convtdfnet(sd, x)))(w)) for s, w in zip(MDX_STAGES, mdx_w)]
+    # stage 1: song -> vocals (main stem), instrumental (inverse)         main.py:171-172
+    voc, inst = om.run_mdx_arrays(song, nets[0][0], nets[0][1], denoise=True, m_threads=2)
+    # stage 2: vocals -> backup (main), main vocals (inverse)              main.py:175-176
+    bak, mainv = om.run_mdx_arrays(stems["vocals"], nets[1][0], nets[1][1], denoise=True, m_threads=2)
+    # stage 3: main vocals -> (discarded), de-reverbed (inverse)           main.py:181-182
+    _, derev = om.run_mdx_arrays(stems["main"], nets[2][0], nets[2][1], denoise=True, m_threads=2)
+    for name, ref in (("vocals", voc), ("instrumental", inst), ("backup", bak), ("main", mainv), ("dereverb", derev)):
+        e = rms(stems[name] - ref)
+        print(f"[cover 30 s] {name:13s} abs rms err {e:.3e} (ref rms {rms(ref):.3e})")
+        assert np.isfinite(stems[name]).all() and rms(ref) > 1e-3
+        assert e < 1e-3, name
+    # ingest stand-in: stereo 44.1 k -> mono 16 k
+    d = torch.from_numpy(stems["dereverb"]).cuda()
+    n16 = int(d.shape[1] * 16000 // 44100)
+    mono = torch.empty(n16, device="cuda")
+    ops.resample_sinc_mono(d.contiguous(), mono, 44100, 16000)
+    mono_h = mono.cpu().numpy()
+    e = rms(mono_h - odsp.resample_sinc_mono(stems["dereverb"], n16, 44100, 16000))
+    print(f"[cover 30 s] resample      abs rms err {e:.3e} (rms {rms(mono_h):.3e})")
+    assert e < 1e-5
+    # RVC on the device-resampled vocal
+    eng.vc.set_noise_seed(5)
+    eng.vc.keep_float = True
+    ai = eng.convert(d)
+    ref_i16, info = opipe.pipeline(hsd, cpt, rsd, mono_h.copy(), index=index, seed=5, return_all=True)
+    os.unlink(tmp.name)
+    from scipy import signal
+    pad = np.pad(signal.filtfilt(opipe.bh, opipe.ah, mono_h), (48000, 48000), mode="reflect")
+    pitch, _ = eng.vc.get_f0("x", pad, len(pad) // 160, 0, "rmvpe", 3, 128)
+    mism = int((pitch[:len(info["pitch"])] != info["pitch"]).sum())
+    e = rms(eng.vc.last_float_output.astype(np.float64) - info["float_out"])
+    print(f"[cover 30 s] VC.pipeline   coarse-pitch mismatches {mism}/{len(info['pitch'])}; float waveform abs rms err {e:.3e} "
+          f"(ref rms {rms(info['float_out']):.3e}); voiced {float((info['pitchf'] > 0).mean()):.2f}")
+    assert ai.shape == ref_i16.shape and mism == 0 and e < 1e-3
+    # mix stand-in
+    cover = eng.mix(ai, torch.from_numpy(stems["backup"]).cuda(), torch.from_numpy(stems["instrumental"]).cuda()).cpu().numpy()
+    ref_mix = odsp.mix3(ai.astype(np.float32) / 32768.0, 40000, stems["backup"], stems["instrumental"], 44100,
+                        db_gain(-4), db_gain(-6), db_gain(-7))
+    e = rms(cover - ref_mix)
+    print(f"[cover 30 s] mix           abs rms err {e:.3e} (rms {rms(ref_mix):.3e})")
+    assert e < 1e-5
+    # and the one-call form produces the same cover from the same song (device noise draws differ: seed again)
+    eng.vc.set_noise_seed(5)
+    full = eng.cover(song)
+    assert full.shape == cover.shape and np.isfinite(full).all()
+    assert rms(full - cover) < 1e-6

