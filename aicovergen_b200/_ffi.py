@@ -96,6 +96,8 @@ def _declare(lib):
     lib.b200vc_last_error.restype = C.c_char_p
     lib.b200vc_launch_count.restype = C.c_int64
     lib.b200vc_sizeof_tapgemm_params.restype = C.c_int64
+    lib.b200vc_count_launches.argtypes = [C.c_int64]
+    lib.b200vc_count_launches.restype = None
     if lib.b200vc_sizeof_tapgemm_params() != C.sizeof(TapGemmParams):
         raise RuntimeError(
             f"ABI mismatch: sizeof(b200vc_tapgemm_params)={lib.b200vc_sizeof_tapgemm_params()} "

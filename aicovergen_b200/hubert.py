@@ -15,7 +15,7 @@ import torch
 
 from . import _ffi, ops
 from . import tapgemm as tg
-from .plans import PlanCache
+from .plans import PlanCache, StepGraph
 from .synth import round_tf32
 from .tapgemm import Epi
 
@@ -190,10 +190,10 @@ class _HubertPlan:
             add(lambda i=i: ops.layernorm(tmp, W[f"l{i}.ln2.g"], W[f"l{i}.ln2.b"], x))
         self.x = x
         self.steps = steps
+        self.graph = StepGraph(steps)
         self.L = L
 
     def run(self, source: torch.Tensor) -> torch.Tensor:
         self.wav[:self.L].copy_(source.reshape(-1))
-        for st in self.steps:
-            st()
+        self.graph()
         return self.x.view(1, self.T, -1)

@@ -26,6 +26,7 @@ from scipy.io import wavfile
 
 from . import _ffi, ops
 from . import tapgemm as tg
+from .plans import StepGraph
 from .synth import round_tf32
 from .tapgemm import Epi
 
@@ -296,10 +297,10 @@ class _NetPlan:
         # ---- final conv (1x1, g -> 4) writing [B, ch, T, F, ri]: pointwise, read-bound -> its own row kernel
         add(lambda x=x: ops.mdx_final_conv(x, W["final.w"], W["final.b"], self.spec_out, R))
         self.steps = steps
+        self.graph = StepGraph(steps)
 
     def run(self):
-        for st in self.steps:
-            st()
+        self.graph()
 
 
 def shard_range(n_items: int, rank: int, world: int):
@@ -371,6 +372,7 @@ class MDX:
         self.process = lambda spec: self.ort.run(None, {"input": spec.cpu().numpy()})[0]
         self.prog = None
         self._io = None
+        self._desc_cache = {}
 
     @staticmethod
     def get_hash(model_path):
@@ -412,13 +414,26 @@ class MDX:
         independent, mdx.py:190-196); the caller sums the per-rank outputs (each sample is written by exactly one chunk)."""
         m, dev = self.model, self.device
         n = wave_dev.shape[1]
-        src, lo, hi, dst, klo, khi = self._descriptors(n, mt_threads)
-        c_lo, c_hi = shard_range(len(src), shard[0], shard[1])
-        src, lo, hi, dst, klo, khi = (v[c_lo:c_hi] for v in (src, lo, hi, dst, klo, khi))
-        nchunks = len(src)
+        # chunk descriptors of the whole sweep: built and uploaded ONCE per (song length, split, shard), padded to whole
+        # batches with dummy chunks that read nothing (lo == hi) and keep nothing
+        key = (n, mt_threads, tuple(shard))
+        ent = self._desc_cache.get(key)
+        if ent is None:
+            desc = self._descriptors(n, mt_threads)
+            c_lo, c_hi = shard_range(len(desc[0]), shard[0], shard[1])
+            nchunks = c_hi - c_lo
+            B = min(self.BATCH, max(nchunks, 1))
+            padded_n = -(-nchunks // B) * B
+            host = np.zeros((6, max(padded_n, 1)), dtype=np.int64)
+            for r, v in enumerate(desc):
+                host[r, :nchunks] = v[c_lo:c_hi]
+            ent = (nchunks, B, torch.from_numpy(host).to(dev))
+            if len(self._desc_cache) >= 8:
+                self._desc_cache.pop(next(iter(self._desc_cache)))
+            self._desc_cache[key] = ent
+        nchunks, B, ddev = ent
         if nchunks == 0:
             return
-        B = min(self.BATCH, nchunks)
         R = self.backend == tg.BACKEND_TC
         fwd, inv, env = m.dft(R)
         pl = self.ort.plan(B)
@@ -428,23 +443,15 @@ class MDX:
             frames = torch.empty(B, 2, m.dim_t, m.n_fft, device=dev)
             stft = _stft_gemm(padded, fwd, pl.spec_in, m, self.backend)
             istft = tg.linear(pl.spec_out.view(-1, 2 * m.dim_f), inv, frames.view(-1, m.n_fft), None, self.backend, name="mdx.istft")
-            self._io = (pl, padded, frames, stft, istft)
-        _, padded, frames, stft, istft = self._io
+            # STFT -> U-Net -> iSTFT of one chunk batch as ONE replayable launch sequence (see plans.StepGraph)
+            self._io = (pl, padded, frames, StepGraph([stft, *pl.steps, istft]))
+        _, padded, frames, net_graph = self._io
         trim = m.n_fft // 2
         for s in range(0, nchunks, B):
             e = min(s + B, nchunks)
-
-            def desc(a, fill):
-                v = np.full(B, fill, dtype=np.int64)
-                v[: e - s] = a[s:e]
-                return torch.from_numpy(v).to(dev)
-
-            d_src, d_lo, d_hi = desc(src, 0), desc(lo, 0), desc(hi, 0)          # dummy chunks read nothing (lo == hi)
-            d_dst, d_klo, d_khi = desc(dst, 0), desc(klo, 0), desc(khi, 0)      # ... and keep nothing
+            d_src, d_lo, d_hi, d_dst, d_klo, d_khi = (ddev[r, s:s + B] for r in range(6))
             ops.mdx_gather_chunks(wave_dev, d_src, d_lo, d_hi, padded, m.chunk_size, trim, sign, R)
-            stft()
-            pl.run()
-            istft()
+            net_graph()
             ops.mdx_ola_store(frames, env, d_dst, d_klo, d_khi, out_dev, m.dim_t, m.n_fft, m.hop, m.chunk_size, trim,
                               coef, accumulate)
             if self.prog is not None:
@@ -504,7 +511,7 @@ def run_mdx_device(mdx_sess: MDX, wave_dev: torch.Tensor, denoise=False, m_threa
 
 def _run_mdx_device(mdx_sess: MDX, wave_dev: torch.Tensor, denoise, m_threads, group):
     model = mdx_sess.model
-    peak = float(torch.maximum(wave_dev.max(), wave_dev.min().abs()).item())       # max(np.max(w), abs(np.min(w)))
+    peak = torch.maximum(wave_dev.max(), wave_dev.min().abs())       # max(np.max(w), abs(np.min(w))), kept on the device: no host sync
     w = (wave_dev / peak).contiguous()
     proc = torch.zeros_like(w)
     shard = (0, 1)
@@ -521,7 +528,8 @@ def _run_mdx_device(mdx_sess: MDX, wave_dev: torch.Tensor, denoise, m_threads, g
         # so one NCCL sum over NVLink reassembles the stem on all ranks
         dist.all_reduce(proc, group=group)
     inverse = torch.empty_like(w)
-    ops.mdx_finalize(proc, w, inverse, peak, model.compensation)
+    proc.mul_(peak)                                                   # wave_processed *= peak (mdx.py:267)
+    ops.mdx_finalize(proc, w, inverse, 1.0, model.compensation)       # inverse = -proc * compensation + wave_norm (mdx.py:280)
     return proc, inverse
 
 

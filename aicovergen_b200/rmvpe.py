@@ -17,7 +17,7 @@ import torch
 
 from . import _ffi, ops
 from . import tapgemm as tg
-from .plans import PlanCache
+from .plans import PlanCache, StepGraph
 from .tapgemm import Epi
 
 BN_EPS = 1e-5
@@ -268,12 +268,12 @@ class _RmvpePlan:
         self.f0 = torch.empty(nf, device=dev, dtype=torch.float64)
         self.cents = torch.empty(nf, device=dev, dtype=torch.float64)
         self.steps = steps
+        self.graph = StepGraph(steps)
 
     def run(self, audio: torch.Tensor):
         self.audio.copy_(audio.reshape(-1))
         self.mel_is_log = False
-        for st in self.steps:
-            st()
+        self.graph()
 
     def run_from_logmel(self, mel_t: torch.Tensor):
         """mel_t [n_frames, 128] log-mel (what MelSpectrogram.forward returns, transposed): skips the front-end."""

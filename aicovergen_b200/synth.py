@@ -19,7 +19,7 @@ import torch
 
 from . import _ffi, ops
 from . import tapgemm as tg
-from .plans import PlanCache
+from .plans import PlanCache, StepGraph
 from .tapgemm import Epi
 
 LRELU = 0.1
@@ -359,6 +359,7 @@ class _Plan:
         self.audio = torch.empty(L, **f32)
         add(lambda prev=prev: ops.conv1d_to1(prev, W["post.w"], self.audio, W["post.w"].shape[0] // 2, tg.ACT_TANH))
         self.steps = steps
+        self.graph = StepGraph(steps)
 
     def run(self, phone, pitch, nsff0, cond, noise_z, noise_src):
         m, P = self.m, self.P
@@ -378,8 +379,7 @@ class _Plan:
         self.pre_b.copy_(cond["pre.b"])
         for (f, j), b in self.in_b.items():
             b.copy_(cond[f"f{f}.in{j}.b"])
-        for st in self.steps:
-            st()
+        self.graph()
         o = self.audio.view(1, 1, -1)
         x_mask = torch.ones(1, 1, P, device=m.device)
         m_p = self.stats[:, :m.inter].t().unsqueeze(0)

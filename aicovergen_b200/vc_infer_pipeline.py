@@ -156,9 +156,10 @@ class VC(object):
             audio_pad = self._reflect_pad(audio64, self.window // 2)
             audio_sum = torch.empty(n, dtype=torch.float64, device=audio64.device)
             ops.boxsum_f64(audio_pad, audio_sum, n, self.window)
-            for t in range(self.t_center, n, self.t_center):
-                seg = audio_sum[t - self.t_query: t + self.t_query].abs()
-                opt_ts.append(t - self.t_query + int(torch.argmin(seg).item()))   # argmin returns the first minimum
+            centers = list(range(self.t_center, n, self.t_center))
+            # first minimum of |sum| in every +-t_query window; ONE device->host copy for all cut points
+            rel = torch.stack([torch.argmin(audio_sum[t - self.t_query: t + self.t_query].abs()) for t in centers]).cpu().tolist()
+            opt_ts = [t - self.t_query + int(r) for t, r in zip(centers, rel)]
         return opt_ts
 
     @_ffi.on_device

@@ -429,8 +429,11 @@ def main():
     sampler.stop()
     # ---- one more step OUTSIDE the timed regions with CUDA events around every tcgen05 tap-GEMM launch (the event
     # pairs perturb launch overlap, so they must not sit inside the step timing): per-kernel-family roofline data
+    from aicovergen_b200 import plans
     install_tc_profiler.enabled = True
+    plans.graphs_enabled(False)            # the event pairs need the eager launch path (graph replays bypass Python)
     prof_ms = timed_loop(lambda: eng.cover_device(song_dev), 1)
+    plans.graphs_enabled(True)
     install_tc_profiler.enabled = False
 
     audio_s = args.seconds * world

@@ -119,6 +119,8 @@ const char* b200vc_version(void);
 const char* b200vc_last_error(void);
 /* number of kernels this library has launched in this process (bench.py: gpu_launches) */
 int64_t b200vc_launch_count(void);
+/* adds n to that counter: a host that replays a captured CUDA graph of this library's launches accounts for them here */
+void b200vc_count_launches(int64_t n);
 /* sizeof(b200vc_tapgemm_params) as compiled: bindings verify their struct mirror against it */
 int64_t b200vc_sizeof_tapgemm_params(void);
 
