@@ -79,6 +79,9 @@ class TapGemmParams(C.Structure):
         ("vec4", C.c_int32),
         ("round_tf32", C.c_int32),
         ("dtype", C.c_int32),
+        ("split", C.c_int32),
+        ("o_split", C.c_int64),
+        ("r_split", C.c_int64),
         ("taps", Tap * MAX_TAPS),
     ]
 

@@ -66,6 +66,27 @@ __global__ void avgpool2x2_kernel(const float* __restrict__ in, float* __restric
   out[e] = 0.25f * (p[0] + p[ldi] + p[(long long)W * ldi] + p[(long long)W * ldi + ldi]);
 }
 
+// the same on 3xTF32 split tensors: x = hi + lo per input pixel, pooled in fp32, written back as hi | lo | hi planes
+__global__ void avgpool2x2_split_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int H, int W, int C,
+                                        long long ldi, long long in_split, long long ldo, long long out_split) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int Ho = H / 2, Wo = W / 2;
+  if (e >= (long long)B * Ho * Wo * C) return;
+  const int c = (int)(e % C);
+  long long r = e / C;
+  const int wo = (int)(r % Wo); r /= Wo;
+  const int ho = (int)(r % Ho);
+  const int b = (int)(r / Ho);
+  const float* p = in + (((long long)b * H + 2 * ho) * W + 2 * wo) * ldi + c;
+  const long long dn = (long long)W * ldi;
+  const float x00 = p[0] + p[in_split], x01 = p[ldi] + p[ldi + in_split];
+  const float x10 = p[dn] + p[dn + in_split], x11 = p[dn + ldi] + p[dn + ldi + in_split];
+  const float v = 0.25f * (x00 + x01 + x10 + x11);
+  const float hi = round_tf32(v);
+  float* o = out + (((long long)b * Ho + ho) * Wo + wo) * ldo + c;
+  o[0] = hi; o[out_split] = round_tf32(v - hi); o[2 * out_split] = hi;
+}
+
 // ---------------------------------------------------------------------------
 // BiGRU recurrence (rmvpe.py:8-20; torch.nn.GRU gate order r,z,n).
 // grid = 2 clusters x CL CTAs; cluster d handles direction d.  CTA `rank` owns hidden units
@@ -257,6 +278,16 @@ int b200vc_avgpool2x2(const float* in, float* out, int B, int H, int W, int C, i
   B200VC_REQUIRE(in && out && B > 0 && H % 2 == 0 && W % 2 == 0 && C > 0, "avgpool2x2: bad args");
   const long long n = (long long)B * (H / 2) * (W / 2) * C;
   avgpool2x2_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(in, out, B, H, W, C, ldi);
+  count_launch();
+  B200VC_LAUNCH_CHECK();
+  return kOk;
+}
+
+int b200vc_avgpool2x2_split(const float* in, float* out, int B, int H, int W, int C, int64_t ldi, int64_t in_split,
+                            int64_t ldo, int64_t out_split, void* stream) {
+  B200VC_REQUIRE(in && out && B > 0 && H % 2 == 0 && W % 2 == 0 && C > 0, "avgpool2x2_split: bad args");
+  const long long n = (long long)B * (H / 2) * (W / 2) * C;
+  avgpool2x2_split_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(in, out, B, H, W, C, ldi, in_split, ldo, out_split);
   count_launch();
   B200VC_LAUNCH_CHECK();
   return kOk;

@@ -72,7 +72,11 @@ __device__ __forceinline__ float tg_epi1(const TgParams& p, const TgRow& r, int 
   if (p.bias) v += p.bias_per_row ? __ldg(p.bias + r.brow) : __ldg(p.bias + n);
   v = apply_act(v, p.act_pre, p.act_pre_p);
   if (p.row_scale) v *= __ldg(p.row_scale + r.brow);
-  if (p.res) { const float rr = tg_ld(p.res, r.r_off + n * p.r_sn, p.dtype & TG_DT_RES); v = (p.res_op & 1) ? v * rr : v + rr; }
+  if (p.res) {
+    float rr = tg_ld(p.res, r.r_off + n * p.r_sn, p.dtype & TG_DT_RES);
+    if (p.split & 2) rr += p.res[r.r_off + n * p.r_sn + p.r_split];      // split residual: hi + lo
+    v = (p.res_op & 1) ? v * rr : v + rr;
+  }
   v *= p.scale;
   if (p.res2) v += tg_ld(p.res2, r.o_off + n * p.o_sn, p.dtype & TG_DT_RES2);
   v = apply_act(v, p.act_post, p.act_post_p);
@@ -83,6 +87,12 @@ __device__ __forceinline__ float tg_epi1(const TgParams& p, const TgRow& r, int 
 __device__ __forceinline__ void tg_store1(const TgParams& p, const TgRow& r, int n, float acc) {
   if (!r.valid || n >= p.N) return;
   float v = tg_epi1(p, r, n, acc);
+  if (p.split & 1) {          // 3xTF32 planes hi | lo | hi
+    const float hi = round_tf32(v);
+    float* o = p.out + r.o_off + n * p.o_sn;
+    o[0] = hi; o[p.o_split] = round_tf32(v - hi); o[2 * p.o_split] = hi;
+    return;
+  }
   tg_st(p.out, r.o_off + n * p.o_sn, (p.round_tf32 & 1) ? round_tf32(v) : v, p.dtype & TG_DT_OUT);
   if (p.out2) {
     float v2 = apply_act(v, p.act2, p.act2_p);
@@ -101,7 +111,7 @@ constexpr int TG_VEC_ALL = TG_VEC_OUT | TG_VEC_BIAS | TG_VEC_OUT2 | TG_VEC_RES;
 // Store 4 consecutive n (n % 4 == 0). Uses float4 when every epilogue tensor is channels-last + aligned and in range.
 __device__ __forceinline__ void tg_store4(const TgParams& p, const TgRow& r, int n, float4 acc) {
   if (!r.valid || n >= p.N) return;
-  if ((p.vec4 & TG_VEC_ALL) == TG_VEC_ALL && n + 3 < p.N && !(p.dtype & TG_DT_EPI)) {
+  if ((p.vec4 & TG_VEC_ALL) == TG_VEC_ALL && n + 3 < p.N && !(p.dtype & TG_DT_EPI) && !p.split) {
     float v[4] = {acc.x, acc.y, acc.z, acc.w};
     if (p.row_scale_pre) {
       const float rs = __ldg(p.row_scale_pre + r.brow);
@@ -324,6 +334,12 @@ __device__ __forceinline__ void tg_store16(const TgParams& p, const TgRow& r, in
     float rr[16];
     if (p.dtype & TG_DT_RES) tg_load16h(rr, reinterpret_cast<const __half*>(p.res) + r.r_off + n * p.r_sn, p.r_sn, (p.vec4 & TG_VEC_RES) != 0);
     else tg_load16(rr, p.res + r.r_off + n * p.r_sn, p.r_sn, (p.vec4 & TG_VEC_RES) != 0, wide);
+    if (p.split & 2) {        // split residual: hi + lo
+      float r2[16];
+      tg_load16(r2, p.res + r.r_off + n * p.r_sn + p.r_split, p.r_sn, (p.vec4 & TG_VEC_RES) != 0, wide);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) rr[j] += r2[j];
+    }
     if (p.res_op & 1) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] *= rr[j];
@@ -345,6 +361,16 @@ __device__ __forceinline__ void tg_store16(const TgParams& p, const TgRow& r, in
     for (int j = 0; j < 16; ++j) v[j] += rr[j];
   }
   tg_act_vec(v, p.act_post, p.act_post_p);
+  if (p.split & 1) {          // 3xTF32 planes hi | lo | hi (fp32, channels-last)
+    float hi[16], lo[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { hi[j] = round_tf32(v[j]); lo[j] = round_tf32(v[j] - hi[j]); }
+    float* o = p.out + r.o_off + n * p.o_sn;
+    tg_put16(o, p.o_sn, vec, false, wide, hi);
+    tg_put16(o + p.o_split, p.o_sn, vec, false, wide, lo);
+    tg_put16(o + 2 * p.o_split, p.o_sn, vec, false, wide, hi);
+    return;
+  }
   if (p.dtype & TG_DT_OUT) tg_put16h(reinterpret_cast<__half*>(p.out) + r.o_off + n * p.o_sn, p.o_sn, vec, v);
   else tg_put16(p.out + r.o_off + n * p.o_sn, p.o_sn, vec, (p.round_tf32 & 1) != 0, wide, v);
   if (p.out2) {

@@ -29,6 +29,7 @@ _ffi.declare("b200vc_reflect_pad_1d", [_P, _P, _i64, _i64, _P])
 _ffi.declare("b200vc_magnitude", [_P, _P, _i64, _i32, _i64, _i64, _P])
 _ffi.declare("b200vc_logmel_affine_reflect", [_P, _P, _i32, _i32, _i32, _f32, _f32, _f32, _P])
 _ffi.declare("b200vc_avgpool2x2", [_P, _P, _i32, _i32, _i32, _i32, _i64, _P])
+_ffi.declare("b200vc_avgpool2x2_split", [_P, _P, _i32, _i32, _i32, _i32, _i64, _i64, _i64, _i64, _P])
 _ffi.declare("b200vc_bigru", [_P, _P, _P, _P, _i32, _i32, _P])
 _ffi.declare("b200vc_rmvpe_decode", [_P, _P, _P, _i32, _i32, _i64, _f32, _P])
 _ffi.declare("b200vc_groupnorm_time", [_P, _P, _P, _P, _P, _i64, _i32, _f32, _i32, _i32, _P])
@@ -178,6 +179,14 @@ def bigru(xp, whh, bhh, out, hidden):
     T = xp.shape[0]
     assert xp.is_contiguous() and whh.is_contiguous() and bhh.is_contiguous() and out.is_contiguous()
     _ffi.check(_ffi.lib().b200vc_bigru(_p(_f32c(xp)), _p(whh), _p(bhh), _p(out), T, hidden, _s()), "bigru")
+
+
+def avgpool2x2_split(x, in_split, out, out_split):
+    """3xTF32 split tensors: x / out are the plane-0 views [B,H,W,C] / [B,H/2,W/2,C] (pixel pitches from the strides)."""
+    B, H, W, Cc = x.shape
+    assert x.stride(3) == 1 and x.stride(1) == W * x.stride(2) and out.stride(3) == 1 and out.stride(1) == (W // 2) * out.stride(2)
+    _ffi.check(_ffi.lib().b200vc_avgpool2x2_split(_p(_f32c(x)), _p(out), B, H, W, Cc, x.stride(2), in_split, out.stride(2),
+                                                  out_split, _s()), "avgpool2x2_split")
 
 
 def rmvpe_decode(sal, f0, T, thred, cents=None):

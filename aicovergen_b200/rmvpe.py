@@ -3,9 +3,11 @@
 
 log-mel front-end as a windowed-DFT GEMM, the DeepUnet as NHWC tap-GEMM convolutions with
 BatchNorm folded into the weights, the BiGRU as a cluster kernel, and the cents decode in the
-reference's numpy summation order — all through libb200vc.so.  Default backend is the exact
-fp32 SIMT GEMM: the decoded F0 feeds an argmax / coarse-pitch quantiser whose indices must
-match the reference bit for bit (BASELINE.json north_star), so TF32 is opt-in here.
+reference's numpy summation order — all through libb200vc.so.  The decoded F0 feeds an argmax /
+coarse-pitch quantiser whose indices must match the reference bit for bit (BASELINE.json
+north_star), so the U-Net runs on tcgen05 with 3xTF32 split operands (fp32-level accuracy, ~2^-22
+relative) rather than plain TF32; the front-end DFT, the GRU projections and the salience head
+stay on the exact-fp32 kernel, which is also available for the whole net (backend=BACKEND_SIMT).
 """
 from __future__ import annotations
 
@@ -56,10 +58,43 @@ def _fold_bn(w: torch.Tensor, sd, p: str, out_dim: int = 0):
     return w.float() * s.reshape(shape), b - mu * s
 
 
+def split3_weights(wp: torch.Tensor) -> torch.Tensor:
+    """[taps, N, K] fp32 -> [taps, N, 3K] = [W_hi | W_hi | W_lo] (hi = RN_tf32(W), lo = RN_tf32(W - hi)): the weight side of the
+    3xTF32 scheme; the activation side is stored [hi | lo | hi] by the producing epilogue (b200vc.h `split`)."""
+    from .synth import round_tf32
+    w = wp.float().contiguous()
+    hi = round_tf32(w)
+    lo = round_tf32((w - hi).contiguous())
+    return torch.cat([hi, hi, lo], dim=-1).contiguous()
+
+
+class _Sp:
+    """3xTF32 split activation: planes hi | lo | hi, each `Ct` channels wide, inside t [1, H, W, 3*Ct]; the handle addresses
+    columns [col, col + C) of every plane (sub-handles let two producers fill one concat buffer)."""
+
+    def __init__(self, H, W, Ct, dev, t=None, col=0, C=None):
+        self.t = t if t is not None else torch.empty(1, H, W, 3 * Ct, device=dev, dtype=torch.float32)
+        self.H, self.W, self.Ct, self.col, self.C = H, W, Ct, col, (Ct if C is None else C)
+
+    def sub(self, col, C):
+        return _Sp(self.H, self.W, self.Ct, None, self.t, col, C)
+
+    @property
+    def plane0(self):
+        return self.t[..., self.col:self.col + self.C]
+
+    @property
+    def gemm_in(self):
+        assert self.col == 0 and self.C == self.Ct
+        return self.t
+
+
 class RMVPEB200:
-    def __init__(self, model, is_half: bool = False, device: str = "cuda:0", backend: int = tg.BACKEND_SIMT,
+    def __init__(self, model, is_half: bool = False, device: str = "cuda:0", backend: int = tg.BACKEND_TC,
                  n_blocks: int = 4, n_enc: int = 5, n_inter: int = 4):
-        """`model`: path to rmvpe.pt or an already-loaded state dict (E2E(4,1,(2,2)) names)."""
+        """`model`: path to rmvpe.pt or an already-loaded state dict (E2E(4,1,(2,2)) names).
+        backend = BACKEND_TC (default): the U-Net's convolutions run on tcgen05 as 3xTF32 split-operand GEMMs (fp32-level
+        accuracy, see split3_weights); BACKEND_SIMT: everything on the exact-fp32 FMA kernel (cross-check)."""
         sd = torch.load(model, map_location="cpu") if isinstance(model, (str, bytes)) or hasattr(model, "__fspath__") else model
         self.device = torch.device(device)
         self.is_half = is_half          # kept for interface parity; arithmetic is fp32 (or TF32 if backend=TC)
@@ -80,6 +115,10 @@ class RMVPEB200:
         if p + "shortcut.weight" in sd:
             W[key + ".ws"] = self._dev(sd[p + "shortcut.weight"][:, :, 0, 0])
             W[key + ".bs"] = self._dev(sd[p + "shortcut.bias"])
+        if self.backend == tg.BACKEND_TC:
+            for nm in (".w1", ".w2", ".ws"):
+                if key + nm in W and W[key + nm].shape[-1] >= 4:
+                    W[key + nm + "s"] = split3_weights(W[key + nm])
 
     def _load(self, sd):
         self.W = W = {}
@@ -106,9 +145,12 @@ class RMVPEB200:
             p = f"unet.decoder.layers.{i}."
             wt, bt = _fold_bn(sd[p + "conv1.0.weight"], sd, p + "conv1.1", out_dim=1)
             W[f"dec{i}.up.w"], W[f"dec{i}.up.b"] = self._dev(tg.pack_convt2d(wt)), self._dev(bt)
+            if self.backend == tg.BACKEND_TC:
+                W[f"dec{i}.up.ws"] = split3_weights(W[f"dec{i}.up.w"])
             for b in range(self.n_blocks):
                 self._block_weights(sd, p + f"conv2.{b}.", f"dec{i}.{b}")
         W["cnn.w"], W["cnn.b"] = self._dev(tg.pack_conv2d(sd["cnn.weight"])), self._dev(sd["cnn.bias"])
+        W["cnn.w2"] = torch.cat([W["cnn.w"], W["cnn.w"]], dim=-1).contiguous()      # split input: x = hi + lo, exact-fp32 kernel
         # GRU: input features arrive as (w, c) = w*3 + c (NHWC flatten); the reference uses c*128 + w
         Hh = sd["fc.0.gru.weight_hh_l0"].shape[1]
         self.hidden = Hh
@@ -186,7 +228,6 @@ class RMVPEB200:
 class _RmvpePlan:
     def __init__(self, m: RMVPEB200, n_samples: int):
         dev, W, be = m.device, m.W, m.backend
-        R = be == tg.BACKEND_TC
         f32 = dict(device=dev, dtype=torch.float32)
         steps: List = []
         add = steps.append
@@ -202,62 +243,99 @@ class _RmvpePlan:
         # ---- log-mel: frames (overlapping rows, stride HOP) x windowed DFT basis, magnitude, mel GEMM
         spec = torch.empty(nf, 2 * (N_FFT // 2 + 1), **f32)
         frames = tg.View(padded, (N_FFT, nf, 1, 1, 1), (1, HOP, 0, 0, 0))
-        add(tg.TapGemm(frames, tg.weights(W["dft"]), [(0, 0, 0, 0, 0)], (nf, 1, 1), tg.out_of(spec), None, be, name="stft"))
+        add(tg.TapGemm(frames, tg.weights(W["dft"]), [(0, 0, 0, 0, 0)], (nf, 1, 1), tg.out_of(spec), None, tg.BACKEND_SIMT, name="stft"))
         mag = torch.empty(nf, 516, **f32)
         add(lambda: ops.magnitude(spec, mag, N_FFT // 2 + 1))
         melp = torch.empty(nf, N_MELS, **f32)
-        add(tg.linear(mag, W["mel"], melp, None, be, name="mel"))
+        add(tg.linear(mag, W["mel"], melp, None, tg.BACKEND_SIMT, name="mel"))
         img = torch.empty(1, T, N_MELS, 1, **f32)        # NHWC: H = frames, W = mel bins, C = 1
         self.n_front = len(steps)                        # steps before this one build `melp` from audio
-        self.melp, self.mel_is_log = melp, False
+        self.melp, self.mel_is_log, self.img = melp, False, img
         add(lambda: ops.logmel_affine_reflect(melp, img.view(T, N_MELS), nf, -1.0 if self.mel_is_log else 1e-5, m.bn_a, m.bn_b))
 
-        def block(x, key, out, cin, cout, H_, W_):
-            t1 = torch.empty(1, H_, W_, cout, **f32)
-            add(tg.conv2d(x, W[key + ".w1"], t1, 3, 3, (1, 1), Epi(bias=W[key + ".b1"], act_pre=tg.ACT_RELU, round_out=R), be, name=key + ".c1"))
+        S = be == tg.BACKEND_TC          # tensor-core path = 3xTF32 split operands; everything else exact-fp32 SIMT
+        ex = tg.BACKEND_SIMT
+
+        def new(H_, W_, C_):
+            return _Sp(H_, W_, C_, dev) if S else torch.empty(1, H_, W_, C_, **f32)
+
+        def block(x, key, out, H_, W_, cout):
+            """ConvBlockRes (rmvpe.py:23-58).  x / out: _Sp handles on the tensor-core path (x is the plain 1-channel image for
+            the very first block), plain NHWC tensors on the SIMT path."""
+            t1 = new(H_, W_, cout)
+            b1, b2 = W[key + ".b1"], W[key + ".b2"]
+            if not S:
+                add(tg.conv2d(x, W[key + ".w1"], t1, 3, 3, (1, 1), Epi(bias=b1, act_pre=tg.ACT_RELU), ex, name=key + ".c1"))
+                sc = x
+                if key + ".ws" in W:
+                    sc = torch.empty(1, H_, W_, cout, **f32)
+                    add(tg.linear(x, W[key + ".ws"], sc, Epi(bias=W[key + ".bs"]), ex, name=key + ".sc"))
+                add(tg.conv2d(t1, W[key + ".w2"], out, 3, 3, (1, 1), Epi(bias=b2, act_pre=tg.ACT_RELU, res=sc), ex, name=key + ".c2"))
+                return
+            first = not isinstance(x, _Sp)       # Cin = 1: not TMA-addressable, stays on the exact-fp32 kernel
+            xin = x if first else x.gemm_in
+            add(tg.conv2d(xin, W[key + (".w1" if first else ".w1s")], t1.plane0, 3, 3, (1, 1),
+                          Epi(bias=b1, act_pre=tg.ACT_RELU, split_out=t1.Ct), ex if first else be, name=key + ".c1"))
             if key + ".ws" in W:
                 sc = torch.empty(1, H_, W_, cout, **f32)
-                add(tg.linear(x, W[key + ".ws"], sc, Epi(bias=W[key + ".bs"]), be, name=key + ".sc"))
+                add(tg.linear(xin, W[key + (".ws" if first else ".wss")], sc, Epi(bias=W[key + ".bs"]), ex if first else be, name=key + ".sc"))
+                epi2 = Epi(bias=b2, act_pre=tg.ACT_RELU, res=sc, split_out=out.Ct)
             else:
-                sc = x
-            add(tg.conv2d(t1, W[key + ".w2"], out, 3, 3, (1, 1), Epi(bias=W[key + ".b2"], act_pre=tg.ACT_RELU, res=sc), be, name=key + ".c2"))
+                epi2 = Epi(bias=b2, act_pre=tg.ACT_RELU, res=x.plane0, res_split=x.Ct, split_out=out.Ct)
+            add(tg.conv2d(t1.gemm_in, W[key + ".w2s"], out.plane0, 3, 3, (1, 1), epi2, be, name=key + ".c2"))
 
         # ---- encoder (rmvpe.py:61-119): level output goes straight into the decoder's concat buffer
         x = img
-        H_, W_, cin, cout = T, N_MELS, 1, 16
+        H_, W_, cout = T, N_MELS, int(W["enc0.0.w1"].shape[1])
         cats = []
         for i in range(m.n_enc):
-            cat = torch.empty(1, H_, W_, 2 * cout, **f32)
+            cat = new(H_, W_, 2 * cout)
             cats.append((cat, H_, W_, cout))
             for b in range(m.n_blocks):
                 last = b == m.n_blocks - 1
-                out = cat[..., cout:] if last else torch.empty(1, H_, W_, cout, **f32)
-                block(x, f"enc{i}.{b}", out, cin if b == 0 else cout, cout, H_, W_)
+                if last:
+                    out = cat.sub(cout, cout) if S else cat[..., cout:]
+                else:
+                    out = new(H_, W_, cout)
+                block(x, f"enc{i}.{b}", out, H_, W_, cout)
                 x = out
-            pooled = torch.empty(1, H_ // 2, W_ // 2, cout, **f32)
-            add(lambda x=x, pooled=pooled: ops.avgpool2x2(x, pooled))
+            pooled = new(H_ // 2, W_ // 2, cout)
+            if S:
+                add(lambda x=x, pooled=pooled: ops.avgpool2x2_split(x.plane0, x.Ct, pooled.plane0, pooled.Ct))
+            else:
+                add(lambda x=x, pooled=pooled: ops.avgpool2x2(x, pooled))
             x = pooled
-            H_, W_, cin, cout = H_ // 2, W_ // 2, cout, cout * 2
+            H_, W_, cout = H_ // 2, W_ // 2, cout * 2
         # ---- intermediate (rmvpe.py:122-138)
         for i in range(m.n_inter):
             for b in range(m.n_blocks):
-                out = torch.empty(1, H_, W_, cout, **f32)
-                block(x, f"mid{i}.{b}", out, cin if (i == 0 and b == 0) else cout, cout, H_, W_)
+                out = new(H_, W_, cout)
+                block(x, f"mid{i}.{b}", out, H_, W_, cout)
                 x = out
         # ---- decoder (rmvpe.py:141-187)
         for i in range(m.n_enc):
             cat, Hc, Wc, cc = cats[-1 - i]
-            for op in tg.conv_transpose2d_s2(x, W[f"dec{i}.up.w"], cat[..., :cc], 3, 1,
-                                             Epi(bias=W[f"dec{i}.up.b"], act_pre=tg.ACT_RELU), be, name=f"dec{i}.up"):
+            if S:
+                ups = tg.conv_transpose2d_s2(x.gemm_in, W[f"dec{i}.up.ws"], cat.sub(0, cc).plane0, 3, 1,
+                                             Epi(bias=W[f"dec{i}.up.b"], act_pre=tg.ACT_RELU, split_out=cat.Ct), be, name=f"dec{i}.up")
+            else:
+                ups = tg.conv_transpose2d_s2(x, W[f"dec{i}.up.w"], cat[..., :cc], 3, 1,
+                                             Epi(bias=W[f"dec{i}.up.b"], act_pre=tg.ACT_RELU), ex, name=f"dec{i}.up")
+            for op in ups:
                 add(op)
             x = cat
             for b in range(m.n_blocks):
-                out = torch.empty(1, Hc, Wc, cc, **f32)
-                block(x, f"dec{i}.{b}", out, 2 * cc if b == 0 else cc, cc, Hc, Wc)
+                out = new(Hc, Wc, cc)
+                block(x, f"dec{i}.{b}", out, Hc, Wc, cc)
                 x = out
-        # ---- head (rmvpe.py:241-258)
+        # ---- head (rmvpe.py:241-258): N = 3 output channels -> exact-fp32 kernel; on the split path it reads hi + lo
         feat = torch.empty(1, T, N_MELS, 3, **f32)
-        add(tg.conv2d(x, W["cnn.w"], feat, 3, 3, (1, 1), Epi(bias=W["cnn.b"]), be, name="cnn"))
+        if S:
+            add(tg.conv2d(x.t[..., :2 * x.Ct], W["cnn.w2"], feat, 3, 3, (1, 1), Epi(bias=W["cnn.b"]), ex, name="cnn"))
+        else:
+            add(tg.conv2d(x, W["cnn.w"], feat, 3, 3, (1, 1), Epi(bias=W["cnn.b"]), ex, name="cnn"))
+        be = ex                                # GRU input projection and salience head: exact fp32
+        self.feat, self.n_unet_end = feat, len(steps)
         Hh = m.hidden
         xp = torch.empty(T, 2 * 3 * Hh, **f32)
         add(tg.linear(feat.view(T, 3 * N_MELS), W["gru.wih"], xp, Epi(bias=W["gru.bih"]), be, name="gru.in"))

@@ -137,6 +137,8 @@ class Epi:
     act2_p: float = 0.0
     round_out: bool = False     # store `out` rounded (RN) to TF32: for tensors only consumed by TF32 GEMMs
     round_out2: bool = False
+    split_out: int = 0          # > 0: write `out` as 3xTF32 planes hi | lo | hi, `split_out` elements apart (b200vc.h `split`)
+    res_split: int = 0          # > 0: `res` is a split tensor, value = res[..] + res[.. + res_split]
 
 
 def _tile_box(OW: int, OH: int) -> Tuple[int, int]:
@@ -232,6 +234,13 @@ class TapGemm:
             self._keep.append(epi.out2)
         p.act2, p.act2_p = epi.act2, float(epi.act2_p)
         p.round_tf32 = (1 if epi.round_out else 0) | (2 if epi.round_out2 else 0)
+        p.split = (1 if epi.split_out else 0) | (2 if epi.res_split else 0)
+        p.o_split, p.r_split = int(epi.split_out), int(epi.res_split)
+        if epi.split_out:
+            assert epi.res2 is None and epi.out2 is None and out.t.dtype == torch.float32 and out.sn == 1
+            assert epi.split_out % 4 == 0
+        if epi.res_split:
+            assert epi.res is not None and epi.res.dtype == torch.float32 and epi.res_split % 4 == 0
         for i, (c_off, dw, dh, dp, widx) in enumerate(self.taps):
             t = p.taps[i]
             t.c_off, t.dw, t.dh, t.dp, t.widx = int(c_off), int(dw), int(dh), int(dp), int(widx)

@@ -111,6 +111,12 @@ typedef struct b200vc_tapgemm_params {
                            only; bit1 out, bit2 out2, bit3 res, bit4 res2 are fp16.  Pointers stay typed `float*` in
                            this struct; offsets and strides are in ELEMENTS of the tensor's own type.
                            EXPERIMENTAL in round 1: compiled and emulator-tested, not yet validated on a GPU. */
+  int32_t split;        /* 3xTF32 split-operand storage (fp32 accuracy on the TF32 tensor core: x = hi + lo with hi = RN_tf32(x),
+                           lo = RN_tf32(x - hi); a consumer GEMM reads the K-concatenation [hi | lo | hi] against weights
+                           [W_hi | W_hi | W_lo], i.e. hi.W_hi + lo.W_hi + hi.W_lo, dropping only lo.W_lo ~ 2^-22):
+                           bit0: `out` is written as three planes hi | lo | hi, plane p at element offset p * o_split;
+                           bit1: `res` is such a split tensor: the residual value is res[..] + res[.. + r_split].       */
+  int64_t o_split, r_split;
   b200vc_tap taps[B200VC_MAX_TAPS];
 } b200vc_tapgemm_params;
 
@@ -201,6 +207,10 @@ int b200vc_logmel_affine_reflect(const float* x, float* out, int rows, int rows_
 
 /* NHWC 2x2 average pooling; input pixel pitch ldi (nn.AvgPool2d, rmvpe.py:111,117) */
 int b200vc_avgpool2x2(const float* in, float* out, int B, int H, int W, int C, int64_t ldi, void* stream);
+/* the same on 3xTF32 split tensors (see b200vc_tapgemm_params.split): x = in[..] + in[.. + in_split] is pooled in fp32 and
+ * written as planes hi | lo | hi at out + {0,1,2} * out_split; pixel pitches ldi / ldo */
+int b200vc_avgpool2x2_split(const float* in, float* out, int B, int H, int W, int C, int64_t ldi, int64_t in_split,
+                            int64_t ldo, int64_t out_split, void* stream);
 
 /* Bidirectional GRU recurrence (nn.GRU(384,256,bidirectional), rmvpe.py:8-20) as a 2x8-CTA cluster kernel.
  * xp [T, 2*3H] = x W_ih^T + b_ih (dir d at column d*3H); whh [2,3H,H]; bhh [2,3H]; out [T,2H]. */

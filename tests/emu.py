@@ -39,6 +39,11 @@ def _act(v, code, p):
     raise ValueError(code)
 
 
+def _rn_tf32(t: torch.Tensor) -> torch.Tensor:
+    i = t.contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
 def emulate(op) -> None:
     """Run op on its (CPU) tensors, writing op.out (and out2) in place."""
     p = op.params
@@ -98,6 +103,8 @@ def emulate(op) -> None:
         else:
             ridx = r.storage_offset() + bb * st[0] + hh * st[1] + ww * st[2]
         rv = rf[ridx[:, None] + n_idx[None, :] * st[3]]
+        if getattr(epi, "res_split", 0):
+            rv = rv + rf[ridx[:, None] + n_idx[None, :] * st[3] + epi.res_split]
         v = v * rv if epi.res_mul else v + rv
     v = v * epi.scale
     mh, mw = hh * out.osh + out.ooh, ww * out.osw + out.oow
@@ -111,6 +118,13 @@ def emulate(op) -> None:
     v = _act(v, epi.act_post, epi.act_post_p)
     of = _flat(out.t)
     sel = valid
+    if getattr(epi, "split_out", 0):        # 3xTF32 planes hi | lo | hi
+        v32 = v.float()
+        hi = _rn_tf32(v32)
+        lo = _rn_tf32(v32 - hi)
+        for plane, val in ((0, hi), (1, lo), (2, hi)):
+            of[(o_idx[sel] + plane * epi.split_out).reshape(-1)] = val[sel].reshape(-1)
+        return
     of[o_idx[sel].reshape(-1)] = v[sel].reshape(-1).to(of.dtype)
     if epi.out2 is not None and hasattr(epi.out2, "sn"):       # tapgemm.Out: its own layout, addressed by the mapped pixel
         q = epi.out2
