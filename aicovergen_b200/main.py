@@ -76,11 +76,13 @@ class CoverEngine:
 
     @_ffi.on_device
     @torch.no_grad()
-    def separate(self, song_dev: torch.Tensor) -> Dict[str, torch.Tensor]:
-        """The three MDX passes of preprocess_song on a device tensor [2,N] float32 @44.1k -> stems (device tensors)."""
-        vocals, instrumental = run_mdx_device(self.mdx[0], song_dev, denoise=True)
-        backup, main_vocals = run_mdx_device(self.mdx[1], vocals, denoise=True)
-        _, dereverb = run_mdx_device(self.mdx[2], main_vocals, denoise=True)
+    def separate(self, song_dev: torch.Tensor, group=None) -> Dict[str, torch.Tensor]:
+        """The three MDX passes of preprocess_song on a device tensor [2,N] float32 @44.1k -> stems (device tensors).
+        With a torch.distributed `group` the chunk list of every pass is shared by the group's ranks (strong scaling of ONE
+        song: chunk ranges per rank, one all-gather of the stem per pass)."""
+        vocals, instrumental = run_mdx_device(self.mdx[0], song_dev, denoise=True, group=group)
+        backup, main_vocals = run_mdx_device(self.mdx[1], vocals, denoise=True, group=group)
+        _, dereverb = run_mdx_device(self.mdx[2], main_vocals, denoise=True, group=group)
         return dict(vocals=vocals, instrumental=instrumental, backup=backup, main=main_vocals, dereverb=dereverb)
 
     @_ffi.on_device
@@ -117,10 +119,16 @@ class CoverEngine:
         return out
 
     @_ffi.on_device
-    def cover_device(self, song_dev: torch.Tensor, main_gain=0, backup_gain=0, inst_gain=0, **convert_kw) -> torch.Tensor:
-        """song already in HBM -> cover in HBM (the converted utterance is handed to the mix as a device tensor)."""
-        stems = self.separate(song_dev)
-        ai = self.convert(stems["dereverb"], return_device=True, **convert_kw)
+    def cover_device(self, song_dev: torch.Tensor, main_gain=0, backup_gain=0, inst_gain=0, group=None, **convert_kw) -> torch.Tensor:
+        """song already in HBM -> cover in HBM (the converted utterance is handed to the mix as a device tensor).
+        `group`: ranks of a torch.distributed group work on the SAME song (every rank must call this with the same song):
+        MDX chunks and RVC segments are shared, every rank ends with the full cover."""
+        stems = self.separate(song_dev, group)
+        self.vc.group = group
+        try:
+            ai = self.convert(stems["dereverb"], return_device=True, **convert_kw)
+        finally:
+            self.vc.group = None
         return self.mix(ai, stems["backup"], stems["instrumental"], main_gain, backup_gain, inst_gain)
 
     @_ffi.on_device

@@ -310,6 +310,43 @@ def shard_range(n_items: int, rank: int, world: int):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def shard_spans(n, n_fft, chunk_size, mt_threads, world, margin=44100):
+    """For every rank of `world`: the half-open SAMPLE range [lo, hi) of the song its contiguous chunk range produces.
+    Kept output samples are monotone in the flattened chunk order (half 0 keeps [0, n/2), half 1 keeps [n/2, n); inside a
+    half chunk i keeps [i*gen, (i+1)*gen)), so a contiguous chunk range owns one contiguous slice of the stem — which is
+    what makes the final concat an all-gather of disjoint slices (mdx.py:190-197, 107-117)."""
+    src, lo, hi, dst, klo, khi = chunk_descriptors(n, n_fft, chunk_size, mt_threads, margin)
+    gen = chunk_size - n_fft
+    k_lo = np.maximum(dst, klo)
+    k_hi = np.minimum(np.minimum(dst + gen, khi), n)
+    spans = []
+    for r in range(world):
+        a, b = shard_range(len(src), r, world)
+        live = [(int(k_lo[i]), int(k_hi[i])) for i in range(a, b) if k_hi[i] > k_lo[i]]
+        spans.append((min(x for x, _ in live), max(y for _, y in live)) if live else (0, 0))
+    return spans
+
+
+def allgather_spans(t: torch.Tensor, spans, group) -> None:
+    """In place: every rank holds valid data of t[:, lo_r:hi_r] for its own span and receives everybody else's.
+    One all-gather of equal-size (padded) slices — the only collective of the sharded MDX pass."""
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    width = max(hi - lo for lo, hi in spans)
+    if width == 0:
+        return
+    rows = t.shape[0]
+    send = torch.zeros(rows, width, dtype=t.dtype, device=t.device)
+    lo, hi = spans[rank]
+    send[:, :hi - lo] = t[:, lo:hi]
+    recv = torch.empty(world * rows, width, dtype=t.dtype, device=t.device)       # concatenation along dim 0 (gloo and nccl)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    recv = recv.view(world, rows, width)
+    for r, (lo, hi) in enumerate(spans):
+        if r != rank and hi > lo:
+            t[:, lo:hi] = recv[r, :, :hi - lo]
+
+
 def segment_bounds(n, chunk_size, margin_size):
     """Start/end of the overlapping segments MDX.segment(combine=False) cuts (mdx.py:119-141)."""
     if chunk_size <= 0 or chunk_size > n:
@@ -524,9 +561,10 @@ def _run_mdx_device(mdx_sess: MDX, wave_dev: torch.Tensor, denoise, m_threads, g
     else:
         mdx_sess._process_device(w, proc, 1.0, 1.0, False, m_threads, shard)
     if shard[1] > 1:
-        # the only collective on the path: every rank holds a disjoint set of output samples (zeros elsewhere),
-        # so one NCCL sum over NVLink reassembles the stem on all ranks
-        dist.all_reduce(proc, group=group)
+        # the only collective on the path: every rank computed one contiguous, disjoint sample range of the stem (both
+        # denoise sweeps use the same chunk split and were accumulated locally) -> all-gather of those slices over NVLink
+        spans = shard_spans(w.shape[1], model.n_fft, model.chunk_size, m_threads, shard[1], MDX.DEFAULT_MARGIN_SIZE)
+        allgather_spans(proc, spans, group)
     inverse = torch.empty_like(w)
     proc.mul_(peak)                                                   # wave_processed *= peak (mdx.py:267)
     ops.mdx_finalize(proc, w, inverse, 1.0, model.compensation)       # inverse = -proc * compensation + wave_norm (mdx.py:280)

@@ -46,13 +46,15 @@ class VC(object):
         self.keep_float = False      # tests: keep the float waveform before/after the RMS mix
         self.exact_hpf = False       # True: scipy.signal.filtfilt on the host (the reference's exact ba-form numerics)
         self.return_device = False   # extension: pipeline() returns the int16 utterance as a device tensor (no D2H)
+        self.group = None            # extension: torch.distributed group -> one utterance's segments are shared by its ranks
 
     # ------------------------------------------------------------------ extension for parity tests
     def set_noise_seed(self, seed: Optional[int]):
         self._noise_gen = None if seed is None else torch.Generator().manual_seed(int(seed))
 
-    def _draw_noise(self, net_g, P):
-        """Replays the reference's draw order inside net_g.infer (models.py:748, :337, :368)."""
+    def _draw_noise(self, net_g, P, upload=True):
+        """Replays the reference's draw order inside net_g.infer (models.py:748, :337, :368).  upload=False only advances
+        the stream (segments another rank converts)."""
         if self._noise_gen is None:
             return None, None
         g = self._noise_gen
@@ -61,6 +63,8 @@ class VC(object):
         if net_g.f0:                     # the *_nono models draw randn_like(m_p) only (models.py:847-853)
             _ = torch.rand(1, 1, generator=g)
             ns = torch.randn(1, P * net_g.upp, 1, generator=g)
+        if not upload:
+            return None, None
         dev = self.device
         return nz.to(dev), (None if ns is None else ns.to(dev))
 
@@ -140,6 +144,32 @@ class VC(object):
         times[2] += t2 - t1
         return audio1
 
+    # ------------------------------------------------------------------ segment sharding (extension)
+    def _segment_frames(self, n_in: int) -> int:
+        """p_len of a segment of n_in samples: min(n_in // window, 2 * HuBERT frames) (vc_infer_pipeline.py:433-441)."""
+        from .hubert import conv_out_len
+        return min(n_in // self.window, 2 * conv_out_len(n_in)[-1])
+
+    def _gather_segments(self, outs, seg_samples, net_g, world, rank):
+        """All-gather of the converted segments (<= 38 MB for a 4-min song): round k exchanges segments k*world .. k*world +
+        world-1, each rank contributing the one it converted, padded to the longest of the round."""
+        import torch.distributed as dist
+        lens = [self._segment_frames(n) * net_g.upp - 2 * self.t_pad_tgt for n in seg_samples]
+        for k in range(0, len(outs), world):
+            ids = list(range(k, min(k + world, len(outs))))
+            width = max(lens[i] for i in ids)
+            send = torch.zeros(width, device=self.device, dtype=torch.float32)
+            mine = k + rank
+            if mine < len(outs):
+                assert outs[mine].shape[0] == lens[mine], (outs[mine].shape, lens[mine])
+                send[:lens[mine]] = outs[mine]
+            recv = torch.empty(world * width, device=self.device, dtype=torch.float32)
+            dist.all_gather_into_tensor(recv, send, group=self.group)
+            recv = recv.view(world, width)
+            for i in ids:
+                if i != mine:
+                    outs[i] = recv[i - k, :lens[i]].clone()
+
     # ------------------------------------------------------------------ whole utterance
     @staticmethod
     def _reflect_pad(t: torch.Tensor, p: int) -> torch.Tensor:
@@ -210,35 +240,50 @@ class VC(object):
                 traceback.print_exc()
         sid = torch.tensor(sid, device=self.device).unsqueeze(0).long()
         pitch, pitchf = None, None
+        world, rank = 1, 0
+        if self.group is not None:
+            import torch.distributed as dist
+            world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
         if if_f0 == 1:
-            pitch, pitchf = self.get_f0(input_audio_path, audio_pad, p_len, f0_up_key, f0_method, filter_radius,
-                                        crepe_hop_length, inp_f0)
-            pitch = pitch[:p_len]
-            pitchf = pitchf[:p_len]
-            pitch = torch.tensor(pitch, device=self.device).unsqueeze(0).long()
-            pitchf = torch.tensor(pitchf, device=self.device).unsqueeze(0).float()
+            if rank == 0:       # the F0 is one whole-utterance estimate (bidirectional GRU): group rank 0 computes it ...
+                pitch, pitchf = self.get_f0(input_audio_path, audio_pad, p_len, f0_up_key, f0_method, filter_radius,
+                                            crepe_hop_length, inp_f0)
+                pitch = torch.tensor(pitch[:p_len], device=self.device).unsqueeze(0).long()
+                pitchf = torch.tensor(pitchf[:p_len], device=self.device).unsqueeze(0).float()
+            else:
+                pitch = torch.empty(1, p_len, device=self.device, dtype=torch.int64)
+                pitchf = torch.empty(1, p_len, device=self.device, dtype=torch.float32)
+            if world > 1:       # ... and broadcasts pitch / pitchf (~300 KB for 4 minutes)
+                src = dist.get_global_rank(self.group, 0)
+                dist.broadcast(pitch, src=src, group=self.group)
+                dist.broadcast(pitchf, src=src, group=self.group)
         t2 = ttime()
         times[1] += t2 - t1
         # the padded utterance goes to HBM once; segments are device slices of it
         pad_dev = audio_pad.float()
         w = self.window
+        # segment list exactly as the reference walks it (:548-603): (sample range of the padded utterance, F0 frame range)
+        segs = []
         for t in opt_ts:
             t = t // w * w
-            seg = pad_dev[s: t + self.t_pad2 + w]
+            segs.append((s, t + self.t_pad2 + w, s // w, (t + self.t_pad2) // w))
+            s = t
+        segs.append((t if t is not None else 0, None, t // w if t is not None else 0, None))
+        audio_opt = [None] * len(segs)
+        for i, (a0, a1, p0, p1) in enumerate(segs):
+            seg = pad_dev[a0:a1]
+            if i % world != rank:          # another rank of the group converts this segment (independent after the global F0)
+                if self._noise_gen is not None:
+                    self._draw_noise(net_g, self._segment_frames(seg.shape[0]), upload=False)
+                continue
             if if_f0 == 1:
-                out = self.vc(model, net_g, sid, seg, pitch[:, s // w: (t + self.t_pad2) // w],
-                              pitchf[:, s // w: (t + self.t_pad2) // w], times, index, big_npy, index_rate, version, protect)
+                out = self.vc(model, net_g, sid, seg, pitch[:, p0:p1], pitchf[:, p0:p1], times, index, big_npy, index_rate,
+                              version, protect)
             else:
                 out = self.vc(model, net_g, sid, seg, None, None, times, index, big_npy, index_rate, version, protect)
-            audio_opt.append(out[self.t_pad_tgt: -self.t_pad_tgt].clone())
-            s = t
-        seg = pad_dev[t:] if t is not None else pad_dev
-        if if_f0 == 1:
-            out = self.vc(model, net_g, sid, seg, pitch[:, t // w:] if t is not None else pitch,
-                          pitchf[:, t // w:] if t is not None else pitchf, times, index, big_npy, index_rate, version, protect)
-        else:
-            out = self.vc(model, net_g, sid, seg, None, None, times, index, big_npy, index_rate, version, protect)
-        audio_opt.append(out[self.t_pad_tgt: -self.t_pad_tgt].clone())
+            audio_opt[i] = out[self.t_pad_tgt: -self.t_pad_tgt].clone()
+        if world > 1:
+            self._gather_segments(audio_opt, [pad_dev[a0:a1].shape[0] for (a0, a1, _, _) in segs], net_g, world, rank)
         audio_dev = torch.cat(audio_opt).contiguous()
         if self.keep_float:
             self.last_float_output = audio_dev.cpu().numpy()   # pre-RMS-mix float waveform (parity tests)
