@@ -101,6 +101,13 @@ def _declare(lib):
     lib.b200vc_sizeof_tapgemm_params.restype = C.c_int64
     lib.b200vc_count_launches.argtypes = [C.c_int64]
     lib.b200vc_count_launches.restype = None
+    lib.b200vc_plan_begin.argtypes = [C.POINTER(C.c_void_p)]
+    lib.b200vc_plan_end.argtypes = []
+    lib.b200vc_plan_size.argtypes = [C.c_void_p]
+    lib.b200vc_plan_run.argtypes = [C.c_void_p, C.c_void_p]
+    lib.b200vc_plan_destroy.argtypes = [C.c_void_p]
+    for fn in (lib.b200vc_plan_begin, lib.b200vc_plan_end, lib.b200vc_plan_size, lib.b200vc_plan_run, lib.b200vc_plan_destroy):
+        fn.restype = C.c_int
     if lib.b200vc_sizeof_tapgemm_params() != C.sizeof(TapGemmParams):
         raise RuntimeError(
             f"ABI mismatch: sizeof(b200vc_tapgemm_params)={lib.b200vc_sizeof_tapgemm_params()} "

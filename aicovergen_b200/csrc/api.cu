@@ -2,6 +2,8 @@
 #include "tapgemm.cuh"
 #include <atomic>
 #include <cstdarg>
+#include <memory>
+#include <vector>
 
 namespace b200vc {
 
@@ -19,6 +21,17 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 }  // namespace b200vc
 
+// A recorded launch sequence: what a per-shape "model handle" is below Python (include/b200vc.h, b200vc_plan_*).
+struct b200vc_plan {
+  std::vector<std::function<int(void*)>> steps;
+};
+
+namespace b200vc {
+static thread_local b200vc_plan* g_recording = nullptr;
+bool plan_recording() { return g_recording != nullptr; }
+void plan_push(std::function<int(void*)> step) { g_recording->steps.push_back(std::move(step)); }
+}  // namespace b200vc
+
 using namespace b200vc;
 
 extern "C" {
@@ -29,8 +42,45 @@ int64_t b200vc_launch_count(void) { return (int64_t)g_launches.load(); }
 void b200vc_count_launches(int64_t n) { g_launches.fetch_add((long long)n, std::memory_order_relaxed); }
 int64_t b200vc_sizeof_tapgemm_params(void) { return (int64_t)sizeof(b200vc_tapgemm_params); }
 
+int b200vc_plan_begin(b200vc_plan** out) {
+  B200VC_REQUIRE(out != nullptr, "plan_begin: null handle pointer");
+  B200VC_REQUIRE(g_recording == nullptr, "plan_begin: this thread is already recording a plan");
+  *out = new b200vc_plan();
+  g_recording = *out;
+  return kOk;
+}
+
+int b200vc_plan_end(void) {
+  B200VC_REQUIRE(g_recording != nullptr, "plan_end: no plan is being recorded on this thread");
+  g_recording = nullptr;
+  return kOk;
+}
+
+int b200vc_plan_size(const b200vc_plan* plan) { return plan ? (int)plan->steps.size() : -1; }
+
+int b200vc_plan_run(const b200vc_plan* plan, void* stream) {
+  B200VC_REQUIRE(plan != nullptr, "plan_run: null plan");
+  B200VC_REQUIRE(g_recording == nullptr, "plan_run: called while recording");
+  for (const auto& st : plan->steps) {
+    const int rc = st(stream);
+    if (rc) return rc;
+  }
+  return kOk;
+}
+
+int b200vc_plan_destroy(b200vc_plan* plan) {
+  if (g_recording == plan) g_recording = nullptr;
+  delete plan;
+  return kOk;
+}
+
 int b200vc_tapgemm(const b200vc_tapgemm_params* p, int backend, void* stream) {
   B200VC_REQUIRE(p != nullptr, "tapgemm: null descriptor");
+  if (plan_recording()) {       // the descriptor is copied: the caller's struct need not outlive the call
+    auto copy = std::make_shared<b200vc_tapgemm_params>(*p);
+    plan_push([copy, backend](void* s) -> int { return b200vc_tapgemm(copy.get(), backend, s); });
+    return kOk;
+  }
   B200VC_REQUIRE(p->A && p->Wt && p->out, "tapgemm: null operand pointer");
   B200VC_REQUIRE(p->ntaps >= 1 && p->ntaps <= B200VC_MAX_TAPS, "tapgemm: ntaps %d out of range", p->ntaps);
   B200VC_REQUIRE(p->BW >= 1 && p->BH >= 1 && p->BW * p->BH == TG_TILE_M, "tapgemm: BW*BH must be 128 (got %d x %d)", p->BW, p->BH);

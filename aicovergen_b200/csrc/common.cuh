@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 
 namespace b200vc {
 
@@ -51,6 +52,19 @@ void set_last_error(const char* fmt, ...);
 
 // Launch counter (bench.py reports it as gpu_launches).
 void count_launch(int n = 1);
+
+// Launch-plan recording (b200vc_plan_* in b200vc.h): between b200vc_plan_begin and b200vc_plan_end every recordable entry
+// point called on this thread is appended to the plan as a closure over its arguments instead of being launched;
+// b200vc_plan_run replays the closures on a stream.  All pointer arguments of recordable entries are DEVICE pointers.
+bool plan_recording();
+void plan_push(std::function<int(void*)> step);
+#define B200VC_RECORD(call)                                                          \
+  do {                                                                               \
+    if (::b200vc::plan_recording()) {                                                \
+      ::b200vc::plan_push([=](void* stream) -> int { (void)stream; return call; });  \
+      return ::b200vc::kOk;                                                          \
+    }                                                                                \
+  } while (0)
 
 // ---------------------------------------------------------------------------
 // Activation codes shared by all epilogues (also mirrored in _ffi.py).

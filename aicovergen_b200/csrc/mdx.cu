@@ -190,6 +190,7 @@ extern "C" {
 int b200vc_mdx_gather_chunks(const float* wave, int64_t n_song, const int64_t* src_start, const int64_t* lo,
                              const int64_t* hi, float* out, int B, int chunk, int half, float sign, int round_out,
                              void* stream) {
+  B200VC_RECORD(b200vc_mdx_gather_chunks(wave, n_song, src_start, lo, hi, out, B, chunk, half, sign, round_out, stream));
   B200VC_REQUIRE(wave && src_start && lo && hi && out && B > 0 && chunk > half && half >= 0, "mdx_gather_chunks: bad args");
   const long long n = (long long)B * 2 * ((long long)chunk + 2 * half);
   mdx_gather_chunks_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
@@ -202,6 +203,7 @@ int b200vc_mdx_gather_chunks(const float* wave, int64_t n_song, const int64_t* s
 
 int b200vc_mdx_first_conv(const float* spec, const float* w4, const float* bias, float* out, int B, int T, int F, int g,
                           int round_out, int out_half, void* stream) {
+  B200VC_RECORD(b200vc_mdx_first_conv(spec, w4, bias, out, B, T, F, g, round_out, out_half, stream));
   B200VC_REQUIRE(spec && w4 && bias && out && B > 0 && T > 0 && F > 0 && g > 0 && g % 4 == 0, "mdx_first_conv: bad args (g=%d)", g);
   B200VC_REQUIRE(((uintptr_t)spec % 8 == 0) && ((uintptr_t)w4 % 16 == 0) && ((uintptr_t)out % 16 == 0), "mdx_first_conv: alignment");
   const long long npix = (long long)B * T * F;
@@ -214,6 +216,7 @@ int b200vc_mdx_first_conv(const float* spec, const float* w4, const float* bias,
 
 int b200vc_mdx_final_conv(const float* x, const float* w, const float* bias, float* spec, int B, int T, int F, int c,
                           int round_out, int x_half, void* stream) {
+  B200VC_RECORD(b200vc_mdx_final_conv(x, w, bias, spec, B, T, F, c, round_out, x_half, stream));
   B200VC_REQUIRE(x && w && bias && spec && B > 0 && T > 0 && F > 0 && c > 0 && c % 4 == 0 && c <= 2048, "mdx_final_conv: bad args (c=%d)", c);
   B200VC_REQUIRE(((uintptr_t)x % 16 == 0) && ((uintptr_t)spec % 8 == 0), "mdx_final_conv: alignment");
   const long long npix = (long long)B * T * F;
@@ -226,6 +229,7 @@ int b200vc_mdx_final_conv(const float* x, const float* w, const float* bias, flo
 
 int b200vc_nhwc_to_nhcw(const float* x, const float* scale, float* out, int64_t R, int W, int C, int round_out,
                         void* stream) {
+  B200VC_RECORD(b200vc_nhwc_to_nhcw(x, scale, out, R, W, C, round_out, stream));
   B200VC_REQUIRE(x && out && R > 0 && R < 65536 && W > 0 && C > 0, "nhwc_to_nhcw: bad args (R=%lld)", (long long)R);
   dim3 grid((W + 31) / 32, (C + 31) / 32, (unsigned)R), block(32, 8);
   nhwc_to_nhcw_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, scale, out, W, C, round_out);
@@ -236,6 +240,7 @@ int b200vc_nhwc_to_nhcw(const float* x, const float* scale, float* out, int64_t 
 
 int b200vc_nhcw_to_nhwc_add(const float* t, const float* x, float* out, int64_t R, int W, int C, int round_out,
                             void* stream) {
+  B200VC_RECORD(b200vc_nhcw_to_nhwc_add(t, x, out, R, W, C, round_out, stream));
   B200VC_REQUIRE(t && x && out && R > 0 && R < 65536 && W > 0 && C > 0, "nhcw_to_nhwc_add: bad args");
   dim3 grid((W + 31) / 32, (C + 31) / 32, (unsigned)R), block(32, 8);
   nhcw_to_nhwc_add_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(t, x, out, W, C, round_out);
@@ -247,6 +252,7 @@ int b200vc_nhcw_to_nhwc_add(const float* t, const float* x, float* out, int64_t 
 int b200vc_mdx_ola_store(const float* frames, const float* env, const int64_t* dst_start, const int64_t* keep_lo,
                          const int64_t* keep_hi, float* song, int64_t n_song, int B, int T, int n_fft, int hop,
                          int chunk, int trim, float coef, int accumulate, void* stream) {
+  B200VC_RECORD(b200vc_mdx_ola_store(frames, env, dst_start, keep_lo, keep_hi, song, n_song, B, T, n_fft, hop, chunk, trim, coef, accumulate, stream));
   B200VC_REQUIRE(frames && env && dst_start && keep_lo && keep_hi && song && B > 0 && chunk > 2 * trim,
                  "mdx_ola_store: bad args");
   const long long n = (long long)B * 2 * (chunk - 2 * trim);
@@ -260,6 +266,7 @@ int b200vc_mdx_ola_store(const float* frames, const float* env, const int64_t* d
 
 int b200vc_mdx_finalize(float* proc, const float* wave_norm, float* inverse, int64_t n, float peak,
                         float compensation, void* stream) {
+  B200VC_RECORD(b200vc_mdx_finalize(proc, wave_norm, inverse, n, peak, compensation, stream));
   B200VC_REQUIRE(proc && n > 0 && (!inverse || wave_norm), "mdx_finalize: bad args");
   mdx_finalize_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(proc, wave_norm, inverse, n, peak,
                                                                           compensation);

@@ -370,6 +370,7 @@ extern "C" {
 int b200vc_layernorm(const float* x, const float* res, const float* gamma, const float* beta, float* out,
                      int64_t rows, int C, int64_t ldx, int64_t ldr, int64_t ldo, float eps, int round_out,
                      void* stream) {
+  B200VC_RECORD(b200vc_layernorm(x, res, gamma, beta, out, rows, C, ldx, ldr, ldo, eps, round_out, stream));
   B200VC_REQUIRE(x && gamma && beta && out && rows > 0 && C > 0 && C <= 1024, "layernorm: bad args (C=%d)", C);
   cudaStream_t s = (cudaStream_t)stream;
   const int bs = 256;
@@ -388,6 +389,7 @@ int b200vc_layernorm(const float* x, const float* res, const float* gamma, const
 int b200vc_softmax_rows(float* S, int heads, int rows_per_head, int T, int64_t ld, int64_t head_stride,
                         const float* q, int ldq, const float* emb_rel_k, int window, int dk,
                         int round_out, void* stream) {
+  B200VC_RECORD(b200vc_softmax_rows(S, heads, rows_per_head, T, ld, head_stride, q, ldq, emb_rel_k, window, dk, round_out, stream));
   B200VC_REQUIRE(S && heads > 0 && rows_per_head > 0 && T > 0, "softmax_rows: bad args");
   B200VC_REQUIRE(T * 4 <= 200 * 1024, "softmax_rows: row of %d floats does not fit shared memory", T);
   B200VC_REQUIRE(!emb_rel_k || (q && 2 * window + 1 <= 64), "softmax_rows: bad relative-position args");
@@ -407,6 +409,7 @@ int b200vc_softmax_rows(float* S, int heads, int rows_per_head, int T, int64_t l
 
 int b200vc_relpos_value_add(float* out, int ldo, const float* P, int T, int64_t ld, int64_t head_stride,
                             const float* emb_rel_v, int window, int dk, int heads, void* stream) {
+  B200VC_RECORD(b200vc_relpos_value_add(out, ldo, P, T, ld, head_stride, emb_rel_v, window, dk, heads, stream));
   B200VC_REQUIRE(out && P && emb_rel_v && T > 0, "relpos_value_add: bad args");
   relpos_value_add_kernel<<<(unsigned)T, 192, 0, (cudaStream_t)stream>>>(out, ldo, P, T, ld, head_stride,
                                                                         emb_rel_v, window, dk, heads);
@@ -416,6 +419,7 @@ int b200vc_relpos_value_add(float* out, int ldo, const float* P, int T, int64_t 
 }
 
 int b200vc_gather_rows(const float* table, const int64_t* idx, float* out, int64_t rows, int C, void* stream) {
+  B200VC_RECORD(b200vc_gather_rows(table, idx, out, rows, C, stream));
   B200VC_REQUIRE(table && idx && out && rows > 0 && C > 0, "gather_rows: bad args");
   gather_rows_kernel<<<blocks_for(rows * C, 256), 256, 0, (cudaStream_t)stream>>>(
       table, reinterpret_cast<const long long*>(idx), out, rows, C);
@@ -425,6 +429,7 @@ int b200vc_gather_rows(const float* table, const int64_t* idx, float* out, int64
 }
 
 int b200vc_gate_tanh_sigmoid(const float* a, float* out, int64_t rows, int C, int round_out, void* stream) {
+  B200VC_RECORD(b200vc_gate_tanh_sigmoid(a, out, rows, C, round_out, stream));
   B200VC_REQUIRE(a && out && rows > 0 && C > 0, "gate: bad args");
   gate_kernel<<<blocks_for(rows * C, 256), 256, 0, (cudaStream_t)stream>>>(a, out, rows, C, round_out);
   count_launch();
@@ -433,6 +438,7 @@ int b200vc_gate_tanh_sigmoid(const float* a, float* out, int64_t rows, int C, in
 }
 
 int b200vc_zp_sample(const float* stats, const float* noise, float* z, int64_t P, int C, float scale, void* stream) {
+  B200VC_RECORD(b200vc_zp_sample(stats, noise, z, P, C, scale, stream));
   B200VC_REQUIRE(stats && noise && z && P > 0 && C > 0, "zp_sample: bad args");
   zp_sample_kernel<<<blocks_for(P * C, 256), 256, 0, (cudaStream_t)stream>>>(stats, noise, z, P, C, scale);
   count_launch();
@@ -441,6 +447,7 @@ int b200vc_zp_sample(const float* stats, const float* noise, float* z, int64_t P
 }
 
 int b200vc_axpby(const float* a, const float* b, float* out, int64_t n, float alpha, float beta, void* stream) {
+  B200VC_RECORD(b200vc_axpby(a, b, out, n, alpha, beta, stream));
   B200VC_REQUIRE(a && out && n > 0, "axpby: bad args");
   axpby_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(a, b, out, n, alpha, beta);
   count_launch();
@@ -449,6 +456,7 @@ int b200vc_axpby(const float* a, const float* b, float* out, int64_t n, float al
 }
 
 int b200vc_act(const float* x, float* out, int64_t n, int act, float p, int round_out, void* stream) {
+  B200VC_RECORD(b200vc_act(x, out, n, act, p, round_out, stream));
   B200VC_REQUIRE(x && out && n > 0, "act: bad args");
   act_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, out, n, act, p, round_out);
   count_launch();
@@ -458,6 +466,7 @@ int b200vc_act(const float* x, float* out, int64_t n, int act, float p, int roun
 
 int b200vc_nsf_source(const float* f0, const float* noise, float* har, double* scratch_cum, int T, int upp,
                       float sr, float lin_w, float lin_b, void* stream) {
+  B200VC_RECORD(b200vc_nsf_source(f0, noise, har, scratch_cum, T, upp, sr, lin_w, lin_b, stream));
   B200VC_REQUIRE(f0 && noise && har && scratch_cum && T > 0 && upp > 0, "nsf_source: bad args");
   cudaStream_t s = (cudaStream_t)stream;
   nsf_frame_prefix_kernel<<<1, 1024, 1024 * sizeof(double), s>>>(f0, scratch_cum, T, sr);
@@ -471,6 +480,7 @@ int b200vc_nsf_source(const float* f0, const float* noise, float* har, double* s
 int b200vc_conv1d_from1(const float* src, int64_t n_src, const float* w, const float* bias, const float* res, float* out,
                         float* out2, int64_t T, int C, int K, int stride, int64_t src_off, int act2, float act2_p,
                         int round_out2, void* stream) {
+  B200VC_RECORD(b200vc_conv1d_from1(src, n_src, w, bias, res, out, out2, T, C, K, stride, src_off, act2, act2_p, round_out2, stream));
   B200VC_REQUIRE(src && w && out && T > 0 && C > 0 && C % 4 == 0 && K > 0 && stride > 0 && (long long)K * C * 4 <= 160 * 1024,
                  "conv1d_from1: bad args (C=%d K=%d)", C, K);
   const size_t smem = (size_t)K * C * 4;
@@ -488,6 +498,7 @@ int b200vc_conv1d_from1(const float* src, int64_t n_src, const float* w, const f
 
 int b200vc_conv1d_to1(const float* x, const float* w, float* out, int64_t T, int C, int K, int pad, int act,
                       void* stream) {
+  B200VC_RECORD(b200vc_conv1d_to1(x, w, out, T, C, K, pad, act, stream));
   B200VC_REQUIRE(x && w && out && T > 0 && C % 4 == 0 && K * C * 4 <= 48 * 1024, "conv1d_to1: bad args");
   conv1d_to1_kernel<<<blocks_for(T, 256), 256, K * C * 4, (cudaStream_t)stream>>>(x, w, out, T, C, K, pad, act);
   count_launch();
@@ -497,6 +508,7 @@ int b200vc_conv1d_to1(const float* x, const float* w, float* out, int64_t T, int
 
 int b200vc_groupnorm_time(const float* x, const float* gamma, const float* beta, float* out, double* stats,
                           int64_t rows, int C, float eps, int act, int round_out, void* stream) {
+  B200VC_RECORD(b200vc_groupnorm_time(x, gamma, beta, out, stats, rows, C, eps, act, round_out, stream));
   B200VC_REQUIRE(x && gamma && beta && out && stats && rows > 0 && C > 0, "groupnorm_time: bad args");
   cudaStream_t s = (cudaStream_t)stream;
   B200VC_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * C, s));

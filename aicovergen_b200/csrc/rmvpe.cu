@@ -248,6 +248,7 @@ using namespace b200vc;
 extern "C" {
 
 int b200vc_reflect_pad_1d(const float* in, float* out, int64_t N, int64_t pad, void* stream) {
+  B200VC_RECORD(b200vc_reflect_pad_1d(in, out, N, pad, stream));
   B200VC_REQUIRE(in && out && N > pad && pad >= 0, "reflect_pad_1d: bad args");
   const long long total = N + 2 * pad;
   reflect_pad_1d_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(in, out, N, pad, total);
@@ -257,6 +258,7 @@ int b200vc_reflect_pad_1d(const float* in, float* out, int64_t N, int64_t pad, v
 }
 
 int b200vc_magnitude(const float* spec, float* mag, int64_t rows, int nb, int64_t lds, int64_t ldm, void* stream) {
+  B200VC_RECORD(b200vc_magnitude(spec, mag, rows, nb, lds, ldm, stream));
   B200VC_REQUIRE(spec && mag && rows > 0 && nb > 0 && ldm >= nb, "magnitude: bad args");
   magnitude_kernel<<<blocks_for(rows * ldm, 256), 256, 0, (cudaStream_t)stream>>>(spec, mag, rows, nb, lds, ldm);
   count_launch();
@@ -266,6 +268,7 @@ int b200vc_magnitude(const float* spec, float* mag, int64_t rows, int nb, int64_
 
 int b200vc_logmel_affine_reflect(const float* x, float* out, int rows, int rows_total, int C, float clampv,
                                  float a, float b, void* stream) {
+  B200VC_RECORD(b200vc_logmel_affine_reflect(x, out, rows, rows_total, C, clampv, a, b, stream));
   B200VC_REQUIRE(x && out && rows > 0 && rows_total >= rows && rows_total - rows < rows, "logmel: bad args");
   logmel_affine_reflect_kernel<<<blocks_for((long long)rows_total * C, 256), 256, 0, (cudaStream_t)stream>>>(
       x, out, rows, rows_total, C, clampv, a, b);
@@ -275,6 +278,7 @@ int b200vc_logmel_affine_reflect(const float* x, float* out, int rows, int rows_
 }
 
 int b200vc_avgpool2x2(const float* in, float* out, int B, int H, int W, int C, int64_t ldi, void* stream) {
+  B200VC_RECORD(b200vc_avgpool2x2(in, out, B, H, W, C, ldi, stream));
   B200VC_REQUIRE(in && out && B > 0 && H % 2 == 0 && W % 2 == 0 && C > 0, "avgpool2x2: bad args");
   const long long n = (long long)B * (H / 2) * (W / 2) * C;
   avgpool2x2_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(in, out, B, H, W, C, ldi);
@@ -285,6 +289,7 @@ int b200vc_avgpool2x2(const float* in, float* out, int B, int H, int W, int C, i
 
 int b200vc_avgpool2x2_split(const float* in, float* out, int B, int H, int W, int C, int64_t ldi, int64_t in_split,
                             int64_t ldo, int64_t out_split, void* stream) {
+  B200VC_RECORD(b200vc_avgpool2x2_split(in, out, B, H, W, C, ldi, in_split, ldo, out_split, stream));
   B200VC_REQUIRE(in && out && B > 0 && H % 2 == 0 && W % 2 == 0 && C > 0, "avgpool2x2_split: bad args");
   const long long n = (long long)B * (H / 2) * (W / 2) * C;
   avgpool2x2_split_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(in, out, B, H, W, C, ldi, in_split, ldo, out_split);
@@ -294,6 +299,7 @@ int b200vc_avgpool2x2_split(const float* in, float* out, int B, int H, int W, in
 }
 
 int b200vc_bigru(const float* xp, const float* whh, const float* bhh, float* out, int T, int hidden, void* stream) {
+  B200VC_RECORD(b200vc_bigru(xp, whh, bhh, out, T, hidden, stream));
   B200VC_REQUIRE(xp && whh && bhh && out && T > 0, "bigru: bad args");
   B200VC_REQUIRE(hidden == GRU_H, "bigru: hidden size %d unsupported (kernel is specialised for %d)", hidden, GRU_H);
   bigru_kernel<<<2 * GRU_CL, GRU_THREADS, 0, (cudaStream_t)stream>>>(xp, whh, bhh, out, T);
@@ -304,6 +310,7 @@ int b200vc_bigru(const float* xp, const float* whh, const float* bhh, float* out
 
 int b200vc_rmvpe_decode(const float* salience, double* f0, double* cents, int T, int n_bins, int64_t ld, float thred,
                         void* stream) {
+  B200VC_RECORD(b200vc_rmvpe_decode(salience, f0, cents, T, n_bins, ld, thred, stream));
   B200VC_REQUIRE(salience && f0 && T > 0 && n_bins > 0, "rmvpe_decode: bad args");
   rmvpe_decode_kernel<<<blocks_for((long long)T * 32, 256), 256, 0, (cudaStream_t)stream>>>(salience, f0, cents, T,
                                                                                            n_bins, ld, thred);

@@ -43,11 +43,15 @@ def graphs_enabled(on=None) -> bool:
 
 
 class StepGraph:
-    """Runs `steps` (callables that only enqueue work on the current stream over fixed buffers): eagerly the first time
-    (lazy module loading, cudaFuncSetAttribute), then captured into a torch.cuda.CUDAGraph and replayed."""
+    """Runs `steps` (callables that only enqueue library launches on the current stream over fixed buffers).
+    First call: the steps are RECORDED into a C-side launch plan (b200vc_plan_begin/_end: every entry point called in
+    between is stored with its arguments instead of launched) and the plan is run natively — from then on one forward pass
+    is ONE ctypes call (b200vc_plan_run), whatever the host language.  From the second call the plan run is additionally
+    captured into a CUDA graph and replayed."""
 
     def __init__(self, steps):
         self.steps = steps
+        self.plan = None
         self.graph = None
         self.calls = 0
         self.launches = 0
@@ -56,22 +60,53 @@ class StepGraph:
         for st in self.steps:
             st()
 
+    def _record(self):
+        import ctypes as C
+
+        from . import _ffi
+        lib = _ffi.lib()
+        h = C.c_void_p()
+        _ffi.check(lib.b200vc_plan_begin(C.byref(h)), "plan_begin")
+        try:
+            self.eager()
+        finally:
+            _ffi.check(lib.b200vc_plan_end(), "plan_end")
+        self.plan = h
+        self.launches = int(lib.b200vc_plan_size(h))
+
+    def run_plan(self):
+        import ctypes as C
+
+        import torch
+
+        from . import _ffi
+        _ffi.check(_ffi.lib().b200vc_plan_run(self.plan, C.c_void_p(torch.cuda.current_stream().cuda_stream)), "plan_run")
+
     def __call__(self):
         import torch
 
         from . import _ffi
         if not graphs_enabled():
             return self.eager()
+        if self.plan is None:
+            self._record()
         if self.graph is None:
             self.calls += 1
             if self.calls < 2:
-                return self.eager()
+                return self.run_plan()
             l0 = _ffi.launch_count()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self.eager()
-            self.launches = _ffi.launch_count() - l0       # counted while capturing; nothing ran yet
-            _ffi.lib().b200vc_count_launches(-self.launches)
+                self.run_plan()
+            _ffi.lib().b200vc_count_launches(l0 - _ffi.launch_count())     # counted while capturing; nothing ran yet
             self.graph = g
         self.graph.replay()
         _ffi.lib().b200vc_count_launches(self.launches)
+
+    def __del__(self):
+        try:
+            if self.plan is not None:
+                from . import _ffi
+                _ffi.lib().b200vc_plan_destroy(self.plan)
+        except Exception:
+            pass

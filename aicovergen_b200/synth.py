@@ -258,7 +258,7 @@ class _Plan:
         S = torch.empty(P, inter, **f32)
         self.stats, self.z_p = stats, torch.empty(P, inter, **f32)
         add(lambda: ops.zp_sample(stats, self.noise_z, self.z_p))
-        add(lambda: S.copy_(self.z_p))
+        add(lambda: ops.axpby(self.z_p, None, S))          # S = z_p (library op: plan steps must be recordable, see plans.StepGraph)
 
         # ================= reverse flow (models.py:151-152) =================
         half = inter // 2

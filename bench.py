@@ -355,6 +355,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--seconds", type=float, default=float(SONG_SECONDS), help="song length (default: the 4-min headline config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default, BASELINE cfg 5): one song per GPU; strong (cfg 4 style): ONE song shared by all GPUs — MDX chunk "
+                         "ranges per rank + all-gather, RVC segments round-robin after a broadcast F0")
     ap.add_argument("--no-output-check", action="store_true", help="skip the finite / non-silent / F0-parity check of the timed graph")
     args = ap.parse_args()
 
@@ -436,6 +439,20 @@ def main():
     plans.graphs_enabled(True)
     install_tc_profiler.enabled = False
 
+    # ---- strong scaling of ONE song over the N GPUs of the node (every rank holds the same song; MDX chunk ranges per rank +
+    # one NCCL all-gather of the stem per pass; RVC: F0 on rank 0 -> broadcast -> segments round-robin -> all-gather of the PCM)
+    strong = None
+    if world > 1:
+        song0 = torch.from_numpy(synth_song(args.seconds, seed=0)).to(device)
+        for _ in range(3):          # plans / graphs for the sharded shapes
+            eng.cover_device(song0, group=dist.group.WORLD)
+        barrier()
+        strong_ms = timed_loop(lambda: eng.cover_device(song0, group=dist.group.WORLD), args.steps)
+        strong = {"value": args.seconds * args.steps / (strong_ms / 1000.0), "unit": UNIT, "ms_per_step": strong_ms / args.steps,
+                  "songs": 1, "gpus": world,
+                  "how": "one song on all GPUs: MDX chunk ranges per rank + all-gather of the stem per pass (3 passes), RVC F0 on "
+                         "rank 0 -> broadcast -> <= n_segments ranks convert segments -> all-gather; time = max over ranks"}
+
     audio_s = args.seconds * world
     value = audio_s * args.steps / (dev_ms / 1000.0)
     e2e_value = audio_s * args.steps / (e2e_ms / 1000.0)
@@ -490,7 +507,12 @@ def main():
             "gpu_launches": int(launches),
             "roofline": roof,
             "output_check": checks,
+            "strong_scaling": strong,
         }
+        if args.scaling == "strong" and strong is not None:
+            line.update({"value": strong["value"], "ms_per_step": strong["ms_per_step"], "scaling": "strong",
+                         "weak_scaling": {"value": value, "unit": UNIT, "ms_per_step": dev_ms / args.steps}})
+            line["config"]["songs"] = 1
         if world == 1 and not args.no_cpu_baseline:
             thr = best_cpu_threads()
             v, tot, detail = cpu_reference_sample(thr)

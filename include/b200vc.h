@@ -130,6 +130,21 @@ void b200vc_count_launches(int64_t n);
 /* sizeof(b200vc_tapgemm_params) as compiled: bindings verify their struct mirror against it */
 int64_t b200vc_sizeof_tapgemm_params(void);
 
+/* ---- launch plans: the per-shape model handle below Python -----------------------------------------------------------
+ * A forward pass of any model on the path (HuBERT / rmvpe / synthesizer / MDX-Net for ONE input shape) is a fixed sequence of
+ * the launches declared in this header over buffers the caller owns.  b200vc_plan_begin starts RECORDING on the calling
+ * thread: until b200vc_plan_end, every tap-GEMM / row-kernel entry point below (all whose pointers are device pointers; not
+ * the VC.pipeline glue group) is appended to the plan with a copy of its arguments instead of being launched.
+ * b200vc_plan_run(plan, stream) then enqueues the whole forward pass natively — one call per inference, from any host
+ * language, and capturable in a CUDA graph.  Replaces the Python-side loops over torch modules at
+ * infer_pack/models.py:745-751, rmvpe.py:254-258, fairseq HubertModel.extract_features, and the ort.run call at mdx.py:77. */
+typedef struct b200vc_plan b200vc_plan;
+int b200vc_plan_begin(b200vc_plan** out);
+int b200vc_plan_end(void);
+int b200vc_plan_size(const b200vc_plan* plan);                 /* number of recorded launches, -1 for NULL */
+int b200vc_plan_run(const b200vc_plan* plan, void* stream);
+int b200vc_plan_destroy(b200vc_plan* plan);
+
 /* ---- tap-GEMM ---- */
 int b200vc_tapgemm(const b200vc_tapgemm_params* p, int backend, void* stream);
 /* experimental: let the persistent tcgen05 kernel use 256-row tiles (two MMAs per weight tile); off by default */

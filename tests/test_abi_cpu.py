@@ -70,3 +70,27 @@ def test_committed_bench_line_carries_the_contract_keys():
     assert {"value", "unit", "cores", "kind", "sample"} <= set(b["cpu_baseline"]) and b["cpu_baseline"]["kind"] in ("port", "reference")
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(b["clocks"])
     assert not set(b["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+
+
+def test_plan_recorder_records_instead_of_launching():
+    """b200vc_plan_begin .. b200vc_plan_end: entry points called in between are stored (with a copy of their arguments), not
+    launched — so this works without a GPU; the plan reports its launch count; misuse returns an error code."""
+    from aicovergen_b200 import ops  # noqa: F401  (registers the argtypes)
+
+    lib = _ffi.lib()
+    h = ctypes.c_void_p()
+    assert lib.b200vc_plan_end() != 0 and b"no plan" in lib.b200vc_last_error()
+    assert lib.b200vc_plan_begin(ctypes.byref(h)) == 0 and h.value
+    h2 = ctypes.c_void_p()
+    assert lib.b200vc_plan_begin(ctypes.byref(h2)) != 0                       # already recording on this thread
+    fake = ctypes.c_void_p(0x1000)
+    assert lib.b200vc_axpby(fake, None, fake, 16, 1.0, 1.0, None) == 0
+    p = _ffi.TapGemmParams()
+    p.A, p.Wt, p.out = 0x1000, 0x2000, 0x3000
+    p.ntaps, p.BW, p.BH, p.N, p.Kc, p.OW, p.OH, p.OB = 1, 128, 1, 8, 8, 128, 1, 1
+    p.a_stride[0] = 1
+    assert lib.b200vc_tapgemm(ctypes.byref(p), 0, None) == 0
+    assert lib.b200vc_plan_run(h, None) != 0                                   # not while recording
+    assert lib.b200vc_plan_end() == 0
+    assert lib.b200vc_plan_size(h) == 2 and lib.b200vc_plan_size(None) == -1
+    assert lib.b200vc_plan_destroy(h) == 0
