@@ -82,6 +82,10 @@ class TapGemmParams(C.Structure):
         ("split", C.c_int32),
         ("o_split", C.c_int64),
         ("r_split", C.c_int64),
+        ("acc_in", C.c_void_p),
+        ("ai_sb", C.c_int64),
+        ("ai_sh", C.c_int64),
+        ("ai_sw", C.c_int64),
         ("taps", Tap * MAX_TAPS),
     ]
 

@@ -11,6 +11,7 @@ stay on the exact-fp32 kernel, which is also available for the whole net (backen
 """
 from __future__ import annotations
 
+import dataclasses
 import math
 from typing import Dict, List, Optional
 
@@ -255,6 +256,30 @@ class _RmvpePlan:
 
         S = be == tg.BACKEND_TC          # tensor-core path = 3xTF32 split operands; everything else exact-fp32 SIMT
         ex = tg.BACKEND_SIMT
+        # The tensor core rounds its fp32 accumulator toward zero at every K=8 step, so a long reduction (9 taps x 3 x 512
+        # channels = 1728 steps) drifts by ~1e-4 relative — too much for bit-exact F0 indices.  Reductions longer than KMAX
+        # are therefore split over several launches (subsets of the taps) whose partial sums are added on the CUDA cores
+        # (round-to-nearest) through the epilogue's `acc_in`; every accumulation chain stays <= KMAX / 8 steps.
+        KMAX = int(__import__("os").environ.get("B200VC_RMVPE_KMAX", "1728"))
+        scratch = torch.empty(T * N_MELS * 5 + 65536, **f32) if S else None
+
+        def add_tc(op):
+            p = op.params
+            if op.backend != tg.BACKEND_TC or p.Kc * p.ntaps <= KMAX:
+                return add(op)
+            per = max(1, KMAX // p.Kc)
+            groups = [op.taps[i:i + per] for i in range(0, len(op.taps), per)]
+            space = (p.OW, p.OH, p.OB)
+            nel = p.OB * p.OH * p.OW * p.N
+            assert nel <= scratch.numel(), (op.name, nel, scratch.numel())
+            scr = scratch[:nel].view(p.OB, p.OH, p.OW, p.N)
+            for gi, g in enumerate(groups):
+                if gi < len(groups) - 1:
+                    add(tg.TapGemm(op.a, op.w, g, space, tg.out_of(scr), Epi(acc_in=scr if gi else None), op.backend,
+                                   box=(p.BW, p.BH), name=f"{op.name}.k{gi}"))
+                else:
+                    add(tg.TapGemm(op.a, op.w, g, space, op.out, dataclasses.replace(op.epi, acc_in=scr), op.backend,
+                                   box=(p.BW, p.BH), name=op.name))
 
         def new(H_, W_, C_):
             return _Sp(H_, W_, C_, dev) if S else torch.empty(1, H_, W_, C_, **f32)
@@ -274,15 +299,15 @@ class _RmvpePlan:
                 return
             first = not isinstance(x, _Sp)       # Cin = 1: not TMA-addressable, stays on the exact-fp32 kernel
             xin = x if first else x.gemm_in
-            add(tg.conv2d(xin, W[key + (".w1" if first else ".w1s")], t1.plane0, 3, 3, (1, 1),
-                          Epi(bias=b1, act_pre=tg.ACT_RELU, split_out=t1.Ct), ex if first else be, name=key + ".c1"))
+            add_tc(tg.conv2d(xin, W[key + (".w1" if first else ".w1s")], t1.plane0, 3, 3, (1, 1),
+                             Epi(bias=b1, act_pre=tg.ACT_RELU, split_out=t1.Ct), ex if first else be, name=key + ".c1"))
             if key + ".ws" in W:
                 sc = torch.empty(1, H_, W_, cout, **f32)
-                add(tg.linear(xin, W[key + (".ws" if first else ".wss")], sc, Epi(bias=W[key + ".bs"]), ex if first else be, name=key + ".sc"))
+                add_tc(tg.linear(xin, W[key + (".ws" if first else ".wss")], sc, Epi(bias=W[key + ".bs"]), ex if first else be, name=key + ".sc"))
                 epi2 = Epi(bias=b2, act_pre=tg.ACT_RELU, res=sc, split_out=out.Ct)
             else:
                 epi2 = Epi(bias=b2, act_pre=tg.ACT_RELU, res=x.plane0, res_split=x.Ct, split_out=out.Ct)
-            add(tg.conv2d(t1.gemm_in, W[key + ".w2s"], out.plane0, 3, 3, (1, 1), epi2, be, name=key + ".c2"))
+            add_tc(tg.conv2d(t1.gemm_in, W[key + ".w2s"], out.plane0, 3, 3, (1, 1), epi2, be, name=key + ".c2"))
 
         # ---- encoder (rmvpe.py:61-119): level output goes straight into the decoder's concat buffer
         x = img
@@ -322,7 +347,7 @@ class _RmvpePlan:
                 ups = tg.conv_transpose2d_s2(x, W[f"dec{i}.up.w"], cat[..., :cc], 3, 1,
                                              Epi(bias=W[f"dec{i}.up.b"], act_pre=tg.ACT_RELU), ex, name=f"dec{i}.up")
             for op in ups:
-                add(op)
+                add_tc(op)
             x = cat
             for b in range(m.n_blocks):
                 out = new(Hc, Wc, cc)

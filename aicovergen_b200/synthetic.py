@@ -147,21 +147,21 @@ def make_rvc_checkpoint(sr_key: str = "40k", version: str = "v2", seed: int = 12
 # ---------------------------------------------------------------------------
 # rmvpe.pt  (E2E(4, 1, (2, 2)).state_dict(), rmvpe.py:221-258, 331-333)
 # ---------------------------------------------------------------------------
-def _bn(sd, g: _Gen, name: str, c: int):
+def _bn(sd, g: _Gen, name: str, c: int, gamma=(0.5, 1.5), beta=(0.0, 0.1)):
     """BatchNorm2d eval statistics per SURVEY.md §8(d) weights policy."""
-    sd[name + ".weight"] = g.uniform((c,), 0.5, 1.5)
-    sd[name + ".bias"] = g.normal((c,), 0.1)
+    sd[name + ".weight"] = g.uniform((c,), gamma[0], gamma[1])
+    sd[name + ".bias"] = g.normal((c,), beta[1], beta[0])
     sd[name + ".running_mean"] = g.normal((c,), 0.1)
     sd[name + ".running_var"] = g.uniform((c,), 0.5, 1.5)
     sd[name + ".num_batches_tracked"] = torch.tensor(0, dtype=torch.long)
 
 
-def _conv_block_res(sd, g: _Gen, p: str, cin: int, cout: int):
+def _conv_block_res(sd, g: _Gen, p: str, cin: int, cout: int, **bn):
     """ConvBlockRes (rmvpe.py:23-58): conv.0 / bn conv.1 / conv.3 / bn conv.4 (+ 1x1 shortcut if cin != cout)."""
     sd[p + "conv.0.weight"] = g.conv((cout, cin, 3, 3), 1.3)
-    _bn(sd, g, p + "conv.1", cout)
+    _bn(sd, g, p + "conv.1", cout, **bn)
     sd[p + "conv.3.weight"] = g.conv((cout, cout, 3, 3), 0.45)
-    _bn(sd, g, p + "conv.4", cout)
+    _bn(sd, g, p + "conv.4", cout, **bn)
     if cin != cout:
         sd[p + "shortcut.weight"] = g.conv((cout, cin, 1, 1), 0.8)
         sd[p + "shortcut.bias"] = g.normal((cout,), 0.05)
@@ -169,8 +169,9 @@ def _conv_block_res(sd, g: _Gen, p: str, cin: int, cout: int):
 
 def make_rmvpe_state_dict(seed: int = 4321, n_blocks: int = 4, en_de_layers: int = 5, inter_layers: int = 4,
                           en_out_channels: int = 16, n_mels: int = 128, n_gru_hidden: int = 256,
-                          n_class: int = 360) -> Dict[str, torch.Tensor]:
+                          n_class: int = 360, bn_gamma=(0.5, 1.5), bn_beta=(0.0, 0.1)) -> Dict[str, torch.Tensor]:
     g = _Gen(seed)
+    bn = dict(gamma=bn_gamma, beta=bn_beta)
     sd: Dict[str, torch.Tensor] = {}
     # input BN over the single mel "channel": keep log-mel roughly standardised
     sd["unet.encoder.bn.weight"] = torch.tensor([0.35])
@@ -181,22 +182,22 @@ def make_rmvpe_state_dict(seed: int = 4321, n_blocks: int = 4, en_de_layers: int
     cin, cout = 1, en_out_channels
     for i in range(en_de_layers):
         for b in range(n_blocks):
-            _conv_block_res(sd, g, f"unet.encoder.layers.{i}.conv.{b}.", cin if b == 0 else cout, cout)
+            _conv_block_res(sd, g, f"unet.encoder.layers.{i}.conv.{b}.", cin if b == 0 else cout, cout, **bn)
         cin, cout = cout, cout * 2
     # intermediate: first 256 -> 512, then 512 -> 512
     ci, co = cin, cout
     for i in range(inter_layers):
         for b in range(n_blocks):
-            _conv_block_res(sd, g, f"unet.intermediate.layers.{i}.conv.{b}.", ci if b == 0 else co, co)
+            _conv_block_res(sd, g, f"unet.intermediate.layers.{i}.conv.{b}.", ci if b == 0 else co, co, **bn)
         ci = co
     dc = co
     for i in range(en_de_layers):
         do = dc // 2
         # ConvTranspose2d weight [Cin, Cout, 3, 3]; stride 2 -> ~2.25 taps per output
         sd[f"unet.decoder.layers.{i}.conv1.0.weight"] = g.normal((dc, do, 3, 3), 1.2 / math.sqrt(dc * 2.25))
-        _bn(sd, g, f"unet.decoder.layers.{i}.conv1.1", do)
+        _bn(sd, g, f"unet.decoder.layers.{i}.conv1.1", do, **bn)
         for b in range(n_blocks):
-            _conv_block_res(sd, g, f"unet.decoder.layers.{i}.conv2.{b}.", do * 2 if b == 0 else do, do)
+            _conv_block_res(sd, g, f"unet.decoder.layers.{i}.conv2.{b}.", do * 2 if b == 0 else do, do, **bn)
         dc = do
     sd["cnn.weight"] = g.conv((3, en_out_channels, 3, 3), 1.0)
     sd["cnn.bias"] = g.normal((3,), 0.05)
@@ -290,13 +291,14 @@ def make_ivf_index_data(base_feats: torch.Tensor, n_total: int = 87243, nlist: i
 # The .onnx graphs are not in the reference repo: names follow the public KUIELab/UVR module layout.
 # ---------------------------------------------------------------------------
 def make_mdx_state_dict(dim_f: int = 3072, dim_t: int = 256, g: int = 48, l: int = 3, n: int = 5, bn: int = 8,
-                        k: int = 3, dim_c: int = 4, seed: int = 2024) -> Dict[str, torch.Tensor]:
+                        k: int = 3, dim_c: int = 4, seed: int = 2024, bn_gamma=(0.7, 1.3), bn_beta=(0.0, 0.1)) -> Dict[str, torch.Tensor]:
+    """bn_gamma = U(lo, hi) range of the BatchNorm scales, bn_beta = (mean, std) of the BatchNorm shifts."""
     gen = _Gen(seed)
     sd: Dict[str, torch.Tensor] = {}
 
     def bnorm(name, c):
-        sd[name + ".weight"] = gen.uniform((c,), 0.7, 1.3)
-        sd[name + ".bias"] = gen.normal((c,), 0.1)
+        sd[name + ".weight"] = gen.uniform((c,), bn_gamma[0], bn_gamma[1])
+        sd[name + ".bias"] = gen.normal((c,), bn_beta[1], bn_beta[0])
         sd[name + ".running_mean"] = gen.normal((c,), 0.1)
         sd[name + ".running_var"] = gen.uniform((c,), 0.6, 1.4)
 
@@ -381,7 +383,7 @@ def calibrate_mdx_batchnorm(sd: Dict[str, torch.Tensor], x: torch.Tensor, eps: f
 
 
 def calibrate_rmvpe(sd: Dict[str, torch.Tensor], audio: torch.Tensor, peak_sigma_bins: float = 1.3,
-                    logit_gain: float = 4.0, logit_bias: float = -5.2, voicing_sigma: float = 2.0,
+                    logit_gain: float = 4.0, logit_bias: float = -4.8, voicing_sigma: float = 2.0,
                     eps: float = 1e-5) -> Dict[str, torch.Tensor]:
     """Gives a synthetic rmvpe checkpoint the two properties of a TRAINED one that the F0 decode relies on:
       * every BatchNorm's running statistics equal the statistics of its own input on a calibration clip (what training
@@ -487,7 +489,11 @@ def make_rmvpe_trained_like(seed: int = 4321) -> Dict[str, torch.Tensor]:
     """make_rmvpe_state_dict + calibrate_rmvpe on the seeded calibration clip (cached per process)."""
     key = ("rmvpe", seed)
     if key not in _TRAINED_LIKE_CACHE:
-        _TRAINED_LIKE_CACHE[key] = calibrate_rmvpe(make_rmvpe_state_dict(seed), calibration_clip())
+        # BatchNorm shifts well above zero / small scales: the ReLUs work mostly in their linear range, which keeps a RANDOM
+        # deep BatchNorm-ReLU stack from being chaotic (such stacks amplify any perturbation ~1.3x per layer at init; trained
+        # networks do not).  Without it fp32 rounding noise grows to 1e-5 of salience, TF32 noise to 10 % of an MDX stem.
+        _TRAINED_LIKE_CACHE[key] = calibrate_rmvpe(make_rmvpe_state_dict(seed, bn_gamma=(0.3, 0.5), bn_beta=(0.6, 0.1)),
+                                                   calibration_clip())
     return _TRAINED_LIKE_CACHE[key]
 
 
@@ -520,6 +526,8 @@ def make_mdx_trained_like(dim_f: int = 3072, dim_t: int = 256, n_fft: int = 7680
     seconds of CPU time at the full 3072-bin geometry."""
     key = ("mdx", dim_f, dim_t, n_fft, seed, cal_frames, tuple(sorted(kw.items())))
     if key not in _TRAINED_LIKE_CACHE:
+        kw.setdefault("bn_gamma", (0.3, 0.5))          # near-linear BatchNorm-ReLU operating point: see make_rmvpe_trained_like
+        kw.setdefault("bn_beta", (0.6, 0.1))
         sd = make_mdx_state_dict(dim_f=dim_f, dim_t=dim_t, seed=seed, **kw)
         n_lvl = int(sd["_meta"][4])
         T = max(cal_frames, 2 ** n_lvl)

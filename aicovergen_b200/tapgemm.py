@@ -139,6 +139,7 @@ class Epi:
     round_out2: bool = False
     split_out: int = 0          # > 0: write `out` as 3xTF32 planes hi | lo | hi, `split_out` elements apart (b200vc.h `split`)
     res_split: int = 0          # > 0: `res` is a split tensor, value = res[..] + res[.. + res_split]
+    acc_in: Optional[torch.Tensor] = None   # fp32 partial sums [.., N] channels-last over the GEMM pixel space, added to the accumulator
 
 
 def _tile_box(OW: int, OH: int) -> Tuple[int, int]:
@@ -241,6 +242,16 @@ class TapGemm:
             assert epi.split_out % 4 == 0
         if epi.res_split:
             assert epi.res is not None and epi.res.dtype == torch.float32 and epi.res_split % 4 == 0
+        if epi.acc_in is not None:
+            ai = epi.acc_in
+            assert ai.dtype == torch.float32 and ai.stride(-1) == 1 and ai.data_ptr() % 16 == 0
+            st = list(ai.stride())
+            while len(st) < 4:
+                st.insert(0, 0)
+            assert all(s_ % 4 == 0 for s_ in st[:3])
+            p.acc_in = ai.data_ptr()
+            p.ai_sb, p.ai_sh, p.ai_sw = int(st[0]), int(st[1]), int(st[2])
+            self._keep.append(ai)
         for i, (c_off, dw, dh, dp, widx) in enumerate(self.taps):
             t = p.taps[i]
             t.c_off, t.dw, t.dh, t.dp, t.widx = int(c_off), int(dw), int(dh), int(dp), int(widx)

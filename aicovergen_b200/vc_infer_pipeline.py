@@ -220,7 +220,7 @@ class VC(object):
         else:
             a32 = torch.from_numpy(np.ascontiguousarray(audio, dtype=np.float32)).to(dev)
         if self.exact_hpf:
-            audio = torch.from_numpy(signal.filtfilt(bh, ah, a32.cpu().numpy())).to(dev)
+            audio = torch.from_numpy(np.ascontiguousarray(signal.filtfilt(bh, ah, a32.cpu().numpy()))).to(dev)
         else:
             audio = ops.filtfilt(a32, bh, ah)                      # fp64 on the device (sos cascade)
         opt_ts = self._cut_points(audio)

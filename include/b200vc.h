@@ -117,6 +117,11 @@ typedef struct b200vc_tapgemm_params {
                            bit0: `out` is written as three planes hi | lo | hi, plane p at element offset p * o_split;
                            bit1: `res` is such a split tensor: the residual value is res[..] + res[.. + r_split].       */
   int64_t o_split, r_split;
+  const float* acc_in;  /* optional fp32 partial sums (channels-last, element (b,h,w,n) at b*ai_sb + h*ai_sh + w*ai_sw + n) added to
+                           the accumulator BEFORE the epilogue: a long reduction is split over several launches (subsets of the
+                           taps) so that no tensor-core accumulation chain is longer than a few hundred K=8 steps — the tensor
+                           core rounds its fp32 accumulator toward zero, CUDA-core adds between launches round to nearest.     */
+  int64_t ai_sb, ai_sh, ai_sw;
   b200vc_tap taps[B200VC_MAX_TAPS];
 } b200vc_tapgemm_params;
 

@@ -76,6 +76,13 @@ def emulate(op) -> None:
             acc[sel] += vals[sel] @ Wm.t()
     # ---- epilogue
     v = acc
+    if getattr(epi, "acc_in", None) is not None:
+        ai = epi.acc_in
+        st = list(ai.stride())
+        while len(st) < 4:
+            st.insert(0, 0)
+        aif = _flat(ai).double()
+        v = v + aif[(ai.storage_offset() + bb * st[0] + hh * st[1] + ww * st[2])[:, None] + torch.arange(N)[None, :]]
     if epi.row_scale_pre is not None:
         v = v * epi.row_scale_pre.double()[(hh * OW + ww)][:, None]
     if epi.bias is not None:

@@ -37,7 +37,9 @@ def test_rmvpe_f0_parity(seconds, weights):
     f0_ref = orm.decode(hid_ref.numpy().copy(), 0.03)
     pitch_ref, pitchf_ref = orm.coarse_pitch(f0_ref, 0)
 
-    net = RMVPEB200(sd, device="cuda:0")
+    # trained-like weights: the default backend (U-Net on tcgen05, 3xTF32 split operands); round-1 raw weights: the exact-fp32
+    # SIMT kernel (their unstructured salience head turns any rounding difference into a different octave)
+    net = RMVPEB200(sd, device="cuda:0", backend=tg.BACKEND_TC if weights == "trained_like" else tg.BACKEND_SIMT)
     sal = net.salience_from_audio(torch.from_numpy(x).cuda()).cpu()
     err = (sal - hid_ref).abs().max().item()
     print(f"[rmvpe {weights} {seconds}s] salience max abs err {err:.3e} over {tuple(sal.shape)}")
@@ -49,13 +51,14 @@ def test_rmvpe_f0_parity(seconds, weights):
     rel = np.abs(f0 - f0_ref)[both] / f0_ref[both]
     print(f"[rmvpe {weights} {seconds}s] coarse-pitch mismatches {mism}/{len(pitch)}; f0 max rel diff {rel.max():.3e}; voiced "
           f"{(f0_ref > 0).mean():.2f}; {len(np.unique(pitch_ref))} distinct levels")
-    assert err < (3e-3 if weights == "trained_like" else 3e-4)
+    assert err < (1.5e-3 if weights == "trained_like" else 3e-4)
     assert mism == 0, "coarse pitch indices must match the reference bit for bit"
     assert np.array_equal(f0 > 0, f0_ref > 0) and rel.max() < 1e-3
 
 
+@pytest.mark.parametrize("backend,bar", [(tg.BACKEND_TC, 2e-4), (tg.BACKEND_SIMT, 5e-5)])
 @pytest.mark.parametrize("kind", ["sweep", "vocal"])
-def test_rmvpe_net_parity_given_logmel(kind):
+def test_rmvpe_net_parity_given_logmel(kind, backend, bar):
     """`RMVPE.mel2hidden(mel)` plug point (rmvpe.py:350-357): U-Net + BiGRU + head on the ORACLE's log-mel, i.e. without the
     STFT front-end in the comparison — the network's own error against the fp32 CPU oracle."""
     import sys, os
@@ -69,13 +72,14 @@ def test_rmvpe_net_parity_given_logmel(kind):
     x = sweep(4.0) if kind == "sweep" else vocal_like(4.0, seed=9)
     mel = orm.log_mel(torch.from_numpy(x)[None])
     ref = orm.mel2hidden(sd, mel)[0]
-    net = RMVPEB200(sd, device="cuda:0")
+    net = RMVPEB200(sd, device="cuda:0", backend=backend)
     got = net.mel2hidden(mel.cuda())[0].cpu()
     err = (got - ref).abs().max().item()
     f0, f0_ref = net.decode(got.numpy()), orm.decode(ref.numpy().copy(), 0.03)
     mism = int((orm.coarse_pitch(f0)[0] != orm.coarse_pitch(f0_ref)[0]).sum())
-    print(f"[rmvpe net | oracle log-mel, {kind}] salience max abs err {err:.3e}; coarse-pitch mismatches {mism}/{len(f0)}")
-    assert got.shape == ref.shape and err < 5e-5 and mism == 0
+    print(f"[rmvpe net {'3xTF32 tcgen05' if backend == tg.BACKEND_TC else 'fp32 simt'} | oracle log-mel, {kind}] salience max abs err {err:.3e}; "
+          f"coarse-pitch mismatches {mism}/{len(f0)}")
+    assert got.shape == ref.shape and err < bar and mism == 0
     # the front-end alone: device log-mel vs torch.stft log-mel on bins above the clamp region
     pl = net._plan(len(x))
     net.salience_from_audio(torch.from_numpy(x).cuda())
