@@ -374,11 +374,14 @@ def calibrate_mdx_batchnorm(sd: Dict[str, torch.Tensor], x: torch.Tensor, eps: f
             t = t * skips[-i - 1]
             t = tfc_tdf(f"decoding_blocks.{i}", t)
         if out_gain > 0:
-            # a separator's output spectrogram has the level of its input: rescale the final 1x1 conv accordingly
+            # a separator's output has the level of its input: rescale the final 1x1 conv so that the FLUCTUATING part of the
+            # output spectrogram (what survives the iSTFT as audio; a per-bin constant is only a click per frame) has
+            # out_gain x the input's level, and drop most of its constant part
             y = F.conv2d(t.transpose(-1, -2), out["final_conv.0.weight"], out["final_conv.0.bias"])
-            sc = out_gain * x.float().pow(2).mean().sqrt() / y.pow(2).mean().sqrt().clamp_min(1e-12)
+            fl = y - y.mean(dim=(0, 2, 3), keepdim=True)
+            sc = out_gain * x.float().pow(2).mean().sqrt() / fl.pow(2).mean().sqrt().clamp_min(1e-12)
             out["final_conv.0.weight"] = out["final_conv.0.weight"] * sc
-            out["final_conv.0.bias"] = out["final_conv.0.bias"] * sc
+            out["final_conv.0.bias"] = (out["final_conv.0.bias"] - y.mean(dim=(0, 2, 3))) * sc
     return out
 
 
@@ -537,5 +540,5 @@ def make_mdx_trained_like(dim_f: int = 3072, dim_t: int = 256, n_fft: int = 7680
         seg = song[:, 22050:22050 + hop * (T - 1)]
         z = torch.stft(seg, n_fft=n_fft, hop_length=hop, window=torch.hann_window(n_fft), center=True, return_complex=True)
         z = torch.view_as_real(z).permute(0, 3, 1, 2)[:, :, :dim_f]                 # [ch, ri, F, T]
-        _TRAINED_LIKE_CACHE[key] = calibrate_mdx_batchnorm(sd, z.reshape(1, 4, dim_f, T), out_gain=0.05)
+        _TRAINED_LIKE_CACHE[key] = calibrate_mdx_batchnorm(sd, z.reshape(1, 4, dim_f, T), out_gain=0.3)
     return _TRAINED_LIKE_CACHE[key]

@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -33,6 +34,8 @@ sys.path.insert(0, ROOT)
 SONG_SECONDS = 240
 SR = 44100
 METRIC = "audio_seconds_per_second_full_cover_pipeline_4min_44k1_stereo"
+DTYPE_NOTE = ("fp16 operands (MDX-Net U-Net, tcgen05 kind::f16) + tf32 (other tensor-core GEMMs; rmvpe as 3xTF32 split operands), fp32 "
+              "accumulate; fp32/fp64 row kernels")
 UNIT = "audio-s/s"
 
 
@@ -199,7 +202,15 @@ def install_tc_profiler():
             orig(self, stream, backend)
             e.record()
             rows = p.OW * p.OH * p.OB
-            records.append((self._family, self.flops(), 4.0 * rows * (p.N + p.Kc), s, e))
+            es_in = self.a.t.element_size()
+            es_out = self.out.t.element_size()
+            flops = self.flops()
+            if self.name in ("mdx.stft", "mdx.istft"):
+                # a DFT restricted to dim_f bins run as a dense GEMM: count what an FFT of that frame would cost
+                # (2.5 n log2 n real-FFT flops), not the 2*M*N*K of the GEMM, so the DFT does not inflate the roofline
+                n_fft = p.Kc if self.name == "mdx.stft" else p.N
+                flops = rows * 2.5 * n_fft * math.log2(n_fft)
+            records.append((self._family, flops, float(rows) * (es_out * p.N + es_in * p.Kc), s, e, bool(p.dtype & 1), self.name))
         else:
             orig(self, stream, backend)
 
@@ -347,6 +358,136 @@ def run_reference(args, rank):
 
 
 # --------------------------------------------------------------------------------------------------------------
+# BASELINE.json configs 1-4 as separate bench lines (--config rmvpe10 | hubert30 | vc60 | mdx4min)
+# --------------------------------------------------------------------------------------------------------------
+def run_config(args, device):
+    """One JSON line for one of BASELINE.json's per-operator configs: device-resident value, end-to-end value through the
+    reference-facing array API (host buffers in, host result out), and the CPU oracle on the same input (bounded sample)."""
+    from aicovergen_b200 import _ffi
+    hsd, rsd, cpt, mdx_w = bench_checkpoints()
+    name = args.config
+    sr16 = 16000
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=device)
+    cpu = None
+    if name == "rmvpe10":
+        from aicovergen_b200.rmvpe import RMVPEB200
+        from oracle import rmvpe as orm
+        seconds = 10.0
+        t = np.arange(int(sr16 * seconds)) / sr16
+        x = (0.5 * np.sin(2 * np.pi * (100 * t + 45 * t * t))).astype(np.float32)
+        net = RMVPEB200(rsd, device=device)
+        xd = torch.from_numpy(x).to(device)
+        dev_fn = lambda: net.infer_from_audio_device(xd, 0.03)
+        e2e_fn = lambda: net.infer_from_audio(x, 0.03)
+        h2d, d2h = x.nbytes, 8 * (1 + len(x) // 160)
+        cpu_fn, cpu_units = (lambda: orm.infer_from_audio(rsd, x, 0.03)), seconds
+        workload = "cfg 1: rmvpe F0 on a 10 s 100->1000 Hz sine sweep @16 kHz (RMVPE.infer_from_audio, thred 0.03)"
+    elif name == "hubert30":
+        from aicovergen_b200.hubert import HubertB200
+        from oracle import hubert as ohub
+        seconds = 30.0
+        g = torch.Generator().manual_seed(0)
+        n = int(sr16 * seconds)
+        tt = torch.arange(n) / sr16
+        x = (0.1 * torch.randn(n, generator=g) + 0.5 * torch.sin(2 * np.pi * (100 * tt + 15 * tt * tt))).float()[None]
+        net = HubertB200(hsd, device)
+        xd = x.to(device)
+        dev_fn = lambda: net.extract_features(source=xd, padding_mask=None, output_layer=12)
+        xp = x.pin_memory()
+        e2e_fn = lambda: net.extract_features(source=xp.to(device, non_blocking=True), padding_mask=None, output_layer=12)[0].cpu()
+        h2d, d2h = x.numel() * 4, 1499 * 768 * 4
+        cpu_fn, cpu_units = (lambda: ohub.extract_features(hsd, x, 12)), seconds
+        workload = "cfg 2: HuBERT-base layer-12 features of 30 s @16 kHz (extract_features, T = 1499)"
+    elif name == "vc60":
+        from aicovergen_b200 import rvc
+        from aicovergen_b200.faiss_io import write_ivfflat
+        from aicovergen_b200.rmvpe import RMVPEB200
+        from aicovergen_b200.synthetic import make_ivf_index_data
+        from oracle import pipeline as opipe
+        seconds = 60.0
+        x = synth_song(seconds * 44100 / 48000 + 1.0, 7).mean(0)[::3][: int(sr16 * seconds)].astype(np.float32).copy()
+        cfg = rvc.Config(device, True)
+        hub = rvc.load_hubert(device, True, {"model": hsd})
+        cpt2, version, net_g, tgt_sr, vc = rvc.get_vc(device, True, cfg, dict(cpt))
+        vc.model_rmvpe = RMVPEB200(rsd, device=device)
+        clip = torch.from_numpy(synth_song(20.0, 99).mean(0)[::3].copy())[None].to(device)
+        feats = hub.extract_features(source=clip, padding_mask=None, output_layer=12)[0][0].cpu()
+        cent, vecs = make_ivf_index_data(feats, n_total=87243, nlist=2237, lloyd=False)
+        from aicovergen_b200.index import write_index_npz
+        path = os.path.join(os.environ.get("TMPDIR", "/tmp"), f"b200vc_bench_cfg3_{os.getpid()}.npz")
+        write_index_npz(path, cent, vecs)
+        xd = torch.from_numpy(x).to(device)
+        call = lambda a: vc.pipeline(hub, net_g, 0, a, "x.wav", [0, 0, 0], 0, "rmvpe", path, 0.5, 1, 3, tgt_sr, 0, 0.25, version, 0.33, 128)
+
+        def dev_fn():
+            vc.return_device = True
+            try:
+                return call(xd)
+            finally:
+                vc.return_device = False
+        e2e_fn = lambda: call(x)
+        h2d, d2h = x.nbytes, 2399200 * 2
+        cpu_fn, cpu_units = (lambda: opipe.pipeline(hsd, cpt, rsd, x[: 20 * sr16].copy(), index=None, seed=0)), 20.0
+        workload = "cfg 3: VC.pipeline on a 60 s vocal, rvc.Config (3,10,60,65), rmvpe, IVF2237 x 87243 index_rate 0.5, v2 40k (CPU: 20 s, no index)"
+    elif name == "mdx4min":
+        from aicovergen_b200.mdx import MDX, MDXModel, run_mdx_arrays, run_mdx_device
+        from oracle import mdx as om
+        seconds = 240.0
+        wave = synth_song(seconds, 0)
+        sess = MDX(mdx_w[0], MDXModel(device, 3072, 256, 7680, stem_name="Vocals", compensation=1.009), int(device.split(":")[-1]))
+        wd = torch.from_numpy(wave).to(device)
+        dev_fn = lambda: run_mdx_device(sess, wd, denoise=False, m_threads=2)
+        e2e_fn = lambda: run_mdx_arrays(sess, wave, denoise=False, m_threads=2)
+        h2d, d2h = wave.nbytes, 2 * wave.nbytes
+        mp = om.MdxParams(3072, 256, 7680)
+        xc = torch.from_numpy(wave[:, :mp.chunk_size].copy())[None]
+        cpu_fn = lambda: (mp.istft(om.convtdfnet(mdx_w[0], mp.stft(xc))))
+        cpu_units = seconds / 44.0            # one of the 44 chunk inferences of the sweep
+        workload = "cfg 4: mdx.run_mdx arithmetic (Kim_Vocal_2 geometry 3072x256/7680, denoise=False) on a 4-min 44.1 kHz stereo song, 44 chunk inferences (CPU: 1 chunk x44)"
+    else:
+        raise SystemExit(f"unknown --config {name}")
+
+    def timed(fn, steps):
+        tot = 0.0
+        for _ in range(steps):
+            flush.fill_(1.0)
+            torch.cuda.synchronize()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            fn()
+            e.record()
+            torch.cuda.synchronize()
+            tot += s.elapsed_time(e)
+        return tot
+
+    for _ in range(max(args.warmup, 3)):
+        dev_fn()
+    sampler = ClockSampler(int(device.split(":")[-1]))
+    sampler.start()
+    l0 = _ffi.launch_count()
+    dev_ms = timed(dev_fn, args.steps)
+    launches = _ffi.launch_count() - l0
+    e2e_fn()
+    e2e_ms = timed(e2e_fn, args.steps)
+    sampler.stop()
+    line = {"metric": f"audio_seconds_per_second_{name}", "value": seconds * args.steps / (dev_ms / 1e3), "unit": UNIT, "n_gpus": 1,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "tf32/fp16 tensor-core GEMMs + fp32 row kernels", "data": "synthetic",
+            "config": {"workload": workload, "l2": "256 MB buffer written between steps"}, "clocks": sampler.summary(),
+            "e2e": {"value": seconds * args.steps / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches)}
+    if not args.no_cpu_baseline:
+        thr = best_cpu_threads()
+        torch.set_num_threads(thr)
+        t0 = time.perf_counter()
+        cpu_fn()
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": cpu_units / dt, "unit": UNIT, "cores": thr, "kind": "port", "sample": f"{cpu_units:.1f} audio-s of the workload in {dt:.1f} s (oracle/)"}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -355,6 +496,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--seconds", type=float, default=float(SONG_SECONDS), help="song length (default: the 4-min headline config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="cover", choices=["cover", "rmvpe10", "hubert30", "vc60", "mdx4min"],
+                    help="cover (default): the headline 4-min song_cover_pipeline graph; the others: BASELINE.json configs 1-4 as their own lines")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak (default, BASELINE cfg 5): one song per GPU; strong (cfg 4 style): ONE song shared by all GPUs — MDX chunk "
                          "ranges per rank + all-gather, RVC segments round-robin after a broadcast F0")
@@ -377,6 +520,13 @@ def main():
     device = f"cuda:{local_rank}"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(device))
+    if args.config != "cover":
+        if rank == 0:
+            run_config(args, device)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     warm = max(args.warmup, 3)
     records = install_tc_profiler()
     eng = build_engine(device, rank)
@@ -457,45 +607,76 @@ def main():
     value = audio_s * args.steps / (dev_ms / 1000.0)
     e2e_value = audio_s * args.steps / (e2e_ms / 1000.0)
 
-    # ---- roofline of the dominant kernel family (tcgen05 tap-GEMM, by tile width)
+    # ---- roofline of the dominant kernel family (tcgen05 tap-GEMM, by tile width) and of the whole step
     pk, pk_src = peaks()
-    fam = {}
-    for tile_n, fl, by, s, e in records:
-        d = fam.setdefault(tile_n, [0.0, 0.0, 0.0, 0])
-        d[0] += s.elapsed_time(e)
+    f16_peak = pk["bf16_tflops_sustained"]            # fp16/bf16 dense, measured (sustained figure: kernels timed inside a long step)
+    tf32_peak = f16_peak / 2.0                         # TF32 runs at half the fp16 rate on tcgen05 (nominal ratio; not measured separately)
+    fam, layer = {}, {}
+    for tile_n, fl, by, s, e, is_f16, lname in records:
+        ms_i = s.elapsed_time(e)
+        d = fam.setdefault(tile_n, [0.0, 0.0, 0.0, 0, 0.0])
+        d[0] += ms_i
         d[1] += fl
         d[2] += by
         d[3] += 1
-    roof = None
+        d[4] += fl / (f16_peak if is_f16 else tf32_peak)          # roofline time of this launch, TFLOP / (TFLOP/s) units
+        key = "".join("#" if c.isdigit() else c for c in lname)
+        ly = layer.setdefault(key, [0.0, 0.0, 0])
+        ly[0] += ms_i
+        ly[1] += fl
+        ly[2] += 1
+    roof, step_roof = None, None
+    traffic = None
+    try:    # per-launch DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum, one ncu --set full capture) of the
+            # representative launch of the dominant family: profiles/r02_dominant_traffic.json
+        with open(os.path.join(ROOT, "profiles", "r02_dominant_traffic.json")) as f:
+            traffic = json.load(f)
+    except Exception:
+        pass
     if fam:
         top = max(fam.items(), key=lambda kv: kv[1][0])
-        tn, (ms, fl, by, cnt) = top
+        tn, (ms, fl, by, cnt, roof_t) = top
+        tot_ms = sum(v[0] for v in fam.values())
+        tot_fl = sum(v[1] for v in fam.values())
+        tot_roof = sum(v[4] for v in fam.values())
+        top_layers = sorted(layer.items(), key=lambda kv: -kv[1][0])[:6]
         common = {"launches": cnt, "avg_launch_ms": round(ms / cnt, 4),
                   "share_of_step": round(ms / prof_ms, 4),
                   "algorithmic_tflops": round(fl / (ms / 1000.0) / 1e12, 2),
                   "algorithmic_gbs": round(by / (ms / 1000.0) / 1e9, 1),
-                  "traffic_note": "per-launch DRAM bytes of representative launches: profiles/r01_ncu_kernels.md",
                   "families_ms_per_step": {str(k): round(v[0], 2) for k, v in sorted(fam.items())},
-                  "profiled_step_ms": round(prof_ms, 1)}
+                  "top_layers_ms": {k: {"ms": round(v[0], 2), "tflops": round(v[1] / v[0] / 1e9, 1), "launches": v[2]} for k, v in top_layers},
+                  "profiled_step_ms": round(prof_ms, 1),
+                  "flops_note": "2*M*N*K per tap-GEMM launch; the MDX STFT/iSTFT DFT-GEMMs are counted at FFT cost (2.5 n log2 n per frame)"}
+        if traffic and traffic.get("family") == tn:
+            common["traffic_detail"] = traffic
         if tn == "ws":
             # small-channel convolutions: arithmetic intensity below the machine balance -> HBM roofline
             achieved = by / (ms / 1000.0) / 1e9
-            roof = {"kernel": "tapgemm_ws_kernel (weight-stationary + halo, tcgen05.mma kind::tf32)", "bound": "hbm",
+            roof = {"kernel": "tapgemm_ws_kernel (weight-stationary + halo, tcgen05.mma kind::tf32 / kind::f16)", "bound": "hbm",
                     "achieved": round(achieved, 1), "peak": round(pk["hbm_gbs"], 1), "unit": "GB/s",
-                    "frac": round(achieved / pk["hbm_gbs"], 4), "traffic": None, "peak_source": f"{pk_src} hbm_gbs", **common}
+                    "frac": round(achieved / pk["hbm_gbs"], 4), "traffic": (traffic or {}).get("dram_bytes_per_launch") if (traffic or {}).get("family") == tn else None,
+                    "peak_source": f"{pk_src} hbm_gbs", **common}
         else:
             achieved = fl / (ms / 1000.0) / 1e12
-            tf32_peak = pk["bf16_tflops_sustained"] / 2.0
-            roof = {"kernel": f"tapgemm_{tn} (persistent tcgen05.mma kind::tf32, double-buffered TMEM)", "bound": "tensor",
-                    "achieved": round(achieved, 2), "peak": round(tf32_peak, 1), "unit": "TFLOP/s",
-                    "frac": round(achieved / tf32_peak, 4), "traffic": None,
-                    "peak_source": f"{pk_src} bf16_tflops_sustained / 2 (nominal tf32:bf16 ratio)", **common}
+            eff_peak = fl / roof_t if roof_t > 0 else tf32_peak        # FLOP-weighted mix of the fp16 and TF32 peaks (TFLOP/s)
+            roof = {"kernel": f"tapgemm_{tn} (persistent tcgen05.mma kind::tf32 / kind::f16, double-buffered TMEM)", "bound": "tensor",
+                    "achieved": round(achieved, 2), "peak": round(eff_peak, 1), "unit": "TFLOP/s",
+                    "frac": round(achieved / eff_peak, 4),
+                    "traffic": (traffic or {}).get("dram_bytes_per_launch") if (traffic or {}).get("family") == tn else None,
+                    "peak_source": f"{pk_src} bf16_tflops_sustained for kind::f16 launches, half of it for kind::tf32 launches "
+                                   "(nominal 2:1; a TF32 peak was not measured separately), weighted by the FLOPs of each kind", **common}
+        step_roof = {"tensor_tflop_per_step": round(tot_fl / 1e12, 2), "gemm_ms_per_step": round(tot_ms, 1),
+                     "step_tflops": round(tot_fl / (prof_ms / 1000.0) / 1e12, 1),
+                     "frac_of_tensor_roofline_whole_step": round((tot_roof * 1e-12 * 1000.0) / prof_ms, 4),
+                     "frac_of_tensor_roofline_inside_gemms": round((tot_roof * 1e-12 * 1000.0) / tot_ms, 4),
+                     "ms_outside_tcgen05_gemms": round(prof_ms - tot_ms, 1)}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "tf32 (tensor-core GEMMs, fp32 accumulate) + fp32 (rmvpe, IVF coarse, row kernels)", "data": "synthetic",
+            "dtype": DTYPE_NOTE, "data": "synthetic",
             "config": {"workload": f"song_cover_pipeline stage graph on one {args.seconds:.0f}-s 44.1 kHz stereo song per GPU: 3 MDX-Net passes "
                                    "(3072x256/7680, 2048x256/5120, 3072x512/6144; denoise=True) + VC.pipeline (HuBERT-base, rmvpe, "
                                    "IVF2237 x 87243 index_rate 0.5, v2 40k synthesizer) + mix",
@@ -506,6 +687,7 @@ def main():
                     "d2h_bytes_per_step": int(out_host["cover"].nbytes) * world, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches),
             "roofline": roof,
+            "step_roofline": step_roof,
             "output_check": checks,
             "strong_scaling": strong,
         }

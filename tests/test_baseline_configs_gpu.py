@@ -123,10 +123,12 @@ def test_cfg4_mdx_4min_sweep_sampled_chunks():
         half_start = 0 if h == 0 else n // 2 - 44100
         keep_lo = half_start + (0 if h == 0 else 44100)
         keep_hi = half_start + half.shape[1] - (44100 if h == 0 else 0)
-        for i in sorted(set([0, 21]) | set(rng.choice(22, 2, replace=False).tolist())):
-            w = mp.istft(net(mp.stft(mix[i:i + 1])))[0, :, trim:-trim].numpy() * peak          # [2, gen]
+        for i in sorted(set([0, 20, 21]) | set(rng.choice(22, 2, replace=False).tolist())):
             a = half_start + i * gen
             lo, hi = max(a, keep_lo), min(a + gen, keep_hi, half_start + half.shape[1])
+            if hi <= lo:          # the chunk lies entirely inside the margin the segment combine drops (mdx.py:107-117)
+                continue
+            w = mp.istft(net(mp.stft(mix[i:i + 1])))[0, :, trim:-trim].numpy() * peak          # [2, gen]
             ref = w[:, lo - a: hi - a]
             got = main[:, lo:hi]
             e = rms(got - ref)
