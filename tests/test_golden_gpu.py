@@ -9,6 +9,14 @@ import torch
 from siggen import stereo_tones, vocal_like
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _tf32_storage(monkeypatch):
+    """Golden fixtures were generated with the round-1 raw random checkpoints: pin TF32 storage for the MDX U-Net (raw
+    BatchNorm statistics exceed fp16's range; the default fp16 mode is tested on trained-like checkpoints)."""
+    import aicovergen_b200.mdx as bm
+    monkeypatch.setattr(bm, "MDX_FP16", False)
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 

@@ -10,6 +10,15 @@ from aicovergen_b200.synthetic import make_mdx_state_dict
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def _storage_mode(monkeypatch, request):
+    """The U-Net's default storage is fp16 (B200VC_MDX_FP16=1).  Tests on the round-1 RAW random checkpoints pin TF32 storage:
+    raw BatchNorm statistics drive activations to 1e5..1e10, beyond fp16's range; fp16 tests use trained-like checkpoints."""
+    import aicovergen_b200.mdx as bm
+    if "fp16" not in request.node.name:
+        monkeypatch.setattr(bm, "MDX_FP16", False)
+
+
 def rel_rms(a, b):
     a, b = torch.as_tensor(a).double(), torch.as_tensor(b).double()
     return ((a - b).pow(2).mean().sqrt() / (b.pow(2).mean().sqrt() + 1e-20)).item()
@@ -122,12 +131,10 @@ def test_first_and_final_conv_row_kernels():
     assert (so.cpu() - ref_spec).abs().max() < 1e-4
 
 
-@pytest.mark.skipif(__import__("os").environ.get("B200VC_EXPERIMENTAL") != "1",
-                    reason="experimental fp16 activation storage (set B200VC_EXPERIMENTAL=1)")
 @pytest.mark.parametrize("cfg", [dict(dim_f=256, dim_t=32, g=8, n=3), dict(dim_f=3072, dim_t=256, g=48, n=5)])
 def test_convtdfnet_parity_fp16_storage(cfg, monkeypatch):
-    """The U-Net with fp16 activation / weight storage (tcgen05 kind::f16, fp32 accumulate): same tolerance as the TF32 path
-    (both carry 10 mantissa bits).  Opt-in until validated on a GPU."""
+    """The U-Net with fp16 activation / weight storage (tcgen05 kind::f16, fp32 accumulate) — the DEFAULT mode — on
+    trained-like checkpoints: same mantissa width as the TF32 path, half the bytes."""
     import aicovergen_b200.mdx as bm
     from oracle import mdx as om
 
@@ -144,4 +151,27 @@ def test_convtdfnet_parity_fp16_storage(cfg, monkeypatch):
     got = torch.from_numpy(net.run(None, {"input": x.numpy()})[0])
     e = rel_rms(got, ref)
     print(f"[mdx net fp16 storage {cfg['dim_f']}x{cfg['dim_t']}] rel rms err {e:.3e}")
-    assert torch.isfinite(got).all() and e < 8e-3
+    assert torch.isfinite(got).all() and e < 3e-3
+
+
+def test_process_wave_full_geometry_fp16_abs_rms():
+    """Kim_Vocal_2-class geometry, default fp16 storage, trained-like checkpoint: 12 s stereo -> 2 halves x 2 chunks;
+    the stem is compared in ABSOLUTE RMS on [-1, 1] audio (north_star bar 1e-3)."""
+    import aicovergen_b200.mdx as bm
+    from aicovergen_b200.synthetic import make_mdx_trained_like
+    from oracle import mdx as om
+
+    assert bm.MDX_FP16, "fp16 storage is the default"
+    dim_f, dim_t, n_fft = 3072, 256, 7680
+    sd = make_mdx_trained_like(dim_f, dim_t, n_fft)
+    wave = song(44100 * 12, 9)
+    wave /= np.abs(wave).max()
+    mp = om.MdxParams(dim_f, dim_t, n_fft)
+    ref = om.process_wave(wave.copy(), mp, lambda s: om.convtdfnet(sd, s), 2)
+    sess = bm.MDX(sd, bm.MDXModel("cuda:0", dim_f, dim_t, n_fft), 0, backend=tg.BACKEND_TC)
+    assert sess.ort.half
+    got = sess.process_wave(wave.copy(), 2)
+    a = float(np.sqrt(((got - ref) ** 2).mean()))
+    r = float(np.sqrt((ref ** 2).mean()))
+    print(f"[mdx full geometry fp16] abs rms err {a:.3e} (ref rms {r:.3e}, rel {a / r:.2e})")
+    assert got.shape == wave.shape and r > 1e-2 and a < 1e-3 and a / r < 5e-3
