@@ -122,9 +122,13 @@ class ConvTDFNetB200:
     def __init__(self, sd: Dict[str, torch.Tensor], device, backend=tg.BACKEND_TC):
         self.device = torch.device(device)
         self.backend = backend
-        self.half = bool(MDX_FP16 and backend == tg.BACKEND_TC)
         meta = [int(v) for v in sd["_meta"]]
         (self.dim_f, self.dim_t, self.g, self.l, self.n, self.bn, self.k, self.dim_c) = meta
+        # fp16 storage needs every GEMM of the plan on the TMA/tcgen05 kernels (there is no fp16 SIMT path); the narrowest
+        # one is the bottleneck TDF with K = dim_f / 2^n / bn (an fp32-operand fallback GEMM when that is not a multiple of 8,
+        # which itself needs K % 4 == 0).  Real UVR geometries (dim_f >= 2048) satisfy it; toy geometries fall back to fp32.
+        k_min = (self.dim_f >> self.n) // self.bn
+        self.half = bool(MDX_FP16 and backend == tg.BACKEND_TC and k_min % 4 == 0)
         self.W: Dict[str, torch.Tensor] = {}
         self._plans: Dict[int, "_NetPlan"] = {}
         self._load(sd)

@@ -116,3 +116,30 @@ def test_rmvpe_decode_kernel_exact():
     print(f"[rmvpe decode] host-finished f0 exact {(f0h == ref).mean():.4f}")
     assert np.array_equal(f0h, ref)
     assert (orm.coarse_pitch(got)[0] == orm.coarse_pitch(ref)[0]).all()
+
+
+@pytest.mark.parametrize("T", [37, 1024, 24608])
+def test_bigru_kernel_matches_torch_gru(T):
+    """b200vc_bigru (2 clusters x 8 CTAs, one DSMEM hop per step) against torch.nn.GRU(384, 256, bidirectional) on the CPU:
+    24 608 steps = the F0 of a 4-min song."""
+    from aicovergen_b200 import ops
+
+    g = torch.Generator().manual_seed(T)
+    gru = torch.nn.GRU(384, 256, num_layers=1, batch_first=True, bidirectional=True).eval()
+    x = torch.randn(1, T, 384, generator=g)
+    with torch.no_grad():
+        ref = gru(x)[0][0]
+        xp = torch.cat([x[0] @ gru.weight_ih_l0.t() + gru.bias_ih_l0, x[0] @ gru.weight_ih_l0_reverse.t() + gru.bias_ih_l0_reverse], 1)
+    whh = torch.stack([gru.weight_hh_l0, gru.weight_hh_l0_reverse]).detach().contiguous().cuda()
+    bhh = torch.stack([gru.bias_hh_l0, gru.bias_hh_l0_reverse]).detach().contiguous().cuda()
+    out = torch.empty(T, 512, device="cuda")
+    ops.bigru(xp.contiguous().cuda(), whh, bhh, out, 256)
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    ops.bigru(xp.contiguous().cuda(), whh, bhh, out, 256)
+    e.record()
+    torch.cuda.synchronize()
+    err = (out.cpu() - ref).abs().max().item()
+    print(f"[bigru T={T}] max abs err {err:.3e}; {s.elapsed_time(e):.2f} ms = {s.elapsed_time(e) * 1e3 / T:.3f} us/step")
+    assert err < 2e-5
