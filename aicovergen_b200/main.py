@@ -43,7 +43,7 @@ MDX_STAGES = (
 )
 
 
-SUPPORTED_F0_METHODS = ("rmvpe",)
+SUPPORTED_F0_METHODS = ("rmvpe", "mangio-crepe")
 
 
 def db_gain(db: float) -> float:
@@ -300,7 +300,7 @@ def song_cover_pipeline(song_input, voice_model, pitch_change, keep_files, is_we
                 orig_song_path, instrumentals_path, main_vocals_dereverb_path, backup_vocals_path = paths
         pitch_change = pitch_change * 12 + pitch_change_all
         stem = os.path.splitext(os.path.basename(orig_song_path))[0]
-        ai_vocals_path = os.path.join(song_dir, f"{stem}_{voice_model}_p{pitch_change}_i{index_rate}_fr{filter_radius}_rms{rms_mix_rate}_pro{protect}_{f0_method}.wav")
+        ai_vocals_path = os.path.join(song_dir, f"{stem}_{voice_model}_p{pitch_change}_i{index_rate}_fr{filter_radius}_rms{rms_mix_rate}_pro{protect}_{f0_method}{'' if f0_method != 'mangio-crepe' else f'_{crepe_hop_length}'}.wav")
         if output_format != "wav":
             display_progress("[!] mp3 export needs ffmpeg; writing WAV instead.", 0.0, is_webui, progress)
         ai_cover_path = os.path.join(song_dir, f"{stem} ({voice_model} Ver).wav")

@@ -30,6 +30,10 @@ _ffi.declare("b200vc_magnitude", [_P, _P, _i64, _i32, _i64, _i64, _P])
 _ffi.declare("b200vc_logmel_affine_reflect", [_P, _P, _i32, _i32, _i32, _f32, _f32, _f32, _P])
 _ffi.declare("b200vc_avgpool2x2", [_P, _P, _i32, _i32, _i32, _i32, _i64, _P])
 _ffi.declare("b200vc_avgpool2x2_split", [_P, _P, _i32, _i32, _i32, _i32, _i64, _i64, _i64, _i64, _P])
+_ffi.declare("b200vc_crepe_frames", [_P, _i64, _i64, _i32, _i32, _P, _i64, _i32, _i32, _i32, _P])
+_ffi.declare("b200vc_maxpool2_affine", [_P, _P, _P, _P, _i64, _i32, _i32, _P])
+_ffi.declare("b200vc_crepe_logprob", [_P, _P, _i32, _i32, _i32, _i32, _P])
+_ffi.declare("b200vc_viterbi_band", [_P, _P, C.c_double, C.c_double, _P, _P, _i32, _i32, _i32, _P])
 _ffi.declare("b200vc_bigru", [_P, _P, _P, _P, _i32, _i32, _P])
 _ffi.declare("b200vc_rmvpe_decode", [_P, _P, _P, _i32, _i32, _i64, _f32, _P])
 _ffi.declare("b200vc_groupnorm_time", [_P, _P, _P, _P, _P, _i64, _i32, _f32, _i32, _i32, _P])
@@ -187,6 +191,34 @@ def avgpool2x2_split(x, in_split, out, out_split):
     assert x.stride(3) == 1 and x.stride(1) == W * x.stride(2) and out.stride(3) == 1 and out.stride(1) == (W // 2) * out.stride(2)
     _ffi.check(_ffi.lib().b200vc_avgpool2x2_split(_p(_f32c(x)), _p(out), B, H, W, Cc, x.stride(2), in_split, out.stride(2),
                                                   out_split, _s()), "avgpool2x2_split")
+
+
+def crepe_frames(audio, first_frame, hop, win, out, off, nframes, round_out=False):
+    """audio [N] f32; out [B, ld] (frame f written at out[f - first_frame, off:off+win])."""
+    assert audio.is_contiguous() and out.stride(1) == 1 and nframes <= out.shape[0]
+    _ffi.check(_ffi.lib().b200vc_crepe_frames(_p(_f32c(audio)), audio.numel(), first_frame, hop, win, _p(out), out.stride(0), off,
+                                              nframes, int(round_out), _s()), "crepe_frames")
+
+
+def maxpool2_affine(x, scale, shift, out, round_out=False):
+    """x [B, L, C] -> out [B, L/2, C] = max over position pairs of scale[c] * x + shift[c]."""
+    assert x.is_contiguous() and out.is_contiguous() and x.shape[1] % 2 == 0
+    _ffi.check(_ffi.lib().b200vc_maxpool2_affine(_p(_f32c(x)), _p(scale), _p(shift), _p(out), out.shape[0] * out.shape[1], x.shape[2],
+                                                 int(round_out), _s()), "maxpool2_affine")
+
+
+def crepe_logprob(act, logp, lo, hi):
+    n, nb = act.shape
+    assert act.is_contiguous() and logp.is_contiguous()
+    _ffi.check(_ffi.lib().b200vc_crepe_logprob(_p(_f32c(act)), _p(logp), n, nb, lo, hi, _s()), "crepe_logprob")
+
+
+def viterbi_band(logp, log_band, log_out, log_init, ptr, states, band):
+    n, ns = logp.shape
+    assert logp.is_contiguous() and log_band.dtype == torch.float64 and log_band.is_contiguous() and ptr.element_size() == 2
+    assert states.dtype == torch.int32 and tuple(log_band.shape) == (ns, 2 * band - 1)
+    _ffi.check(_ffi.lib().b200vc_viterbi_band(_p(_f32c(logp)), _p(log_band), float(log_out), float(log_init), _p(ptr), _p(states), n, ns,
+                                              band, _s()), "viterbi_band")
 
 
 def rmvpe_decode(sal, f0, T, thred, cents=None):

@@ -542,3 +542,62 @@ def make_mdx_trained_like(dim_f: int = 3072, dim_t: int = 256, n_fft: int = 7680
         z = torch.view_as_real(z).permute(0, 3, 1, 2)[:, :, :dim_f]                 # [ch, ri, F, T]
         _TRAINED_LIKE_CACHE[key] = calibrate_mdx_batchnorm(sd, z.reshape(1, 4, dim_f, T), out_gain=0.3)
     return _TRAINED_LIKE_CACHE[key]
+
+
+# ---------------------------------------------------------------------------
+# torchcrepe 'full' weights (torchcrepe/assets/full.pth layout; requirements.txt:19, vc_infer_pipeline.py:116-126)
+# ---------------------------------------------------------------------------
+CREPE_CHANNELS = [1024, 128, 128, 128, 256, 512]
+
+
+def make_crepe_state_dict(seed: int = 606, calibrate: bool = True) -> Dict[str, torch.Tensor]:
+    """Seeded synthetic Crepe('full') checkpoint: conv{i}.weight [Cout, Cin, k, 1] (k = 512 then 64), conv{i}.bias,
+    conv{i}_BN.{weight,bias,running_mean,running_var,num_batches_tracked}, classifier.{weight [360, 2048], bias}.
+    calibrate=True fits the BatchNorm statistics on normalised frames of the seeded calibration clip and gives the classifier
+    a smooth-across-bins structure (one activation bump per frame), like make_rmvpe_trained_like."""
+    import torch.nn.functional as F
+
+    g = _Gen(seed)
+    sd: Dict[str, torch.Tensor] = {}
+    cin = 1
+    for i, co in enumerate(CREPE_CHANNELS):
+        k = 512 if i == 0 else 64
+        sd[f"conv{i + 1}.weight"] = g.conv((co, cin, k, 1), 1.4)
+        sd[f"conv{i + 1}.bias"] = g.normal((co,), 0.05, 0.1)
+        p = f"conv{i + 1}_BN"
+        sd[p + ".weight"] = g.uniform((co,), 0.6, 1.4)
+        sd[p + ".bias"] = g.normal((co,), 0.1, 0.2)
+        sd[p + ".running_mean"] = g.normal((co,), 0.1, 0.3)
+        sd[p + ".running_var"] = g.uniform((co,), 0.5, 1.5)
+        sd[p + ".num_batches_tracked"] = torch.tensor(0, dtype=torch.long)
+        cin = co
+    sd["classifier.weight"] = g.conv((360, 2048), 1.0)
+    sd["classifier.bias"] = g.normal((360,), 0.2, -1.0)
+    if not calibrate:
+        return sd
+    clip = calibration_clip(4.0)
+    hop = 160
+    a = F.pad(clip[None], (512, 512))
+    frames = F.unfold(a[:, None, None, :], kernel_size=(1, 1024), stride=(1, hop)).transpose(1, 2).reshape(-1, 1024)
+    frames = frames - frames.mean(dim=1, keepdim=True)
+    frames = frames / torch.max(torch.tensor(1e-10), frames.std(dim=1, keepdim=True))
+    eps = 0.0010000000474974513
+    with torch.no_grad():
+        x = frames[:, None, :, None]
+        for i in range(6):
+            x = F.pad(x, (0, 0, 254, 254) if i == 0 else (0, 0, 31, 32))
+            x = F.relu(F.conv2d(x, sd[f"conv{i + 1}.weight"], sd[f"conv{i + 1}.bias"], stride=(4, 1) if i == 0 else (1, 1)))
+            p = f"conv{i + 1}_BN"
+            sd[p + ".running_mean"] = x.mean(dim=(0, 2, 3))
+            sd[p + ".running_var"] = x.var(dim=(0, 2, 3), unbiased=False).clamp_min(1e-4)
+            x = F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"], sd[p + ".weight"], sd[p + ".bias"], False, 0.0, eps)
+            x = F.max_pool2d(x, (2, 1), (2, 1))
+        h = x.permute(0, 2, 1, 3).reshape(x.shape[0], -1)
+        k = torch.arange(360, dtype=torch.float32)
+        G = torch.exp(-0.5 * ((k[:, None] - k[None, :]) / 2.0) ** 2)
+        w = (G / G.sum(1, keepdim=True)) @ sd["classifier.weight"]
+        z = h @ w.t()
+        w = w * (2.5 / z.std().clamp_min(1e-6))
+        sd["classifier.weight"] = w
+        sd["classifier.bias"] = torch.full((360,), -3.0) - (h @ w.t()).mean(0)
+    return sd

@@ -69,6 +69,27 @@ class VC(object):
         return nz.to(dev), (None if ns is None else ns.to(dev))
 
     # ------------------------------------------------------------------ F0
+    def get_f0_crepe_computation(self, x, f0_min, f0_max, p_len, hop_length=160, model="full"):
+        """vc_infer_pipeline.py:96-137 with `torchcrepe.predict` replaced by CrepeB200.predict (same arguments: 16 kHz,
+        `hop_length`, fmin/fmax, model 'full', viterbi decoder, pad=True; the reference's batch_size only bounds memory)."""
+        if model != "full":
+            raise NotImplementedError("only torchcrepe's 'full' model is built")
+        if not hasattr(self, "model_crepe"):
+            from .crepe import CrepeB200
+            from .rvc import BASE_DIR
+            sd = torch.load(os.path.join(BASE_DIR, "rvc_models", "crepe_full.pth"), map_location="cpu")   # torchcrepe/assets/full.pth
+            self.model_crepe = CrepeB200(sd, device=self.device)
+        x = x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
+        x = x.astype(np.float32)
+        x /= np.quantile(np.abs(x), 0.999)
+        pitch = self.model_crepe.predict(x, self.sr, hop_length, f0_min, f0_max, dither_seed=getattr(self, "crepe_dither_seed", None),
+                                         dither=getattr(self, "crepe_dither", True))
+        p_len = p_len or x.shape[0] // hop_length
+        source = np.array(pitch, dtype=np.float32)
+        source[source < 0.001] = np.nan
+        target = np.interp(np.arange(0, len(source) * p_len, len(source)) / p_len, np.arange(0, len(source)), source)
+        return np.nan_to_num(target)
+
     def get_f0(self, input_audio_path, x, p_len, f0_up_key, f0_method, filter_radius, crepe_hop_length, inp_f0=None):
         """rmvpe branch of the reference (vc_infer_pipeline.py:262-278, 322-329, 346-370)."""
         f0_min, f0_max = 50, 1100
@@ -83,10 +104,12 @@ class VC(object):
             if isinstance(x, torch.Tensor) and not hasattr(self.model_rmvpe, "infer_from_audio_device"):
                 x = x.cpu().numpy()          # a reference-style RMVPE object was injected: it takes numpy
             f0 = self.model_rmvpe.infer_from_audio(x, thred=0.03)
+        elif f0_method == "mangio-crepe":
+            f0 = self.get_f0_crepe_computation(x, f0_min, f0_max, p_len, crepe_hop_length)
         else:
             raise NotImplementedError(
-                f"f0_method={f0_method!r}: only 'rmvpe' runs on the B200 path (crepe is SURVEY.md §8(f) next-row; "
-                "pm/harvest/dio are CPU libraries outside the hot path)")
+                f"f0_method={f0_method!r}: 'rmvpe' and 'mangio-crepe' run on the B200 path (pm / harvest / dio / pyin are CPU "
+                "libraries outside the hot path; crepe-tiny and the hybrid methods are not built)")
         f0 *= pow(2, f0_up_key / 12)
         tf0 = self.sr // self.window
         if inp_f0 is not None:

@@ -246,6 +246,28 @@ int b200vc_rmvpe_decode(const float* salience, double* f0, double* cents, int T,
 int b200vc_groupnorm_time(const float* x, const float* gamma, const float* beta, float* out, double* stats,
                           int64_t rows, int C, float eps, int act, int round_out, void* stream);
 
+/* ---- crepe F0 estimator pieces (f0_method "mangio-crepe": vc_infer_pipeline.py:96-137 -> torchcrepe.predict) ---- */
+
+/* torchcrepe.preprocess: frame f (f = first_frame .. first_frame+nframes-1) = zero-padded audio[f*hop - win/2 .. + win), minus its
+ * mean, divided by max(1e-10, unbiased std); written at out[(f-first_frame)*ldo + off .. + win). */
+int b200vc_crepe_frames(const float* audio, int64_t n_audio, int64_t first_frame, int hop, int win, float* out, int64_t ldo,
+                        int off, int nframes, int round_out, void* stream);
+
+/* out[r, c] = max(s[c]*x[2r, c] + t[c], s[c]*x[2r+1, c] + t[c]): eval BatchNorm applied AFTER the ReLU + MaxPool2d((2,1)) of
+ * every torchcrepe layer (conv -> relu -> BN -> pool), rows = positions, channels-last. */
+int b200vc_maxpool2_affine(const float* x, const float* scale, const float* shift, float* out, int64_t rows_out, int C,
+                           int round_out, void* stream);
+
+/* torchcrepe.postprocess + the head of librosa.sequence.viterbi: bins outside [lo, hi) -> -inf, softmax over bins (fp32),
+ * logp = log(prob + FLT_MIN) (fp32). act, logp: [n, n_bins]. */
+int b200vc_crepe_logprob(const float* act, float* logp, int n, int n_bins, int lo, int hi, void* stream);
+
+/* librosa.sequence.viterbi for a banded transition matrix, float64: log_band[from][d] = log T[from -> from + d - (band-1)] for
+ * |to - from| < band, every other transition = log_out; uniform start (log_init).  ptr: [n, n_states] scratch; states: [n] out.
+ * One thread block; n_states <= 512. */
+int b200vc_viterbi_band(const float* logp, const double* log_band, double log_out, double log_init, uint16_t* ptr, int* states,
+                        int n, int n_states, int band, void* stream);
+
 /* ---- VC.pipeline glue (vc_infer_pipeline.py) ---- */
 
 /* out[r] = index of the first minimum of S[r, 0..n) */
