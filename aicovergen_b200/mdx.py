@@ -127,8 +127,8 @@ class ConvTDFNetB200:
         # fp16 storage needs every GEMM of the plan on the TMA/tcgen05 kernels (there is no fp16 SIMT path); the narrowest
         # one is the bottleneck TDF with K = dim_f / 2^n / bn (an fp32-operand fallback GEMM when that is not a multiple of 8,
         # which itself needs K % 4 == 0).  Real UVR geometries (dim_f >= 2048) satisfy it; toy geometries fall back to fp32.
-        k_min = (self.dim_f >> self.n) // self.bn
-        self.half = bool(MDX_FP16 and backend == tg.BACKEND_TC and k_min % 4 == 0)
+        tdf_k = [(self.dim_f >> lvl) // self.bn for lvl in range(self.n + 1)]
+        self.half = bool(MDX_FP16 and backend == tg.BACKEND_TC and all(k_ % 4 == 0 for k_ in tdf_k))
         self.W: Dict[str, torch.Tensor] = {}
         self._plans: Dict[int, "_NetPlan"] = {}
         self._load(sd)

@@ -43,7 +43,7 @@ def _run_plan_on_cpu(net, x, monkeypatch):
 
 
 @pytest.mark.parametrize("half", [False, True])
-@pytest.mark.parametrize("cfg", [dict(dim_f=64, dim_t=16, g=8, l=2, n=2, bn=4), dict(dim_f=96, dim_t=8, g=16, l=1, n=1, bn=8)])
+@pytest.mark.parametrize("cfg", [dict(dim_f=64, dim_t=16, g=8, l=2, n=2, bn=4), dict(dim_f=96, dim_t=8, g=16, l=1, n=1, bn=4)])
 def test_mdx_plan_matches_oracle_on_cpu(cfg, half, monkeypatch):
     monkeypatch.setattr(bm, "MDX_FP16", half)
     sd = make_mdx_state_dict(**cfg)
