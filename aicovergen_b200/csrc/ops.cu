@@ -61,7 +61,7 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
 // ---------------------------------------------------------------------------
 __global__ void softmax_rows_kernel(float* __restrict__ S, int T, long long ld, long long head_stride,
                                     int rows_per_head, const float* __restrict__ q, int ldq,
-                                    const float* __restrict__ emb_k, int window, int dk, int round_out) {
+                                    const float* __restrict__ emb_k, int window, int dk, int round_out, int row0) {
   extern __shared__ float row[];
   __shared__ float red[32];
   __shared__ float rel[64];
@@ -72,7 +72,7 @@ __global__ void softmax_rows_kernel(float* __restrict__ S, int T, long long ld, 
   if (emb_k) {
     const int nrel = 2 * window + 1;
     for (int r = tid; r < nrel; r += nt) {
-      const float* qi = q + (long long)i * ldq + head * dk;
+      const float* qi = q + (long long)(i + row0) * ldq + head * dk;
       const float* e = emb_k + r * dk;
       float a = 0.f;
       for (int d = 0; d < dk; ++d) a = fmaf(qi[d], e[d], a);
@@ -84,7 +84,7 @@ __global__ void softmax_rows_kernel(float* __restrict__ S, int T, long long ld, 
   for (int j = tid; j < T; j += nt) {
     float v = s[j];
     if (emb_k) {
-      const int r = j - i + window;
+      const int r = j - (i + row0) + window;
       if (r >= 0 && r <= 2 * window) v += rel[r];
     }
     row[j] = v;
@@ -126,17 +126,17 @@ __global__ void softmax_rows_kernel(float* __restrict__ S, int T, long long ld, 
 // out[i, h*dk + d] += sum_r P[h, i, i + r - W] * emb_v[r, d]   (attentions.py:264-271)
 __global__ void relpos_value_add_kernel(float* __restrict__ out, int ldo, const float* __restrict__ P,
                                         int T, long long ld, long long head_stride,
-                                        const float* __restrict__ emb_v, int window, int dk, int heads) {
+                                        const float* __restrict__ emb_v, int window, int dk, int heads, int row0) {
   const int i = blockIdx.x;
   for (int c = threadIdx.x; c < heads * dk; c += blockDim.x) {
     const int h = c / dk, d = c % dk;
     const float* p = P + (long long)h * head_stride + (long long)i * ld;
     float a = 0.f;
     for (int r = 0; r <= 2 * window; ++r) {
-      const int j = i + r - window;
+      const int j = i + row0 + r - window;
       if (j >= 0 && j < T) a = fmaf(p[j], emb_v[r * dk + d], a);
     }
-    out[(long long)i * ldo + c] += a;
+    out[(long long)(i + row0) * ldo + c] += a;
   }
 }
 
@@ -388,8 +388,8 @@ int b200vc_layernorm(const float* x, const float* res, const float* gamma, const
 
 int b200vc_softmax_rows(float* S, int heads, int rows_per_head, int T, int64_t ld, int64_t head_stride,
                         const float* q, int ldq, const float* emb_rel_k, int window, int dk,
-                        int round_out, void* stream) {
-  B200VC_RECORD(b200vc_softmax_rows(S, heads, rows_per_head, T, ld, head_stride, q, ldq, emb_rel_k, window, dk, round_out, stream));
+                        int round_out, int row0, void* stream) {
+  B200VC_RECORD(b200vc_softmax_rows(S, heads, rows_per_head, T, ld, head_stride, q, ldq, emb_rel_k, window, dk, round_out, row0, stream));
   B200VC_REQUIRE(S && heads > 0 && rows_per_head > 0 && T > 0, "softmax_rows: bad args");
   B200VC_REQUIRE(T * 4 <= 200 * 1024, "softmax_rows: row of %d floats does not fit shared memory", T);
   B200VC_REQUIRE(!emb_rel_k || (q && 2 * window + 1 <= 64), "softmax_rows: bad relative-position args");
@@ -401,18 +401,18 @@ int b200vc_softmax_rows(float* S, int heads, int rows_per_head, int T, int64_t l
     configured = 200 * 1024;
   }
   softmax_rows_kernel<<<(unsigned)(heads * rows_per_head), 256, smem, s>>>(
-      S, T, ld, head_stride, rows_per_head, q, ldq, emb_rel_k, window, dk, round_out);
+      S, T, ld, head_stride, rows_per_head, q, ldq, emb_rel_k, window, dk, round_out, row0);
   count_launch();
   B200VC_LAUNCH_CHECK();
   return kOk;
 }
 
-int b200vc_relpos_value_add(float* out, int ldo, const float* P, int T, int64_t ld, int64_t head_stride,
-                            const float* emb_rel_v, int window, int dk, int heads, void* stream) {
-  B200VC_RECORD(b200vc_relpos_value_add(out, ldo, P, T, ld, head_stride, emb_rel_v, window, dk, heads, stream));
-  B200VC_REQUIRE(out && P && emb_rel_v && T > 0, "relpos_value_add: bad args");
-  relpos_value_add_kernel<<<(unsigned)T, 192, 0, (cudaStream_t)stream>>>(out, ldo, P, T, ld, head_stride,
-                                                                        emb_rel_v, window, dk, heads);
+int b200vc_relpos_value_add(float* out, int ldo, const float* P, int rows, int T, int64_t ld, int64_t head_stride,
+                            const float* emb_rel_v, int window, int dk, int heads, int row0, void* stream) {
+  B200VC_RECORD(b200vc_relpos_value_add(out, ldo, P, rows, T, ld, head_stride, emb_rel_v, window, dk, heads, row0, stream));
+  B200VC_REQUIRE(out && P && emb_rel_v && T > 0 && rows > 0 && row0 >= 0, "relpos_value_add: bad args");
+  relpos_value_add_kernel<<<(unsigned)rows, 192, 0, (cudaStream_t)stream>>>(out, ldo, P, T, ld, head_stride,
+                                                                           emb_rel_v, window, dk, heads, row0);
   count_launch();
   B200VC_LAUNCH_CHECK();
   return kOk;

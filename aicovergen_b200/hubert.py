@@ -20,6 +20,7 @@ from .synth import round_tf32
 from .tapgemm import Epi
 
 CONV = [(512, 10, 5)] + [(512, 3, 2)] * 4 + [(512, 2, 2)] * 2
+ATT_SCRATCH_BYTES = 80 * 1024 * 1024       # score scratch of one query block: sized to stay inside the 126 MB L2
 
 
 class HubertB200:
@@ -171,7 +172,11 @@ class _HubertPlan:
         Tp = (T + 3) // 4 * 4
         qk = torch.empty(T, 2 * D, **f32)
         vT = torch.zeros(D, Tp, **f32)
-        sc = torch.zeros(H, T, Tp, **f32)
+        # Attention runs per block of QB query rows: scores [H, QB, T] are produced, soft-maxed and consumed while they are
+        # still in the 126 MB L2 (12 x 512 x 3300 fp32 = 81 MB) — no [H, T, T] matrix (522 MB for a 66 s segment) ever
+        # exists, and its four HBM passes per layer (write, softmax read + write, PV read) are gone.
+        QB = min(T, max(128, (ATT_SCRATCH_BYTES // (4 * H * Tp)) // 128 * 128))
+        sc = torch.zeros(H, QB, Tp, **f32)
         o = torch.empty(T, D, **f32)
         tmp = torch.empty(T, D, **f32)
         hbuf = torch.empty(T, W["l0.fc1.w"].shape[0], **f32)
@@ -180,9 +185,13 @@ class _HubertPlan:
             add(tg.linear(W[f"l{i}.v.w"], x, vT[:, :T], Epi(bias=W[f"l{i}.v.b"], bias_per_row=True, round_out=R), be, name=f"l{i}.vT"))
             qh = qk[:, :D].view(T, H, dh).permute(1, 0, 2)
             kh = qk[:, D:].view(T, H, dh).permute(1, 0, 2)
-            add(tg.bmm_nt(qh, kh, sc[:, :, :T], None, be, name=f"l{i}.qk^T"))
-            add(lambda: ops.softmax_rows(sc, T, round_out=R))
-            add(tg.bmm_nt(sc[:, :, :T], vT.view(H, dh, Tp)[:, :, :T], o.view(T, H, dh).permute(1, 0, 2), Epi(round_out=R), be, name=f"l{i}.pv"))
+            oh = o.view(T, H, dh).permute(1, 0, 2)
+            for q0 in range(0, T, QB):
+                nq = min(QB, T - q0)
+                scb = sc[:, :nq]
+                add(tg.bmm_nt(qh[:, q0:q0 + nq], kh, scb[:, :, :T], None, be, name=f"l{i}.qk^T"))
+                add(lambda scb=scb: ops.softmax_rows(scb, T, round_out=R))
+                add(tg.bmm_nt(scb[:, :, :T], vT.view(H, dh, Tp)[:, :, :T], oh[:, q0:q0 + nq], Epi(round_out=R), be, name=f"l{i}.pv"))
             add(tg.linear(o, W[f"l{i}.o.w"], tmp, Epi(bias=W[f"l{i}.o.b"], res=x), be, name=f"l{i}.o"))
             add(lambda i=i: ops.layernorm(tmp, W[f"l{i}.ln1.g"], W[f"l{i}.ln1.b"], x))
             add(tg.linear(x, W[f"l{i}.fc1.w"], hbuf, Epi(bias=W[f"l{i}.fc1.b"], act_pre=tg.ACT_GELU, round_out=R), be, name=f"l{i}.fc1"))

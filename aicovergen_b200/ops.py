@@ -16,8 +16,8 @@ _P = C.c_void_p
 _i64, _i32, _f32 = C.c_int64, C.c_int, C.c_float
 
 _ffi.declare("b200vc_layernorm", [_P, _P, _P, _P, _P, _i64, _i32, _i64, _i64, _i64, _f32, _i32, _P])
-_ffi.declare("b200vc_softmax_rows", [_P, _i32, _i32, _i32, _i64, _i64, _P, _i32, _P, _i32, _i32, _i32, _P])
-_ffi.declare("b200vc_relpos_value_add", [_P, _i32, _P, _i32, _i64, _i64, _P, _i32, _i32, _i32, _P])
+_ffi.declare("b200vc_softmax_rows", [_P, _i32, _i32, _i32, _i64, _i64, _P, _i32, _P, _i32, _i32, _i32, _i32, _P])
+_ffi.declare("b200vc_relpos_value_add", [_P, _i32, _P, _i32, _i32, _i64, _i64, _P, _i32, _i32, _i32, _i32, _P])
 _ffi.declare("b200vc_gather_rows", [_P, _P, _P, _i64, _i32, _P])
 _ffi.declare("b200vc_gate_tanh_sigmoid", [_P, _P, _i64, _i32, _i32, _P])
 _ffi.declare("b200vc_zp_sample", [_P, _P, _P, _i64, _i32, _f32, _P])
@@ -77,20 +77,22 @@ def layernorm(x, gamma, beta, out, res=None, eps=1e-5, round_out=False):
                                            eps, int(round_out), _s()), "layernorm")
 
 
-def softmax_rows(S, T, q=None, emb_rel_k=None, window=0, round_out=False):
-    """In-place softmax over S[heads, rows, :T]; optional relative-key bias (q [rows, heads*dk], emb_rel_k [2W+1, dk])."""
+def softmax_rows(S, T, q=None, emb_rel_k=None, window=0, round_out=False, row0=0):
+    """In-place softmax over S[heads, rows, :T]; optional relative-key bias (q [T_q, heads*dk] the FULL query matrix,
+    emb_rel_k [2W+1, dk]); S holds query rows row0 .. row0 + rows - 1."""
     heads, rows, _ = S.shape
     assert S.stride(2) == 1
     dk = 0 if emb_rel_k is None else emb_rel_k.shape[-1]
     _ffi.check(_ffi.lib().b200vc_softmax_rows(_p(_f32c(S)), heads, rows, T, S.stride(1), S.stride(0), _p(q),
                                               0 if q is None else q.stride(0), _p(emb_rel_k), window, dk,
-                                              int(round_out), _s()), "softmax_rows")
+                                              int(round_out), int(row0), _s()), "softmax_rows")
 
 
-def relpos_value_add(out, P, T, emb_rel_v, window, heads):
+def relpos_value_add(out, P, T, emb_rel_v, window, heads, row0=0):
+    """out (full [T_q, heads*dk]) rows row0.. += banded P (block [heads, rows, >=T]) x emb_rel_v."""
     dk = emb_rel_v.shape[-1]
-    _ffi.check(_ffi.lib().b200vc_relpos_value_add(_p(_f32c(out)), out.stride(0), _p(P), T, P.stride(1), P.stride(0),
-                                                  _p(emb_rel_v), window, dk, heads, _s()), "relpos_value_add")
+    _ffi.check(_ffi.lib().b200vc_relpos_value_add(_p(_f32c(out)), out.stride(0), _p(P), P.shape[1], T, P.stride(1), P.stride(0),
+                                                  _p(emb_rel_v), window, dk, heads, int(row0), _s()), "relpos_value_add")
 
 
 def gather_rows(table, idx, out):

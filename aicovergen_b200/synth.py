@@ -23,6 +23,7 @@ from .plans import PlanCache, StepGraph
 from .tapgemm import Epi
 
 LRELU = 0.1
+ATT_SCRATCH_BYTES = 80 * 1024 * 1024       # score scratch of one query block: sized to stay inside the 126 MB L2
 
 
 def fold_weight_norm(sd: Dict[str, torch.Tensor], name: str) -> torch.Tensor:
@@ -231,7 +232,10 @@ class _Plan:
         Tp = (P + 3) // 4 * 4
         qk = torch.empty(P, 2 * H, **f32)
         vT = torch.zeros(H, Tp, **f32)
-        sc = torch.zeros(heads, P, Tp, **f32)
+        # attention per block of QB query rows, score scratch L2-resident (see hubert.py): no [heads, P, P] matrix (348 MB at
+        # P = 6598) and none of its HBM passes; the relative-position band terms take the block's first row as `row0`
+        QB = min(P, max(128, (ATT_SCRATCH_BYTES // (4 * heads * Tp)) // 128 * 128))
+        sc = torch.zeros(heads, QB, Tp, **f32)
         o = torch.empty(P, H, **f32)
         tmp = torch.empty(P, H, **f32)
         hbuf = torch.empty(P, m.filter, **f32)
@@ -242,11 +246,15 @@ class _Plan:
                           be, name=f"l{i}.vT"))
             qh = qk[:, :H].view(P, heads, dk).permute(1, 0, 2)
             kh = qk[:, H:].view(P, heads, dk).permute(1, 0, 2)
-            add(tg.bmm_nt(qh, kh, sc[:, :, :P], None, be, name=f"l{i}.qk^T"))
-            add(lambda i=i: ops.softmax_rows(sc, P, q=qk, emb_rel_k=W[f"l{i}.rel_k"], window=m.window, round_out=R))
-            add(tg.bmm_nt(sc[:, :, :P], vT.view(heads, dk, Tp)[:, :, :P], o.view(P, heads, dk).permute(1, 0, 2),
-                          None, be, name=f"l{i}.pv"))
-            add(lambda i=i: ops.relpos_value_add(o, sc, P, W[f"l{i}.rel_v"], m.window, heads))
+            oh = o.view(P, heads, dk).permute(1, 0, 2)
+            for q0 in range(0, P, QB):
+                nq = min(QB, P - q0)
+                scb = sc[:, :nq]
+                add(tg.bmm_nt(qh[:, q0:q0 + nq], kh, scb[:, :, :P], None, be, name=f"l{i}.qk^T"))
+                add(lambda i=i, scb=scb, q0=q0: ops.softmax_rows(scb, P, q=qk, emb_rel_k=W[f"l{i}.rel_k"], window=m.window,
+                                                                  round_out=R, row0=q0))
+                add(tg.bmm_nt(scb[:, :, :P], vT.view(heads, dk, Tp)[:, :, :P], oh[:, q0:q0 + nq], None, be, name=f"l{i}.pv"))
+                add(lambda i=i, scb=scb, q0=q0: ops.relpos_value_add(o, scb, P, W[f"l{i}.rel_v"], m.window, heads, row0=q0))
             add(tg.linear(o, W[f"l{i}.o.w"], tmp, Epi(bias=W[f"l{i}.o.b"], res=x), be, name=f"l{i}.o"))
             add(lambda i=i: ops.layernorm(tmp, W[f"l{i}.ln1.g"], W[f"l{i}.ln1.b"], x))
             add(tg.conv1d(x, W[f"l{i}.ffn1.w"], hbuf, epi=Epi(bias=W[f"l{i}.ffn1.b"], act_pre=tg.ACT_RELU, round_out=R),

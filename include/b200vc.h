@@ -169,14 +169,16 @@ int b200vc_layernorm(const float* x, const float* res, const float* gamma, const
 
 /* In-place softmax over the last dim of S[heads][rows_per_head][T] (row pitch ld, head pitch head_stride).
  * With emb_rel_k != NULL adds the VITS banded relative-key bias q_i . emb_rel_k[j-i+W] first
- * (infer_pack/attentions.py:238-243,261); q rows are [ldq] wide with head h at column h*dk. */
+ * (infer_pack/attentions.py:238-243,261); q rows are [ldq] wide with head h at column h*dk.
+ * S may hold a BLOCK of query rows: local row i is query row0 + i (q is always the full [T, .] matrix). */
 int b200vc_softmax_rows(float* S, int heads, int rows_per_head, int T, int64_t ld, int64_t head_stride,
                         const float* q, int ldq, const float* emb_rel_k, int window, int dk,
-                        int round_out, void* stream);
+                        int round_out, int row0, void* stream);
 
-/* out[i, h*dk+d] += sum_r P[h,i,i+r-W] * emb_rel_v[r,d]   (infer_pack/attentions.py:264-271) */
-int b200vc_relpos_value_add(float* out, int ldo, const float* P, int T, int64_t ld, int64_t head_stride,
-                            const float* emb_rel_v, int window, int dk, int heads, void* stream);
+/* out[row0+i, h*dk+d] += sum_r P[h,i,row0+i+r-W] * emb_rel_v[r,d] for the `rows` query rows of the block P
+ * (infer_pack/attentions.py:264-271); out is the full [T, .] matrix. */
+int b200vc_relpos_value_add(float* out, int ldo, const float* P, int rows, int T, int64_t ld, int64_t head_stride,
+                            const float* emb_rel_v, int window, int dk, int heads, int row0, void* stream);
 
 /* out[r,:] = table[idx[r],:]  (nn.Embedding at infer_pack/models.py:97,746) */
 int b200vc_gather_rows(const float* table, const int64_t* idx, float* out, int64_t rows, int C, void* stream);
