@@ -199,7 +199,9 @@ bigru_kernel(const float* __restrict__ xp, const float* __restrict__ whh /*[2][3
 //     data and its arrival signal travel together; each CTA waits on its OWN mbarrier for the 1024 bytes of the new h
 //     (armed one step ahead) instead of a cluster-wide barrier.  Double-buffered h: a CTA can only start step s+1 after
 //     every peer has SENT its step-s slice, which each peer does after its last read of the step-s input buffer.
-// Measured r02: 24 608 steps (4-min song) in X ms vs Y ms for v1 (cluster.sync per step).
+// Measured r02d on B200: 24 608 steps (4-min song) take 82 ms = 3.3 us/step — SLOWER than v1 (1.3 us/step): one st.async per
+// (unit, peer) means 256 remote mbarrier updates per CTA and step.  Not the default; a bulk-copy variant (one 128-byte
+// cp.async.bulk per peer) is the next thing to try.
 // ---------------------------------------------------------------------------
 constexpr int GRU2_THREADS = 512;
 
@@ -436,7 +438,9 @@ int b200vc_bigru(const float* xp, const float* whh, const float* bhh, float* out
   B200VC_RECORD(b200vc_bigru(xp, whh, bhh, out, T, hidden, stream));
   B200VC_REQUIRE(xp && whh && bhh && out && T > 0, "bigru: bad args");
   B200VC_REQUIRE(hidden == GRU_H, "bigru: hidden size %d unsupported (kernel is specialised for %d)", hidden, GRU_H);
-  static const bool v1 = [] { const char* e = getenv("B200VC_GRU_V1"); return e && e[0] == '1'; }();
+  // v2 (st.async + mbarrier per step) measured SLOWER on B200 (r02d: 3.3 us/step vs 1.3 us/step for v1: 256 remote
+  // complete_tx updates per CTA and step cost more than one cluster barrier); kept behind B200VC_GRU_V2=1 for experiments
+  static const bool v1 = [] { const char* e = getenv("B200VC_GRU_V2"); return !(e && e[0] == '1'); }();
   if (v1) bigru_kernel<<<2 * GRU_CL, GRU_THREADS, 0, (cudaStream_t)stream>>>(xp, whh, bhh, out, T);
   else bigru_v2_kernel<<<2 * GRU_CL, GRU2_THREADS, 0, (cudaStream_t)stream>>>(xp, whh, bhh, out, T);
   count_launch();

@@ -209,7 +209,6 @@ def test_cover_engine_stage_handoffs_30s():
     eng.vc.keep_float = True
     ai = eng.convert(d)
     ref_i16, info = opipe.pipeline(hsd, cpt, rsd, mono_h.copy(), index=index, seed=5, return_all=True)
-    os.unlink(tmp.name)
     from scipy import signal
     pad = np.pad(signal.filtfilt(opipe.bh, opipe.ah, mono_h), (48000, 48000), mode="reflect")
     pitch, _ = eng.vc.get_f0("x", pad, len(pad) // 160, 0, "rmvpe", 3, 128)
@@ -228,5 +227,6 @@ def test_cover_engine_stage_handoffs_30s():
     # and the one-call form produces the same cover from the same song (device noise draws differ: seed again)
     eng.vc.set_noise_seed(5)
     full = eng.cover(song)
+    os.unlink(tmp.name)
     assert full.shape == cover.shape and np.isfinite(full).all()
     assert rms(full - cover) < 1e-6
