@@ -196,7 +196,9 @@ def install_tc_profiler():
             p = self.params
             if not hasattr(self, "_family"):
                 tile_n = 256 if p.N > 128 else (128 if p.N > 64 else (64 if p.N > 32 else 32))
-                self._family = "ws" if self.ws_applicable() else f"tc2<{tile_n}>"
+                # one family = one kernel template instance: tile width x operand type (kind::f16 and kind::tf32 are different
+                # kernels with different rooflines)
+                self._family = ("ws" if self.ws_applicable() else f"tc2<{tile_n}>") + ("/f16" if p.dtype & 1 else "/tf32")
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
             orig(self, stream, backend)
@@ -650,22 +652,23 @@ def main():
                   "flops_note": "2*M*N*K per tap-GEMM launch; the MDX STFT/iSTFT DFT-GEMMs are counted at FFT cost (2.5 n log2 n per frame)"}
         if traffic and traffic.get("family") == tn:
             common["traffic_detail"] = traffic
-        if tn == "ws":
-            # small-channel convolutions: arithmetic intensity below the machine balance -> HBM roofline
+        if tn.startswith("ws") and fl / max(by, 1.0) < 100.0:
+            # small-channel convolutions whose arithmetic intensity is below the machine balance -> HBM roofline
             achieved = by / (ms / 1000.0) / 1e9
-            roof = {"kernel": "tapgemm_ws_kernel (weight-stationary + halo, tcgen05.mma kind::tf32 / kind::f16)", "bound": "hbm",
+            roof = {"kernel": f"tapgemm_ws_kernel [{tn}] (weight-stationary + halo, tcgen05.mma)", "bound": "hbm",
                     "achieved": round(achieved, 1), "peak": round(pk["hbm_gbs"], 1), "unit": "GB/s",
                     "frac": round(achieved / pk["hbm_gbs"], 4), "traffic": (traffic or {}).get("dram_bytes_per_launch") if (traffic or {}).get("family") == tn else None,
                     "peak_source": f"{pk_src} hbm_gbs", **common}
         else:
             achieved = fl / (ms / 1000.0) / 1e12
             eff_peak = fl / roof_t if roof_t > 0 else tf32_peak        # FLOP-weighted mix of the fp16 and TF32 peaks (TFLOP/s)
-            roof = {"kernel": f"tapgemm_{tn} (persistent tcgen05.mma kind::tf32 / kind::f16, double-buffered TMEM)", "bound": "tensor",
+            roof = {"kernel": (f"tapgemm_ws_kernel [{tn}] (weight-stationary + halo, tcgen05.mma)" if tn.startswith("ws") else
+                               f"tapgemm_tc2_kernel [{tn}] (persistent tcgen05.mma, double-buffered TMEM)"), "bound": "tensor",
                     "achieved": round(achieved, 2), "peak": round(eff_peak, 1), "unit": "TFLOP/s",
                     "frac": round(achieved / eff_peak, 4),
                     "traffic": (traffic or {}).get("dram_bytes_per_launch") if (traffic or {}).get("family") == tn else None,
-                    "peak_source": f"{pk_src} bf16_tflops_sustained for kind::f16 launches, half of it for kind::tf32 launches "
-                                   "(nominal 2:1; a TF32 peak was not measured separately), weighted by the FLOPs of each kind", **common}
+                    "peak_source": f"{pk_src} bf16_tflops_sustained for kind::f16 kernels, half of it for kind::tf32 kernels "
+                                   "(nominal 2:1; a TF32 peak is not in MEASURED_PEAKS.json)", **common}
         step_roof = {"tensor_tflop_per_step": round(tot_fl / 1e12, 2), "gemm_ms_per_step": round(tot_ms, 1),
                      "step_tflops": round(tot_fl / (prof_ms / 1000.0) / 1e12, 1),
                      "frac_of_tensor_roofline_whole_step": round((tot_roof * 1e-12 * 1000.0) / prof_ms, 4),
