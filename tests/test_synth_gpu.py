@@ -80,8 +80,6 @@ def test_conv1d_from1_row_kernel(C, K, stride, pad):
     assert (out2.cpu() - F.leaky_relu(want, 0.1)).abs().max() < 1e-4
 
 
-@pytest.mark.skipif(__import__("os").environ.get("B200VC_EXPERIMENTAL") != "1",
-                    reason="experimental fp16 storage of the vocoder's GEMM-only tensors (set B200VC_EXPERIMENTAL=1)")
 def test_synth_infer_parity_fp16_resblocks(monkeypatch):
     """Same parity bar as the TF32 path (waveform abs RMS <= 1e-3) with the ResBlock operands stored in fp16."""
     import aicovergen_b200.synth as bs

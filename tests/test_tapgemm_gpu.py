@@ -308,12 +308,11 @@ def test_persistent_256_row_tiles_conv2d():
 
 
 # ------------------------------------------------------------------------------------------------------------------
-# fp16 operand storage (tcgen05 kind::f16) — EXPERIMENTAL: not part of the product path in round 1.
-# Run with B200VC_EXPERIMENTAL=1.
+# fp16 operand storage (tcgen05 kind::f16): the default storage of the MDX-Net U-Net from round 2 on.
 # ------------------------------------------------------------------------------------------------------------------
 import os  # noqa: E402
 
-experimental = pytest.mark.skipif(os.environ.get("B200VC_EXPERIMENTAL") != "1", reason="experimental fp16 path (set B200VC_EXPERIMENTAL=1)")
+experimental = pytest.mark.gpu          # (was an opt-in marker in round 1)
 
 
 @experimental
