@@ -15,12 +15,11 @@ import torch
 
 from . import _ffi, ops
 from . import tapgemm as tg
-from .plans import PlanCache, StepGraph
+from .plans import ATT_SCRATCH_BYTES, PlanCache, StepGraph
 from .synth import round_tf32
 from .tapgemm import Epi
 
 CONV = [(512, 10, 5)] + [(512, 3, 2)] * 4 + [(512, 2, 2)] * 2
-ATT_SCRATCH_BYTES = 80 * 1024 * 1024       # score scratch of one query block: sized to stay inside the 126 MB L2
 
 
 class HubertB200:
@@ -172,9 +171,7 @@ class _HubertPlan:
         Tp = (T + 3) // 4 * 4
         qk = torch.empty(T, 2 * D, **f32)
         vT = torch.zeros(D, Tp, **f32)
-        # Attention runs per block of QB query rows: scores [H, QB, T] are produced, soft-maxed and consumed while they are
-        # still in the 126 MB L2 (12 x 512 x 3300 fp32 = 81 MB) — no [H, T, T] matrix (522 MB for a 66 s segment) ever
-        # exists, and its four HBM passes per layer (write, softmax read + write, PV read) are gone.
+        # Attention runs per block of QB query rows (scores [H, QB, T]); QB = T unless the scratch bound says otherwise.
         QB = min(T, max(128, (ATT_SCRATCH_BYTES // (4 * H * Tp)) // 128 * 128))
         sc = torch.zeros(H, QB, Tp, **f32)
         o = torch.empty(T, D, **f32)

@@ -9,6 +9,13 @@ from typing import Callable, Hashable
 
 PLAN_CACHE = int(os.environ.get("B200VC_PLAN_CACHE", "8"))
 
+# Score scratch of one attention query block.  r02e measured that cutting a 66 s segment (T = 3299) into 512-row blocks sized for
+# the L2 made HuBERT 35 % SLOWER (57 -> 77 ms per song: 7x the launches, small GEMMs, and the 81 MB block did not stay
+# L2-resident in practice), so by default a segment is ONE block; the blocked path bounds memory for very long segments
+# (scores of a 10-min segment would be 10 GB) and is what a fused flash-style kernel would replace.
+ATT_SCRATCH_BYTES = int(os.environ.get("B200VC_ATT_SCRATCH_MB", "1024")) * 1024 * 1024
+
+
 
 class PlanCache(OrderedDict):
     def get_or_build(self, key: Hashable, build: Callable[[], object]):

@@ -160,3 +160,31 @@ def test_ivf_index_short_and_empty_lists():
     assert np.isnan(ref[:5]).all() and np.isnan(got[:5]).all(), "empty list -> NaN row on both sides"
     assert np.allclose(got[5:], ref[5:], rtol=1e-4, atol=1e-5)
     assert gidx.ntotal == 61 and np.array_equal(gidx.reconstruct_n(0, 61), vecs)
+
+
+def test_blocked_attention_matches_single_block(monkeypatch):
+    """Attention in query blocks (plans.ATT_SCRATCH_BYTES bounds the score scratch; relative-position band terms take the
+    block's first row) gives the same result as one block per segment: HuBERT features and the synthesizer's latents."""
+    import aicovergen_b200.hubert as bh
+    import aicovergen_b200.synth as bs
+    from oracle import synth as osyn
+
+    hsd, cpt = make_hubert_state_dict(), make_rvc_checkpoint("40k", "v2")
+    x = torch.from_numpy(vocal_like(9.0, seed=2))[None].cuda()
+    P = 700
+    g = torch.Generator().manual_seed(3)
+    phone, pitch = torch.randn(1, P, 768, generator=g).cuda(), torch.randint(1, 255, (1, P), generator=g).cuda()
+    pitchf = (220.0 * 2 ** (0.5 * torch.sin(torch.arange(P) * 0.05)))[None].float().cuda()
+    nz, ns = osyn.draw_noise(7, P, 192, 400)
+    outs = []
+    for scratch in (1 << 30, 1 << 20):          # one block / blocks of 128 rows
+        monkeypatch.setattr(bh, "ATT_SCRATCH_BYTES", scratch)
+        monkeypatch.setattr(bs, "ATT_SCRATCH_BYTES", scratch)
+        feats = bh.HubertB200(hsd, "cuda:0").extract_features(source=x, padding_mask=None, output_layer=12)[0].clone()
+        o, _, lat = bs.SynthesizerB200(cpt, "cuda:0").infer(phone, torch.tensor([P]).cuda(), pitch, pitchf, torch.tensor([0]).cuda(),
+                                                           noise_z=nz.cuda(), noise_src=ns.cuda())
+        outs.append((feats, lat[2].clone(), o.clone()))
+    for a, b, name in zip(outs[0], outs[1], ("hubert features", "enc_p m_p", "waveform")):
+        d = float((a - b).abs().max())
+        print(f"[blocked attention] {name}: max abs diff vs single block {d:.2e}")
+        assert d <= 1e-6 * float(a.abs().max()) + 1e-7
