@@ -37,6 +37,8 @@ else:
               dict(name="b", dim_f=256, dim_t=64, n_fft=1024, stem="Instrumental", compensate=1.035),
               dict(name="c", dim_f=512, dim_t=128, n_fft=2048, stem="Other", compensate=1.035))
     kw, seconds = dict(g=16, n=3), args.seconds or 45.0
+    import aicovergen_b200.mdx as _bm
+    _bm.MDX_FP16 = False        # toy geometries: fp32 storage (their calibration clips are too short for stable fp16 ranges)
 mdx_w = [make_mdx_trained_like(s["dim_f"], s["dim_t"], s["n_fft"], seed=2024 + i, **kw) for i, s in enumerate(stages)]
 eng = CoverEngine(mdx_w, make_hubert_state_dict(), make_rmvpe_trained_like(), make_rvc_checkpoint("40k", "v2"), index=None,
                   device=dev, mdx_stages=stages)
@@ -79,9 +81,11 @@ shard, tn = timed(lambda: run(dist.group.WORLD))
 ok = True
 parts = []
 for k in ("vocals", "instrumental", "backup", "main", "dereverb", "converted", "cover"):
-    d = float((single[k] - shard[k]).abs().max())
-    parts.append(f"{k} {d:.1e}")
-    ok = ok and d == 0.0
+    same = torch.equal(single[k], shard[k])
+    finite = bool(torch.isfinite(single[k]).all())
+    d = float((single[k] - shard[k]).abs().max()) if finite else float("nan")
+    parts.append(f"{k} {d:.1e}" + ("" if finite else " (non-finite stem!)"))
+    ok = ok and same and finite
 print(f"rank {rank}/{world}: sharded vs single max abs diff: {', '.join(parts)} | {seconds:.0f} s song: single {t1 * 1e3:.0f} ms, "
       f"sharded over {world} {tn * 1e3:.0f} ms (x{t1 / tn:.2f})", flush=True)
 dist.barrier()
