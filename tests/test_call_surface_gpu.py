@@ -99,6 +99,7 @@ def test_file_level_call_surface(tmp_path, monkeypatch):
     assert [int(v) for v in weights["_meta"]] == [int(v) for v in sds[name]["_meta"]]
     sess = bmdx.MDX(weights, bmdx.MDXModel("cuda:0", dim_f, 2 ** lt, n_fft, stem_name=stem, compensation=comp), 0)
     main_a, inv_a = bmdx.run_mdx_arrays(sess, wave, denoise=True, m_threads=2)
+    assert np.isfinite(main_a).all() and np.isfinite(inv_a).all() and np.abs(main_a).max() > 1e-3
     for path, arr in ((voc_path, main_a), (inst_path, inv_a)):
         sr_f, d = _read(path)
         want = np.rint(np.clip(arr.T, -1, 1) * 32767.0).astype(np.int16)
