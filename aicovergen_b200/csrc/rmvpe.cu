@@ -327,6 +327,136 @@ bigru_v2_kernel(const float* __restrict__ xp, const float* __restrict__ whh /*[2
   cluster.sync();      // no CTA may exit while a peer could still write into its shared memory
 }
 
+// BiGRU v3: v2's shuffle-combined gates, but the exchange is ONE 128-byte cp.async.bulk (shared::cta -> shared::cluster,
+// mbarrier complete_tx) per peer and step instead of one st.async per (unit, peer): 8 remote transactions per CTA and step.
+__global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(GRU2_THREADS, 1)
+bigru_v3_kernel(const float* __restrict__ xp, const float* __restrict__ whh /*[2][3H][H]*/,
+                const float* __restrict__ bhh /*[2][3H]*/, float* __restrict__ out, int T) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int dir = blockIdx.x / GRU_CL;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool active = lane < 24;
+  const int ul = lane / 12;                         // unit within the warp (0/1); lanes 24..31 idle
+  const int li = lane - ul * 12;                    // 0..11
+  const int g = li >> 2, q = li & 3;                // gate (r,z,n), K quarter
+  const int j = warp * 2 + (active ? ul : 0);       // unit inside this CTA, 0..31
+  const int unit = rank * GRU_UPC + j;
+  const int wrow = g * GRU_H + unit;
+  const bool leader = active && li == 0;
+
+  __shared__ __align__(16) float hbuf[2][GRU_H];
+  __shared__ __align__(16) float hst[2][GRU_UPC];          // this CTA's new slice, staged for the bulk copies
+  __shared__ __align__(8) unsigned long long mbar[2];
+
+  float w[GRU_H / 4];
+  float bh = 0.f;
+  if (active) {
+    const float* src = whh + ((long long)dir * 3 * GRU_H + wrow) * GRU_H + q * (GRU_H / 4);
+#pragma unroll
+    for (int k = 0; k < GRU_H / 4; k += 4) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(src + k));
+      w[k] = v.x; w[k + 1] = v.y; w[k + 2] = v.z; w[k + 3] = v.w;
+    }
+    bh = bhh[dir * 3 * GRU_H + wrow];
+  } else {
+#pragma unroll
+    for (int k = 0; k < GRU_H / 4; ++k) w[k] = 0.f;
+  }
+  for (int i = threadIdx.x; i < 2 * GRU_H; i += GRU2_THREADS) (&hbuf[0][0])[i] = 0.f;
+  const uint32_t mb0 = gru_smem_u32(&mbar[0]), mb1 = gru_smem_u32(&mbar[1]);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb0));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  cluster.sync();
+
+  // remote addresses of every CTA's h buffers / barriers (leader lanes only)
+  uint32_t peer_h[GRU_CL], peer_mb[GRU_CL];
+#pragma unroll
+  for (int d = 0; d < GRU_CL; ++d) {
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer_h[d]) : "r"(gru_smem_u32(&hbuf[0][0])), "r"(d));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer_mb[d]) : "r"(mb0), "r"(d));
+  }
+
+  const long long xp_ld = 2 * 3 * GRU_H;
+  const float* xp_d = xp + dir * 3 * GRU_H;
+  int t = dir == 0 ? 0 : T - 1;
+  // x-projections of this thread's gate row, one step ahead (only the q == 0 lane of each gate uses it)
+  float xv = (active && q == 0) ? __ldg(xp_d + (long long)t * xp_ld + wrow) : 0.f;
+
+  for (int s = 0; s < T; ++s) {
+    const int cur = s & 1, nxt = cur ^ 1;
+    t = dir == 0 ? s : T - 1 - s;
+    const int tn = dir == 0 ? s + 1 : T - 2 - s;
+    // arm the barrier that will collect h_{s+1}: 256 floats from the 8 CTAs of the cluster (this one included)
+    if (threadIdx.x == 0)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(nxt ? mb1 : mb0), "r"(GRU_H * 4) : "memory");
+    float xv_next = 0.f;
+    if (active && q == 0 && s + 1 < T) xv_next = __ldg(xp_d + (long long)tn * xp_ld + wrow);
+
+    const float* h = &hbuf[cur][q * (GRU_H / 4)];
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+    for (int k = 0; k < GRU_H / 4; k += 4) {
+      const float4 hv = *reinterpret_cast<const float4*>(h + k);
+      a0 = fmaf(w[k], hv.x, a0);
+      a1 = fmaf(w[k + 1], hv.y, a1);
+      a2 = fmaf(w[k + 2], hv.z, a2);
+      a3 = fmaf(w[k + 3], hv.w, a3);
+    }
+    float acc = (a0 + a1) + (a2 + a3);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    const float hp = acc + bh;                              // W_h* h + b_h*   (valid on the q == 0 lane of each gate)
+    // gather (x, hp) of the three gates on the unit's leader lane
+    const int base = ul * 12;
+    const float hp_r = __shfl_sync(0xffffffffu, hp, base + 0), hp_z = __shfl_sync(0xffffffffu, hp, base + 4),
+                hp_n = __shfl_sync(0xffffffffu, hp, base + 8);
+    const float x_r = __shfl_sync(0xffffffffu, xv, base + 0), x_z = __shfl_sync(0xffffffffu, xv, base + 4),
+                x_n = __shfl_sync(0xffffffffu, xv, base + 8);
+    if (leader) {
+      const float r = 1.f / (1.f + expf(-(x_r + hp_r)));
+      const float z = 1.f / (1.f + expf(-(x_z + hp_z)));
+      const float n = tanhf(x_n + r * hp_n);
+      const float hprev = hbuf[cur][unit];
+      const float hnew = (1.f - z) * n + z * hprev;
+      out[(long long)t * (2 * GRU_H) + dir * GRU_H + unit] = hnew;
+      hst[nxt][j] = hnew;
+    }
+    xv = xv_next;
+    __syncthreads();                                   // the 32 new values of this CTA are staged
+    if (threadIdx.x == 0) {
+      // generic-proxy writes -> async-proxy reads, then ONE 128-byte bulk copy per peer (data + arrival signal together)
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      const uint32_t src = gru_smem_u32(&hst[nxt][0]);
+      const uint32_t off_h = (uint32_t)((nxt * GRU_H + rank * GRU_UPC) * 4), off_mb = (uint32_t)(nxt * 8);
+#pragma unroll
+      for (int d = 0; d < GRU_CL; ++d)
+        asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(peer_h[d] + off_h),
+                     "r"(src), "r"(GRU_UPC * 4), "r"(peer_mb[d] + off_mb)
+                     : "memory");
+    }
+    // wait for all 256 floats of h_{s+1}
+    {
+      const uint32_t bar = nxt ? mb1 : mb0;
+      const uint32_t parity = (uint32_t)((s >> 1) & 1);
+      asm volatile(
+          "{\n\t"
+          ".reg .pred p;\n\t"
+          "GRU3_WAIT:\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+          "@p bra GRU3_DONE;\n\t"
+          "bra GRU3_WAIT;\n\t"
+          "GRU3_DONE:\n\t"
+          "}" ::"r"(bar), "r"(parity)
+          : "memory");
+    }
+  }
+  cluster.sync();      // no CTA may exit while a peer could still write into its shared memory
+}
+
 // ---------------------------------------------------------------------------
 // to_local_average_cents + decode (rmvpe.py:359-364, 385-409) — one warp per frame, float64 where
 // numpy is float64, and numpy's pairwise summation order for the 9-element reductions:
@@ -439,10 +569,12 @@ int b200vc_bigru(const float* xp, const float* whh, const float* bhh, float* out
   B200VC_REQUIRE(xp && whh && bhh && out && T > 0, "bigru: bad args");
   B200VC_REQUIRE(hidden == GRU_H, "bigru: hidden size %d unsupported (kernel is specialised for %d)", hidden, GRU_H);
   // v2 (st.async + mbarrier per step) measured SLOWER on B200 (r02d: 3.3 us/step vs 1.3 us/step for v1: 256 remote
-  // complete_tx updates per CTA and step cost more than one cluster barrier); kept behind B200VC_GRU_V2=1 for experiments
-  static const bool v1 = [] { const char* e = getenv("B200VC_GRU_V2"); return !(e && e[0] == '1'); }();
-  if (v1) bigru_kernel<<<2 * GRU_CL, GRU_THREADS, 0, (cudaStream_t)stream>>>(xp, whh, bhh, out, T);
-  else bigru_v2_kernel<<<2 * GRU_CL, GRU2_THREADS, 0, (cudaStream_t)stream>>>(xp, whh, bhh, out, T);
+  // complete_tx updates per CTA and step cost more than one cluster barrier); kept behind B200VC_GRU=2 (v3: B200VC_GRU=3) for experiments
+  const char* e = getenv("B200VC_GRU");                 // 1 (default) | 2 | 3: exchange variant, see the kernels above
+  const int ver = (e && (e[0] == '2' || e[0] == '3')) ? e[0] - '0' : 1;
+  if (ver == 1) bigru_kernel<<<2 * GRU_CL, GRU_THREADS, 0, (cudaStream_t)stream>>>(xp, whh, bhh, out, T);
+  else if (ver == 2) bigru_v2_kernel<<<2 * GRU_CL, GRU2_THREADS, 0, (cudaStream_t)stream>>>(xp, whh, bhh, out, T);
+  else bigru_v3_kernel<<<2 * GRU_CL, GRU2_THREADS, 0, (cudaStream_t)stream>>>(xp, whh, bhh, out, T);
   count_launch();
   B200VC_LAUNCH_CHECK();
   return kOk;

@@ -118,12 +118,14 @@ def test_rmvpe_decode_kernel_exact():
     assert (orm.coarse_pitch(got)[0] == orm.coarse_pitch(ref)[0]).all()
 
 
+@pytest.mark.parametrize("ver", ["1", "2", "3"])
 @pytest.mark.parametrize("T", [37, 1024, 24608])
-def test_bigru_kernel_matches_torch_gru(T):
+def test_bigru_kernel_matches_torch_gru(T, ver, monkeypatch):
     """b200vc_bigru (2 clusters x 8 CTAs, one DSMEM hop per step) against torch.nn.GRU(384, 256, bidirectional) on the CPU:
     24 608 steps = the F0 of a 4-min song."""
     from aicovergen_b200 import ops
 
+    monkeypatch.setenv("B200VC_GRU", ver)       # 1: cluster barrier per step (default); 2: st.async per value; 3: bulk copy per peer
     g = torch.Generator().manual_seed(T)
     gru = torch.nn.GRU(384, 256, num_layers=1, batch_first=True, bidirectional=True).eval()
     x = torch.randn(1, T, 384, generator=g)
@@ -141,5 +143,5 @@ def test_bigru_kernel_matches_torch_gru(T):
     e.record()
     torch.cuda.synchronize()
     err = (out.cpu() - ref).abs().max().item()
-    print(f"[bigru T={T}] max abs err {err:.3e}; {s.elapsed_time(e):.2f} ms = {s.elapsed_time(e) * 1e3 / T:.3f} us/step")
+    print(f"[bigru v{ver} T={T}] max abs err {err:.3e}; {s.elapsed_time(e):.2f} ms = {s.elapsed_time(e) * 1e3 / T:.3f} us/step")
     assert err < 2e-5
