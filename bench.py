@@ -384,6 +384,24 @@ def run_config(args, device):
         h2d, d2h = x.nbytes, 8 * (1 + len(x) // 160)
         cpu_fn, cpu_units = (lambda: orm.infer_from_audio(rsd, x, 0.03)), seconds
         workload = "cfg 1: rmvpe F0 on a 10 s 100->1000 Hz sine sweep @16 kHz (RMVPE.infer_from_audio, thred 0.03)"
+    elif name == "crepe60":
+        import types
+
+        from aicovergen_b200.crepe import CrepeB200
+        from aicovergen_b200.synthetic import make_crepe_state_dict
+        from aicovergen_b200.vc_infer_pipeline import VC
+        from oracle import crepe as oc
+        seconds = 60.0
+        x = synth_song(seconds * 44100 / 48000 + 1.0, 7).mean(0)[::3][: int(sr16 * seconds)].astype(np.float32).copy()
+        csd = make_crepe_state_dict()
+        vc = VC(40000, types.SimpleNamespace(device=device, is_half=True, x_pad=3, x_query=10, x_center=60, x_max=65))
+        vc.model_crepe = CrepeB200(csd, device)
+        xd = torch.from_numpy(x).to(device)
+        dev_fn = lambda: vc.model_crepe.viterbi_bins(vc.model_crepe.activations(xd / float(np.quantile(np.abs(x), 0.999)), 128), 50.0, 1100.0)
+        e2e_fn = lambda: vc.get_f0_crepe_computation(x.astype(np.float64), 50, 1100, None, 128)
+        h2d, d2h = x.nbytes, 4 * (1 + len(x) // 128)
+        cpu_fn, cpu_units = (lambda: oc.get_f0_crepe_computation(csd, x[: 4 * sr16].astype(np.float64), 50, 1100, None, 128)), 4.0
+        workload = "crepe F0 (f0_method mangio-crepe, hop 128, torchcrepe 'full' CNN + Viterbi) on a 60 s vocal @16 kHz: 7501 frames, 21 TFLOP (CPU: 4 s)"
     elif name == "hubert30":
         from aicovergen_b200.hubert import HubertB200
         from oracle import hubert as ohub
@@ -498,7 +516,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--seconds", type=float, default=float(SONG_SECONDS), help="song length (default: the 4-min headline config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--config", default="cover", choices=["cover", "rmvpe10", "hubert30", "vc60", "mdx4min"],
+    ap.add_argument("--config", default="cover", choices=["cover", "rmvpe10", "hubert30", "vc60", "mdx4min", "crepe60"],
                     help="cover (default): the headline 4-min song_cover_pipeline graph; the others: BASELINE.json configs 1-4 as their own lines")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak (default, BASELINE cfg 5): one song per GPU; strong (cfg 4 style): ONE song shared by all GPUs — MDX chunk "
