@@ -39,6 +39,10 @@ class MDXModel:
     """Geometry of one MDX-Net model (mdx.py:19-35) plus API-compatible stft / istft on device tensors."""
 
     def __init__(self, device, dim_f, dim_t, n_fft, hop=1024, stem_name=None, compensation=1.000):
+        if n_fft <= hop:
+            # a periodic Hann window of n_fft <= hop has zeros in its overlap-add envelope: the reference's torch.istft
+            # (mdx.py:52-62) raises "window overlap add min: 1" there; refuse up front instead of dividing by zero
+            raise RuntimeError(f"MDXModel: n_fft {n_fft} with hop {hop}: window overlap-add envelope has zeros (torch.istft refuses it)")
         self.dim_f, self.dim_t, self.dim_c = dim_f, dim_t, 4
         self.n_fft, self.hop = n_fft, hop
         self.stem_name, self.compensation = stem_name, compensation

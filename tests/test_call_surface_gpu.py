@@ -27,7 +27,7 @@ pytestmark = pytest.mark.gpu
 # covered by tests/test_baseline_configs_gpu.py): name -> (dim_f, log2 dim_t, n_fft, stem, compensate)
 SMALL_MDX = {
     "UVR-MDX-NET-Voc_FT": (256, 5, 2048, "Vocals", 1.021),
-    "UVR_MDXNET_KARA_2": (128, 5, 1024, "Instrumental", 1.035),
+    "UVR_MDXNET_KARA_2": (128, 5, 2048, "Instrumental", 1.035),
     "Reverb_HQ_By_FoxJoy": (256, 6, 2048, "Other", 1.035),
 }
 

@@ -34,11 +34,9 @@ if args.full:
     x_cfg = None
 else:
     stages = (dict(name="a", dim_f=512, dim_t=64, n_fft=2048, stem="Vocals", compensate=1.021),
-              dict(name="b", dim_f=256, dim_t=64, n_fft=1024, stem="Instrumental", compensate=1.035),
+              dict(name="b", dim_f=256, dim_t=64, n_fft=2048, stem="Instrumental", compensate=1.035),
               dict(name="c", dim_f=512, dim_t=128, n_fft=2048, stem="Other", compensate=1.035))
     kw, seconds = dict(g=16, n=3), args.seconds or 45.0
-    import aicovergen_b200.mdx as _bm
-    _bm.MDX_FP16 = False        # toy geometries: fp32 storage (their calibration clips are too short for stable fp16 ranges)
 mdx_w = [make_mdx_trained_like(s["dim_f"], s["dim_t"], s["n_fft"], seed=2024 + i, **kw) for i, s in enumerate(stages)]
 eng = CoverEngine(mdx_w, make_hubert_state_dict(), make_rmvpe_trained_like(), make_rvc_checkpoint("40k", "v2"), index=None,
                   device=dev, mdx_stages=stages)

@@ -14,7 +14,7 @@ from oracle import mdx as om  # noqa: E402
 from siggen import song_44k  # noqa: E402
 
 wave = song_44k(12.0, seed=3)
-for (dim_f, dim_t, n_fft, g) in ((512, 64, 2048, 16), (256, 64, 1024, 16), (512, 128, 2048, 16), (256, 32, 2048, 8), (256, 64, 2048, 8)):
+for (dim_f, dim_t, n_fft, g) in ((512, 64, 2048, 16), (512, 128, 2048, 16), (256, 32, 2048, 8), (256, 64, 2048, 8)):
     sd = make_mdx_trained_like(dim_f, dim_t, n_fft, g=g, n=3)
     mp = om.MdxParams(dim_f, dim_t, n_fft)
     ref = om.process_wave(wave.copy(), mp, lambda s: om.convtdfnet(sd, s), 2)
