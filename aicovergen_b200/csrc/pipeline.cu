@@ -186,23 +186,6 @@ __global__ void resample_sinc_mono_kernel(const float* __restrict__ x, long long
   out[m] = acc;
 }
 
-// out[ch,n] = ga * lerp(a_mono, n * ra) + gb * b[ch,n] + gc * c[ch,n]  — gain-and-sum stand-in for the pydub overlay
-// at main.py:229-233 (a = converted vocals at its own rate, b = backup vocals, c = instrumental)
-__global__ void mix3_kernel(const float* __restrict__ a, long long n_a, double ra, const float* __restrict__ b,
-                            const float* __restrict__ c, float* __restrict__ out, long long n, float ga, float gb,
-                            float gc) {
-  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= 2 * n) return;
-  const long long i = e % n;
-  const double pos = (double)i * ra;
-  const long long i0 = (long long)pos;
-  const float fr = (float)(pos - (double)i0);
-  float av = 0.f;
-  if (i0 + 1 < n_a) av = a[i0] * (1.f - fr) + a[i0 + 1] * fr;
-  else if (i0 < n_a) av = a[i0];
-  out[e] = ga * av + gb * b[e] + gc * c[e];
-}
-
 }  // namespace
 }  // namespace b200vc
 
@@ -254,15 +237,6 @@ int b200vc_resample_sinc_mono(const float* x, int64_t n_in, int channels, float*
   B200VC_REQUIRE(x && out && n_in > 0 && n_out > 0 && channels > 0 && ratio > 0, "resample_sinc_mono: bad args");
   resample_sinc_mono_kernel<<<blocks_for(n_out, 256), 256, 0, (cudaStream_t)stream>>>(x, n_in, channels, out, n_out, ratio,
                                                                                     zero_crossings);
-  count_launch();
-  B200VC_LAUNCH_CHECK();
-  return kOk;
-}
-
-int b200vc_mix3(const float* a_mono, int64_t n_a, double ratio_a, const float* b, const float* c, float* out, int64_t n,
-                float ga, float gb, float gc, void* stream) {
-  B200VC_REQUIRE(a_mono && b && c && out && n > 0 && n_a > 0, "mix3: bad args");
-  mix3_kernel<<<blocks_for(2 * n, 256), 256, 0, (cudaStream_t)stream>>>(a_mono, n_a, ratio_a, b, c, out, n, ga, gb, gc);
   count_launch();
   B200VC_LAUNCH_CHECK();
   return kOk;

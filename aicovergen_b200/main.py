@@ -7,11 +7,11 @@ Stage graph (main.py:166-190, 193-203, 229-233):
     vocals --MDX(KARA_2, denoise)--> backup vocals (main stem), main vocals (inverse stem)
     main vocals --MDX(Reverb_HQ, denoise, exclude_main)--> de-reverbed main vocals (inverse stem)
     de-reverbed vocals --mono 16 kHz--> RVC VC.pipeline --> converted vocals @ tgt_sr
-    converted + backup + instrumental --gains -4/-6/-7 dB, overlay--> cover
+    converted vocals --high-pass, compressor, reverb (main.py:206-226)--> effected vocals (int16, as the WAV holds them)
+    effected + backup + instrumental --pydub: gains -4/-6/-7 dB, overlay (main.py:229-233)--> cover (int16 frames)
 
-Out of scope here: YouTube download, ffmpeg/sox, pedalboard effects (HPF +
-compressor + reverb) and pydub's mp3 export — the effects stage is a pass-through and the mix is a plain
-gain-and-sum (documented substitution, also used by the CPU arm of bench.py).
+Out of scope here: YouTube download, ffmpeg/sox (`pitch_change_all`) and the mp3 ENCODER behind
+pydub's export — the cover is written as 16-bit WAV (the frames pydub hands to its encoder).
 """
 from __future__ import annotations
 
@@ -26,6 +26,7 @@ import torch
 from scipy.io import wavfile
 
 from . import _ffi, ops
+from . import effects as fx
 from .mdx import MDX, MDXModel, run_mdx, run_mdx_arrays, run_mdx_device, _read_wav_44k, _write_wav_pcm16
 from .rvc import Config, get_vc, load_hubert, rvc_infer
 
@@ -44,10 +45,6 @@ MDX_STAGES = (
 
 
 SUPPORTED_F0_METHODS = ("rmvpe", "mangio-crepe")
-
-
-def db_gain(db: float) -> float:
-    return float(10.0 ** (db / 20.0))
 
 
 class CoverEngine:
@@ -103,24 +100,28 @@ class CoverEngine:
         finally:
             self.vc.return_device = False
 
-    @_ffi.on_device
-    @torch.no_grad()
+    def effects(self, ai_vocals_i16, reverb_rm_size=0.15, reverb_wet=0.2, reverb_dry=0.8, reverb_damping=0.7) -> torch.Tensor:
+        """add_audio_effects (main.py:206-226) on the int16 utterance at tgt_sr (host array or device tensor): the int16
+        samples of `..._mixed.wav`, on the device."""
+        a = ai_vocals_i16 if isinstance(ai_vocals_i16, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(ai_vocals_i16))
+        return fx.add_audio_effects_device(a.to(self.device), self.tgt_sr, reverb_rm_size, reverb_wet, reverb_dry, reverb_damping)
+
     def mix(self, ai_vocals_i16, backup: torch.Tensor, instrumental: torch.Tensor, main_gain=0, backup_gain=0,
             inst_gain=0) -> torch.Tensor:
-        """ai_vocals_i16: the int16 utterance at tgt_sr, host array or device tensor (exactly what the caller passes is
-        mixed; nothing is substituted)."""
-        if isinstance(ai_vocals_i16, torch.Tensor):
-            a = ai_vocals_i16.to(self.device).float() / 32768.0
-        else:
-            a = torch.from_numpy(np.asarray(ai_vocals_i16).astype(np.float32) / 32768.0).to(self.device)
-        out = torch.empty_like(backup)
-        ops.mix3(a, self.tgt_sr, backup.contiguous(), instrumental.contiguous(), out, 44100, db_gain(-4 + main_gain),
-                 db_gain(-6 + backup_gain), db_gain(-7 + inst_gain))
+        """combine_audio (main.py:229-233): ai_vocals_i16 = the int16 utterance at tgt_sr (host array or device tensor; exactly
+        what the caller passes is mixed); backup / instrumental = float stems [2, n] @44.1k in HBM, quantised to the int16
+        frames their WAV files would hold.  Returns the cover's int16 frames [n_out, 2] @44.1k on the device."""
+        a = ai_vocals_i16 if isinstance(ai_vocals_i16, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(ai_vocals_i16))
+        out, rate = fx.combine_audio_device([(a.to(self.device), self.tgt_sr), (fx.pcm16_from_planar(backup), 44100),
+                                             (fx.pcm16_from_planar(instrumental), 44100)], main_gain, backup_gain, inst_gain)
+        self.cover_rate = rate          # max(tgt_sr, 44100): pydub mixes at the highest of the operands' rates
         return out
 
     @_ffi.on_device
-    def cover_device(self, song_dev: torch.Tensor, main_gain=0, backup_gain=0, inst_gain=0, group=None, **convert_kw) -> torch.Tensor:
-        """song already in HBM -> cover in HBM (the converted utterance is handed to the mix as a device tensor).
+    def cover_device(self, song_dev: torch.Tensor, main_gain=0, backup_gain=0, inst_gain=0, group=None, reverb_rm_size=0.15,
+                     reverb_wet=0.2, reverb_dry=0.8, reverb_damping=0.7, **convert_kw) -> torch.Tensor:
+        """song already in HBM -> the cover's int16 frames [n, 2] in HBM (the converted utterance goes through the effects
+        and into the mix as a device tensor).
         `group`: ranks of a torch.distributed group work on the SAME song (every rank must call this with the same song):
         MDX chunks and RVC segments are shared, every rank ends with the full cover."""
         stems = self.separate(song_dev, group)
@@ -129,11 +130,12 @@ class CoverEngine:
             ai = self.convert(stems["dereverb"], return_device=True, **convert_kw)
         finally:
             self.vc.group = None
+        ai = self.effects(ai, reverb_rm_size, reverb_wet, reverb_dry, reverb_damping)
         return self.mix(ai, stems["backup"], stems["instrumental"], main_gain, backup_gain, inst_gain)
 
     @_ffi.on_device
     def cover(self, song: np.ndarray, **kw) -> np.ndarray:
-        """Host array in, host array out (H2D of the song and D2H of the cover included)."""
+        """Host array [2, N] float32 in, the cover's int16 frames [n, 2] out (H2D of the song and D2H of the cover included)."""
         dev = torch.from_numpy(np.ascontiguousarray(song, dtype=np.float32)).to(self.device, non_blocking=True)
         return self.cover_device(dev, **kw).cpu().numpy()
 
@@ -236,30 +238,34 @@ def voice_change(voice_model, vocals_path, output_path, pitch_change, f0_method,
     gc.collect()
 
 
+def _read_wav_i16(path):
+    sr, data = wavfile.read(path)
+    if data.dtype != np.int16:
+        raise ValueError(f"{path}: 16-bit PCM expected (every stage of the pipeline writes PCM_16), got {data.dtype}")
+    return int(sr), data
+
+
 def add_audio_effects(audio_path, reverb_rm_size, reverb_wet, reverb_dry, reverb_damping):
-    """main.py:206-226 applies pedalboard HPF + compressor + reverb; pass-through here."""
+    """main.py:206-226: HighpassFilter -> Compressor(ratio 4, threshold -15 dB) -> Reverb on the converted vocal, written next
+    to it as `<name>_mixed.wav` (16-bit, same rate and channel count)."""
     output_path = f"{os.path.splitext(audio_path)[0]}_mixed.wav"
-    sr, data = wavfile.read(audio_path)
-    wavfile.write(output_path, sr, data)
+    sr, data = _read_wav_i16(audio_path)
+    if data.ndim != 1:
+        raise NotImplementedError("add_audio_effects: mono input only (the RVC output is mono)")
+    out = fx.add_audio_effects_device(torch.from_numpy(data).to("cuda:0"), sr, reverb_rm_size, reverb_wet, reverb_dry, reverb_damping)
+    wavfile.write(output_path, sr, out.cpu().numpy())
     return output_path
 
 
 def combine_audio(audio_paths, output_path, main_gain, backup_gain, inst_gain, output_format):
-    """Gain-and-sum stand-in for the pydub overlay/export (main.py:229-233); always writes 16-bit WAV."""
-    sr_a, a = wavfile.read(audio_paths[0])
-    sr_b, b = wavfile.read(audio_paths[1])
-    sr_c, c = wavfile.read(audio_paths[2])
-    dev = "cuda:0"
-    to_f = lambda x: x.astype(np.float32) / 32768.0 if x.dtype == np.int16 else x.astype(np.float32)
-    a = to_f(a if a.ndim == 1 else a.mean(1))
-    b, c = to_f(b), to_f(c)
-    n = min(len(b), len(c))
-    bt = torch.from_numpy(np.ascontiguousarray(b[:n].T)).to(dev)
-    ct = torch.from_numpy(np.ascontiguousarray(c[:n].T)).to(dev)
-    out = torch.empty_like(bt)
-    ops.mix3(torch.from_numpy(a).to(dev), sr_a, bt, ct, out, sr_b, db_gain(-4 + main_gain), db_gain(-6 + backup_gain),
-             db_gain(-7 + inst_gain))
-    _write_wav_pcm16(output_path, out.cpu().numpy().T, sr_b)
+    """main.py:229-233: pydub gains (-4 / -6 / -7 dB + the user's), overlay of backup vocals and instrumental onto the main
+    vocals, export.  The mp3 encoder is out of scope: the frames are always written as 16-bit WAV."""
+    srcs = []
+    for p in audio_paths:
+        sr, data = _read_wav_i16(p)
+        srcs.append((torch.from_numpy(data).to("cuda:0"), sr))
+    out, rate = fx.combine_audio_device(srcs, main_gain, backup_gain, inst_gain)
+    wavfile.write(output_path, rate, out.cpu().numpy())
 
 
 def song_cover_pipeline(song_input, voice_model, pitch_change, keep_files, is_webui=0, main_gain=0, backup_gain=0,

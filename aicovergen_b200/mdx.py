@@ -543,9 +543,12 @@ def _read_wav_44k(filename):
 
 
 def _write_wav_pcm16(path, data_T, sr):
-    """soundfile.write(path, data, sr) default subtype for .wav is PCM_16 (mdx.py:273,280)."""
-    x = np.clip(data_T, -1.0, 1.0)
-    wavfile.write(path, sr, np.rint(x * 32767.0).astype(np.int16))
+    """soundfile.write(path, data, sr) (mdx.py:273,280): default subtype for .wav is PCM_16, and libsndfile converts float
+    data with lrintf(x * 0x7FFF) WITHOUT clipping (SFC_SET_CLIPPING is off by default): samples beyond +-1 wrap.  The same
+    conversion runs on the device for stems that stay in HBM (b200vc_pcm16_from_planar)."""
+    with np.errstate(invalid="ignore"):
+        q = np.rint(np.asarray(data_T, dtype=np.float32) * np.float32(32767.0)).astype(np.int64).astype(np.int16)
+    wavfile.write(path, sr, q)
 
 
 def run_mdx_device(mdx_sess: MDX, wave_dev: torch.Tensor, denoise=False, m_threads=2, group=None):

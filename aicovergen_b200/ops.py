@@ -47,7 +47,6 @@ _ffi.declare("b200vc_nhcw_to_nhwc_add", [_P, _P, _P, _i64, _i32, _i32, _i32, _P]
 _ffi.declare("b200vc_mdx_ola_store", [_P, _P, _P, _P, _P, _P, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _i32, _P])
 _ffi.declare("b200vc_mdx_finalize", [_P, _P, _P, _i64, _f32, _f32, _P])
 _ffi.declare("b200vc_resample_sinc_mono", [_P, _i64, _i32, _P, _i64, C.c_double, _i32, _P])
-_ffi.declare("b200vc_mix3", [_P, _i64, C.c_double, _P, _P, _P, _i64, _f32, _f32, _f32, _P])
 _ffi.declare("b200vc_change_rms", [_P, _i64, _i32, _P, _i64, _i32, C.c_double, _P, _P])
 _ffi.declare("b200vc_to_int16_peak_guard", [_P, _i64, _P, _P, _P])
 _ffi.declare("b200vc_sosfiltfilt_f64", [_P, _i64, _P, _i32, _P, _P, _P, _i32, _i32, _P, _P, _P])
@@ -329,13 +328,6 @@ def resample_sinc_mono(x, out, rate_in, rate_out, zero_crossings=16):
     assert x.is_contiguous() and out.is_contiguous()
     _ffi.check(_ffi.lib().b200vc_resample_sinc_mono(_p(_f32c(x)), n_in, ch, _p(out), out.numel(), float(rate_in) / float(rate_out),
                                                     zero_crossings, _s()), "resample_sinc_mono")
-
-
-def mix3(a_mono, rate_a, b, c, out, rate, ga, gb, gc):
-    n = out.shape[1]
-    assert a_mono.is_contiguous() and b.is_contiguous() and c.is_contiguous() and out.is_contiguous()
-    _ffi.check(_ffi.lib().b200vc_mix3(_p(_f32c(a_mono)), a_mono.numel(), float(rate_a) / float(rate), _p(b), _p(c), _p(out), n,
-                                      float(ga), float(gb), float(gc), _s()), "mix3")
 
 
 def change_rms(data1, sr1, data2, sr2, rate):

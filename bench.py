@@ -5,7 +5,7 @@ Metric (BASELINE.json): audio-seconds/sec (RTF) of the full cover pipeline on a 
 One "step" = one 4-min song through the song_cover_pipeline stage graph on one GPU:
     3 MDX-Net passes with denoise (Voc_FT / KARA_2 / Reverb_HQ-class geometries, 88+88+44x2 chunk inferences)
     -> mono 16 kHz -> VC.pipeline (HuBERT + rmvpe F0 + IVF index blend + flow/NSF-HiFiGAN synthesizer, 4 segments)
-    -> gain-and-sum mix.
+    -> vocal effects (high-pass, compressor, reverb) -> pydub mix (gains, overlay) -> the cover's int16 frames.
 Weights are seeded synthetic checkpoints of the real architectures (no model files exist offline).
 N GPUs = N songs (one per rank, weak scaling, no data-path collective).
 
@@ -165,8 +165,11 @@ def output_check(eng, song_dev, song_seconds):
     ops.resample_sinc_mono(d.contiguous(), mono, 44100, 16000)
     ai = eng.convert(d, return_device=True)
     res["converted"] = stat(ai.float() / 32768.0)
-    cover = eng.mix(ai, stems["backup"], stems["instrumental"])
-    res["cover"] = stat(cover)
+    fx16 = eng.effects(ai)
+    res["effected"] = stat(fx16.float() / 32768.0)
+    cover = eng.mix(fx16, stems["backup"], stems["instrumental"])
+    res["cover"] = stat(cover.float() / 32768.0)
+    res["cover"]["frames"], res["cover"]["rate"] = int(cover.shape[0]), int(eng.cover_rate)
     bad = [k for k, v in res.items() if not v["finite"] or v["rms"] < 1e-4]
     if bad:
         raise SystemExit(f"bench: non-finite or silent output in {bad}: {res}")
@@ -324,8 +327,14 @@ def cpu_reference_sample(threads: int, parts=None):
             cent, vecs = make_ivf_index_data(feats, n_total=87243, nlist=2237, lloyd=False)
             _CPU_CACHE["index"] = IvfFlatIndex(cent, vecs)
         audio = synth_song(float(vc_s) * 44100 / 48000 + 1.0, 1).mean(0)[::3][: vc_s * 16000].astype(np.float32).copy()
+        from oracle import effects as oeff
+        from oracle import mixdown as omix
+        oeff.build()
+        stem16 = np.rint(synth_song(float(vc_s), 5) * np.float32(32767.0)).astype(np.int16).T.copy()      # [n, 2] @44.1k
         t0 = time.perf_counter()
-        opipe.pipeline(hsd, cpt, rsd, audio, index=_CPU_CACHE["index"], seed=0)
+        ai16 = opipe.pipeline(hsd, cpt, rsd, audio, index=_CPU_CACHE["index"], seed=0)
+        fx16, _ = oeff.add_audio_effects(ai16, cpt["config"][-1], 0.15, 0.2, 0.8, 0.7)                   # main.py:206-226
+        omix.combine_audio(fx16, cpt["config"][-1], stem16, 44100, stem16, 44100)                          # main.py:229-233
         last[3] = time.perf_counter() - t0
         measured += last[3]
     detail["vc_pipeline"] = {f"s_per_{vc_s}s_audio": round(last[3], 3), "index": "IVF2237 x 87243, index_rate 0.5", "timed_this_step": 3 in todo}
@@ -365,11 +374,11 @@ def run_reference(args, rank):
         "warmup": args.warmup, "ms_per_step": meas * 1000.0, "ms_per_full_step_extrapolated": tot * 1000.0,
         "sample_audio_seconds_equivalent": round(v * meas, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "song_cover_pipeline stage graph, 4-min 44.1 kHz stereo song (3 MDX passes w/ denoise + VC.pipeline rmvpe + mix), "
+        "config": {"workload": "song_cover_pipeline stage graph, 4-min 44.1 kHz stereo song (3 MDX passes w/ denoise + VC.pipeline rmvpe + effects + pydub mix), "
                                "CPU time extrapolated from a bounded sample", "sample": vals[-1][2]},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": "EXTRAPOLATED: 1 full-size chunk per MDX model (STFT+net+iSTFT) x chunk count x2 sweeps, + VC.pipeline "
-                                   "(rmvpe, IVF2237 x 87243 index) on 20 s x12; oracle/ restatement pinned against /root/reference",
+                                   "(rmvpe, IVF2237 x 87243 index) + effects + mix on 20 s x12; oracle/ restatement pinned against /root/reference",
                          "extrapolated": True},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -718,7 +727,8 @@ def main():
             "dtype": DTYPE_NOTE, "data": "synthetic",
             "config": {"workload": f"song_cover_pipeline stage graph on one {args.seconds:.0f}-s 44.1 kHz stereo song per GPU: 3 MDX-Net passes "
                                    "(3072x256/7680, 2048x256/5120, 3072x512/6144; denoise=True) + VC.pipeline (HuBERT-base, rmvpe, "
-                                   "IVF2237 x 87243 index_rate 0.5, v2 40k synthesizer) + mix",
+                                   "IVF2237 x 87243 index_rate 0.5, v2 40k synthesizer) + vocal effects (high-pass, compressor, reverb) "
+                                   "+ pydub mix -> int16 cover frames",
                        "songs": world, "l2": "256 MB buffer written between steps; per-step working set >> 126 MB L2",
                        "weights": "seeded synthetic checkpoints of the real architectures, trained-like (BatchNorm statistics fitted on a calibration clip; smooth single-peak rmvpe salience)"},
             "clocks": sampler.summary(),

@@ -334,9 +334,49 @@ int b200vc_mdx_finalize(float* proc, const float* wave_norm, float* inverse, int
 int b200vc_resample_sinc_mono(const float* x, int64_t n_in, int channels, float* out, int64_t n_out, double ratio,
                               int zero_crossings, void* stream);
 
-/* out[2,n] = ga*lerp(a_mono at ratio_a) + gb*b + gc*c : gain-and-sum stand-in for main.combine_audio (main.py:229-233) */
-int b200vc_mix3(const float* a_mono, int64_t n_a, double ratio_a, const float* b, const float* c, float* out, int64_t n,
-                float ga, float gb, float gc, void* stream);
+/* ---- vocal effects + final mix (main.add_audio_effects main.py:206-226, main.combine_audio main.py:229-233) ---- */
+
+/* pedalboard HighpassFilter (JUCE dsp::IIR first-order high-pass, TDF-II: y = b0 x + s; s = b1 x - a1 y) followed by
+ * pedalboard Compressor (JUCE dsp::Compressor: peak BallisticsFilter env += cte (env - |y|) with cte = cte_at when rising else
+ * cte_rl; gain = env < thr ? 1 : (env * thr_inv) ^ expo).  x: the int16 WAV samples (mono), read as x * 2^-15; y: float out.
+ * The signal is processed in chunks of `chunk` samples, each recomputed from `warm` samples earlier with zero state. */
+int b200vc_fx_hpf_comp(const int16_t* x, float* y, int64_t n, int chunk, int warm, float b0, float b1, float a1, float cte_at,
+                       float cte_rl, float thr, float thr_inv, float expo, void* stream);
+
+/* juce::Reverb, mono: the eight parallel comb filters (delays8: HOST array; input x * gain, damping low-pass `damp`, feedback)
+ * written as their delay-line contents Y [8, n] (scratch) and summed into comb_sum [n].  terms = Horner terms of the damping
+ * low-pass (damp^terms below float resolution). */
+int b200vc_fx_reverb_combs(const float* x, float* Y, float* comb_sum, int64_t n, const int* delays8, float gain, float damp,
+                           float feedback, int terms, void* stream);
+
+/* juce::Reverb AllPassFilter (gain 0.5): out[t] = w[t - delay] - in[t], w[t] = in[t] + 0.5 w[t - delay]; in != out. */
+int b200vc_fx_allpass(const float* in, float* out, int64_t n, int delay, int terms, void* stream);
+
+/* samples = reverb * wet1 + x * dry, then JUCE's float -> 16-bit WAV conversion (int32 full scale, round-half-even, >> 16).
+ * out_f (optional): the float samples before the conversion. */
+int b200vc_fx_finish(const float* reverb, const float* x, int16_t* out16, float* out_f, int64_t n, float wet1, float dry,
+                     void* stream);
+
+/* x [channels, n] float (a stem in HBM) -> out [n, channels] int16 as soundfile writes a float array to a PCM_16 WAV
+ * (mdx.py:283-284; libsndfile: lrintf(x * 0x7FFF), the conversion to short wraps). */
+int b200vc_pcm16_from_planar(const float* x, int64_t n, int channels, int16_t* out, void* stream);
+
+/* One operand of the pydub mix: interleaved int16 frames as read from the WAV file. */
+typedef struct b200vc_mix_source {
+  const int16_t* x; /* DEVICE [n, channels] */
+  int64_t n;        /* frames */
+  int64_t used;     /* frames of the (rate-converted) segment that take part in the overlay */
+  int32_t channels; /* 1 or 2; mono is copied to both channels (audioop.tostereo) */
+  int32_t in_rate;  /* frame rate of the file */
+  int32_t out_rate; /* frame rate of the mix (AudioSegment._sync: the maximum); != in_rate -> audioop.ratecv */
+  int32_t pad_;
+  double gain1;     /* AudioSegment - x   -> audioop.mul(data, 2, 10 ** (-x / 20)) */
+  double gain2;     /* AudioSegment + g   -> a second audioop.mul */
+} b200vc_mix_source;
+
+/* main.combine_audio up to the encoder: out[j, c] = clip(clip(s0 + s1) + s2), s_i = ratecv(mul(mul(x_i, g1), g2)), bit-exact
+ * against CPython's audioop (what pydub 0.25.1 calls).  src3: HOST array of 3; out: DEVICE int16 [n_out, channels]. */
+int b200vc_pydub_mix(const b200vc_mix_source* src3, int16_t* out, int64_t n_out, int channels, void* stream);
 
 /* change_rms (vc_infer_pipeline.py:41-60) on the device: half-second RMS envelopes of data1 (fp64, rate sr1) and data2
  * (fp32, rate sr2; librosa.feature.rms center/reflect), linear interpolation to n2 samples, data2 *= rms1^(1-rate) *

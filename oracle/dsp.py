@@ -72,18 +72,3 @@ def resample_sinc_mono(x, n_out, rate_in, rate_out, zero_crossings=16):
         v = mono[np.clip(k, 0, n_in - 1)]
         out[m] = (np.where(ok, v * sinc * win, 0.0)).sum(1) * scale
     return out.astype(np.float32)
-
-
-def mix3(a_mono, rate_a, b, c, rate, ga, gb, gc):
-    """Checker for the device MIX STAND-IN b200vc_mix3 (gain-and-sum in place of pydub's overlay, main.py:229-233):
-    out[ch, n] = ga * lerp(a_mono, n * rate_a / rate) + gb * b[ch, n] + gc * c[ch, n]."""
-    n = b.shape[1]
-    pos = np.arange(n, dtype=np.float64) * (float(rate_a) / float(rate))
-    i0 = pos.astype(np.int64)
-    fr = (pos - i0).astype(np.float32)
-    a = np.asarray(a_mono, dtype=np.float32)
-    na = a.shape[0]
-    a0 = np.where(i0 < na, a[np.clip(i0, 0, na - 1)], 0.0)
-    a1 = a[np.clip(i0 + 1, 0, na - 1)]
-    av = np.where(i0 + 1 < na, a0 * (1.0 - fr) + a1 * fr, a0).astype(np.float32)
-    return (ga * av[None, :] + gb * b + gc * c).astype(np.float32)

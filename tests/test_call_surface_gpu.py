@@ -143,19 +143,24 @@ def test_file_level_call_surface(tmp_path, monkeypatch):
     for suffix in ("_Vocals.wav", "_Instrumental.wav", "_Vocals_Main.wav", "_Vocals_Backup.wav", "_Vocals_Main_DeReverb.wav"):
         assert any(f.endswith(suffix) for f in files), (suffix, files)             # main.py:166-190 naming
     sr_c, cover = _read(cover_path)
-    assert sr_c == 44100 and cover.ndim == 2 and cover.shape[1] == 2 and abs(cover.shape[0] - song.shape[1]) <= 2
+    assert sr_c == 44100 and cover.ndim == 2 and cover.shape[1] == 2 and abs(cover.shape[0] - song.shape[1]) <= 4410
     assert np.abs(cover.astype(np.int32)).max() > 500
-    # the cover is the gain-and-sum of the three files the pipeline kept (main.py:229-233)
-    ai = [f for f in files if "_Synth_p0_i0.5_fr3_rms0.25_pro0.33_rmvpe" in f and f.endswith("_mixed.wav")]
-    assert len(ai) == 1, files
-    from oracle import dsp as odsp
-    a = _read(os.path.join(song_dir, ai[0]))[1].astype(np.float32) / 32768.0
-    b = _read([os.path.join(song_dir, f) for f in files if f.endswith("_Vocals_Backup.wav")][0])[1].astype(np.float32).T / 32768.0
-    c = _read([os.path.join(song_dir, f) for f in files if f.endswith("_Instrumental.wav")][0])[1].astype(np.float32).T / 32768.0
-    nmix = min(b.shape[1], c.shape[1])
-    ref = odsp.mix3(a, 40000, b[:, :nmix], c[:, :nmix], 44100, bmain.db_gain(-4), bmain.db_gain(-6), bmain.db_gain(-7))
-    want = np.rint(np.clip(ref.T, -1, 1) * 32767.0).astype(np.int16)
-    assert np.abs(cover[:nmix].astype(np.int32) - want.astype(np.int32)).max() <= 1
+    # effects (main.py:206-226): the kept `_mixed.wav` is the converted vocal through high-pass, compressor and reverb
+    mixed = [f for f in files if "_Synth_p0_i0.5_fr3_rms0.25_pro0.33_rmvpe" in f and f.endswith("_mixed.wav")]
+    assert len(mixed) == 1, files
+    from oracle import effects as oeff
+    from oracle import mixdown as omix
+    sr_raw, raw = _read(os.path.join(song_dir, mixed[0].replace("_mixed.wav", ".wav")))
+    sr_a, a = _read(os.path.join(song_dir, mixed[0]))
+    want_fx, _ = oeff.add_audio_effects(raw, sr_raw, 0.15, 0.2, 0.8, 0.7)
+    assert sr_a == sr_raw == 40000 and a.shape == raw.shape
+    d = np.abs(a.astype(np.int32) - want_fx.astype(np.int32))
+    assert d.max() <= 1 and (d > 0).mean() < 0.02 and not np.array_equal(a, raw)
+    # mix (main.py:229-233): the cover is pydub's gain / overlay of the three kept files, bit for bit
+    b = _read([os.path.join(song_dir, f) for f in files if f.endswith("_Vocals_Backup.wav")][0])[1]
+    c = _read([os.path.join(song_dir, f) for f in files if f.endswith("_Instrumental.wav")][0])[1]
+    want, rate = omix.combine_audio(a, sr_a, b, 44100, c, 44100)
+    assert rate == 44100 and np.array_equal(cover, want)
     # second call reuses the cached stems and the cached conversion (main.py:271-296) and returns the same path
     assert bmain.song_cover_pipeline(song_path, "Synth", 0, False, 0, 0, 0, 0, 0.5, 3, 0.25, "rmvpe", 128, 0.33, 0, 0.15, 0.2,
                                      0.8, 0.7, "wav") == cover_path

@@ -70,8 +70,8 @@ def run(group):
     eng.vc.group = group
     ai = eng.convert(stems["dereverb"], return_device=True)
     eng.vc.group = None
-    cover = eng.mix(ai, stems["backup"], stems["instrumental"])
-    return dict(stems, converted=ai.float(), cover=cover)
+    cover = eng.mix(eng.effects(ai), stems["backup"], stems["instrumental"])
+    return dict(stems, converted=ai.float(), cover=cover.float())
 
 
 single, t1 = timed(lambda: run(None))
