@@ -10,7 +10,7 @@
 //     of D samples every y[t-D-k] is already known, and `last` forgets like damp^k: each sample evaluates the K-term Horner
 //     form of the one-pole low-pass (the same operation order as the sequential loop, started K samples earlier), one thread
 //     block per comb walks the signal in steps of D samples;
-//   * all-pass (delay D, gain 0.5): w[t] = x[t] + 0.5 w[t-D] = sum_m 0.5^m x[t-mD] — 40 terms, fully parallel;
+//   * all-pass (delay D, gain 0.5): w[t] = x[t] + 0.5 w[t-D] = sum_m 0.5^m x[t-mD] — 32 terms, fully parallel;
 //   * the mix is integer arithmetic per output sample; audioop.ratecv (linear interpolation on an integer phase accumulator)
 //     has the closed form written at src_sample() below — bit-exact against CPython's audioop (tests/test_effects_cpu.py pins
 //     the closed form, tests/test_effects_gpu.py the kernel).
@@ -51,23 +51,29 @@ struct CombDelays {
   int d[8];
 };
 
-// One thread block per comb filter; Y[j][t] = the value the comb writes into its delay line at time t.
-__global__ void __launch_bounds__(1024) fx_comb_kernel(const float* __restrict__ x, float* Y, long long n, CombDelays dl,
-                                                       float gain, float damp, float omd, float fb, int K) {
+// One thread block per comb filter; Y[j][t] = the value the comb writes into its delay line at time t.  The last R samples of
+// the delay line live in a shared-memory ring (R = power of two >= 2 D + K, zero-initialised = the empty delay line): a block of
+// D samples reads y[t-D-K+1 .. t-D] from it and writes y[t]; one barrier per block of D samples.
+__global__ void __launch_bounds__(1024) fx_comb_kernel(const float* __restrict__ x, float* __restrict__ Y, long long n,
+                                                       CombDelays dl, int ring_size, float gain, float damp, float omd, float fb,
+                                                       int K) {
+  extern __shared__ float ring[];
   const int D = dl.d[blockIdx.x];
+  const unsigned mask = (unsigned)ring_size - 1u;
   float* Yj = Y + (long long)blockIdx.x * n;
+  for (int i = threadIdx.x; i < ring_size; i += blockDim.x) ring[i] = 0.f;
+  __syncthreads();
   for (long long s = 0; s < n; s += D) {
     for (int i = threadIdx.x; i < D; i += blockDim.x) {
       const long long t = s + i;
       if (t >= n) break;
+      const float xin = __fmul_rn(x[t], gain);
       float last = 0.f;
-      const long long u0 = t - D;
-      for (int k = K - 1; k >= 0; --k) {
-        const long long u = u0 - k;
-        const float v = (u >= 0) ? Yj[u] : 0.f;
-        last = __fadd_rn(__fmul_rn(v, omd), __fmul_rn(last, damp));
-      }
-      Yj[t] = __fadd_rn(__fmul_rn(x[t], gain), __fmul_rn(last, fb));
+      const unsigned u0 = (unsigned)(t - D);               // ring index arithmetic is modulo 2^32, ring_size divides it
+      for (int k = K - 1; k >= 0; --k) last = __fadd_rn(__fmul_rn(ring[(u0 - (unsigned)k) & mask], omd), __fmul_rn(last, damp));
+      const float y = __fadd_rn(xin, __fmul_rn(last, fb));
+      ring[(unsigned)t & mask] = y;
+      Yj[t] = y;
     }
     __syncthreads();
   }
@@ -110,14 +116,21 @@ __global__ void fx_finish_kernel(const float* __restrict__ rev, const float* __r
   out16[t] = (int16_t)(i32 >> 16);
 }
 
-// planar float stems -> interleaved 16-bit PCM as soundfile / libsndfile writes them (mdx.py:283-284: lrintf(x * 0x7FFF), no
-// clipping: the conversion to short wraps)
+// planar float stems -> interleaved 16-bit PCM as soundfile writes them (mdx.py:273,280): python-soundfile turns libsndfile's
+// clipping on, which selects f2s_clip_array: scaled = x * 2^31 (float); >= 2^31 -> 0x7FFF; <= -2^31 -> -0x8000; else
+// lrintf(scaled) >> 16
 __global__ void pcm16_from_planar_kernel(const float* __restrict__ x, long long n, int channels, int16_t* __restrict__ out) {
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n * channels) return;
   const long long j = e / channels;
   const int c = (int)(e % channels);
-  out[e] = (int16_t)(int)rintf(__fmul_rn(x[(long long)c * n + j], 32767.0f));
+  const float s = __fmul_rn(x[(long long)c * n + j], 2147483648.0f);
+  int q;
+  if (s >= 2147483648.0f) q = 32767;
+  else if (s <= -2147483648.0f) q = -32768;
+  else if (s != s) q = 0;
+  else q = (int)(__float2ll_rn(s) >> 16);
+  out[e] = (int16_t)q;
 }
 
 // ---- pydub mix ----
@@ -195,18 +208,28 @@ int b200vc_fx_reverb_combs(const float* x, float* Y, float* comb_sum, int64_t n,
     B200VC_REQUIRE(delays8[j] > 0, "fx_reverb_combs: comb delay %d is not positive", j);
     dl.d[j] = delays8[j];
   }
+  int dmax = 0;
+  for (int j = 0; j < 8; ++j) dmax = dl.d[j] > dmax ? dl.d[j] : dmax;
+  B200VC_REQUIRE(terms <= 256, "fx_reverb_combs: %d low-pass terms (damping too close to 1)", terms);
+  int ring = 1024;
+  while (ring < 2 * dmax + terms) ring *= 2;
+  B200VC_REQUIRE(ring * sizeof(float) <= 200 * 1024, "fx_reverb_combs: delay lines of %d samples do not fit shared memory", dmax);
+  const size_t smem = ring * sizeof(float);
+  if (smem > 48 * 1024)
+    B200VC_CHECK_CUDA(cudaFuncSetAttribute(fx_comb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  auto launch = [=](cudaStream_t st) {
+    fx_comb_kernel<<<8, 1024, smem, st>>>(x, Y, n, dl, ring, gain, damp, 1.0f - damp, feedback, terms);
+    fx_comb_sum_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(Y, n, dl, comb_sum);
+    count_launch(2);
+  };
   if (plan_recording()) {
     plan_push([=](void* s) -> int {
-      fx_comb_kernel<<<8, 1024, 0, (cudaStream_t)s>>>(x, Y, n, dl, gain, damp, 1.0f - damp, feedback, terms);
-      fx_comb_sum_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)s>>>(Y, n, dl, comb_sum);
-      count_launch(2);
+      launch((cudaStream_t)s);
       return cudaGetLastError() == cudaSuccess ? kOk : kErrCuda;
     });
     return kOk;
   }
-  fx_comb_kernel<<<8, 1024, 0, (cudaStream_t)stream>>>(x, Y, n, dl, gain, damp, 1.0f - damp, feedback, terms);
-  fx_comb_sum_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(Y, n, dl, comb_sum);
-  count_launch(2);
+  launch((cudaStream_t)stream);
   B200VC_LAUNCH_CHECK();
   return kOk;
 }

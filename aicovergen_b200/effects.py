@@ -21,7 +21,7 @@ _P, _i64, _i32, _f32 = C.c_void_p, C.c_int64, C.c_int, C.c_float
 
 COMB_TUNINGS = (1116, 1188, 1277, 1356, 1422, 1491, 1557, 1617)        # juce::Reverb, at 44.1 kHz
 ALLPASS_TUNINGS = (556, 441, 341, 225)
-ALLPASS_TERMS = 40                                                      # 0.5 ** 40 ~ 1e-12
+ALLPASS_TERMS = 32                                                      # 0.5 ** 32 ~ 2e-10 of full scale
 
 
 class MixSource(C.Structure):
@@ -86,7 +86,7 @@ def effect_constants(sample_rate: int, room_size: float, wet_level: float, dry_l
     warm = 0 if decay <= 0.0 else int(math.ceil(math.log(1.0e-10) / math.log(decay))) if decay < 1.0 else 1 << 62
     warm = min(((warm + 1023) // 1024) * 1024, 1 << 30)
     d = float(damp)
-    comb_terms = 1 if d <= 0.0 else max(4, min(4096, int(math.ceil(-30.0 * math.log(2.0) / math.log(d))))) if d < 1.0 else 4096
+    comb_terms = 1 if d <= 0.0 else max(4, min(256, int(math.ceil(-30.0 * math.log(2.0) / math.log(d))))) if d < 1.0 else 256
     return EffectConstants(float(b0), float(b1), float(a1), float(cte_at), float(cte_rl), float(thr), float(thr_inv), float(expo),
                            tuple((sr * t) // 44100 for t in COMB_TUNINGS), tuple((sr * t) // 44100 for t in ALLPASS_TUNINGS),
                            0.015, float(damp), float(feedback), float(wet1), float(dry), comb_terms, warm)

@@ -134,10 +134,19 @@ class CoverEngine:
         return self.mix(ai, stems["backup"], stems["instrumental"], main_gain, backup_gain, inst_gain)
 
     @_ffi.on_device
-    def cover(self, song: np.ndarray, **kw) -> np.ndarray:
-        """Host array [2, N] float32 in, the cover's int16 frames [n, 2] out (H2D of the song and D2H of the cover included)."""
+    def cover(self, song: np.ndarray, out: Optional[torch.Tensor] = None, **kw) -> np.ndarray:
+        """Host array [2, N] float32 in, the cover's int16 frames [n, 2] out (H2D of the song and D2H of the cover included).
+        `out`: optional host int16 tensor [>= n, 2] to receive the frames (pinned memory makes the D2H a single DMA); the
+        returned array is then a view of its first n rows."""
         dev = torch.from_numpy(np.ascontiguousarray(song, dtype=np.float32)).to(self.device, non_blocking=True)
-        return self.cover_device(dev, **kw).cpu().numpy()
+        res = self.cover_device(dev, **kw)
+        if out is None:
+            return res.cpu().numpy()
+        if out.dtype != torch.int16 or out.dim() != 2 or out.shape[1] != res.shape[1] or out.shape[0] < res.shape[0] or out.is_cuda:
+            raise ValueError(f"cover: `out` must be a host int16 tensor [>= {res.shape[0]}, {res.shape[1]}]")
+        view = out[:res.shape[0]]
+        view.copy_(res)
+        return view.numpy()
 
 
 # ---------------------------------------------------------------------------------------------------------------

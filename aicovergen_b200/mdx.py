@@ -542,13 +542,20 @@ def _read_wav_44k(filename):
     return np.ascontiguousarray(data.T), 44100
 
 
-def _write_wav_pcm16(path, data_T, sr):
-    """soundfile.write(path, data, sr) (mdx.py:273,280): default subtype for .wav is PCM_16, and libsndfile converts float
-    data with lrintf(x * 0x7FFF) WITHOUT clipping (SFC_SET_CLIPPING is off by default): samples beyond +-1 wrap.  The same
-    conversion runs on the device for stems that stay in HBM (b200vc_pcm16_from_planar)."""
+def pcm16_soundfile(x: np.ndarray) -> np.ndarray:
+    """float -> PCM_16 as `soundfile.write` does it (mdx.py:273,280: default subtype of .wav).  python-soundfile switches
+    libsndfile's clipping ON for every file (SFC_SET_CLIPPING), which selects f2s_clip_array: scaled = x * 2^31 in float,
+    >= 2^31 -> 0x7FFF, <= -2^31 -> -0x8000, else lrintf(scaled) >> 16 — i.e. floor(x * 32768) with saturation, not
+    round(x * 32767).  The same conversion runs on the device for stems that stay in HBM (b200vc_pcm16_from_planar)."""
+    s = np.asarray(x, dtype=np.float32) * np.float32(2147483648.0)
     with np.errstate(invalid="ignore"):
-        q = np.rint(np.asarray(data_T, dtype=np.float32) * np.float32(32767.0)).astype(np.int64).astype(np.int16)
-    wavfile.write(path, sr, q)
+        q = (np.rint(s).astype(np.int64) >> 16)
+    q = np.where(s >= np.float32(2147483648.0), 32767, np.where(s <= np.float32(-2147483648.0), -32768, q))
+    return np.where(np.isnan(s), 0, q).astype(np.int16)
+
+
+def _write_wav_pcm16(path, data_T, sr):
+    wavfile.write(path, sr, pcm16_soundfile(data_T))
 
 
 def run_mdx_device(mdx_sess: MDX, wave_dev: torch.Tensor, denoise=False, m_threads=2, group=None):

@@ -210,8 +210,10 @@ class RMVPEB200:
         return pl.f0
 
     @_ffi.on_device
-    def infer_from_audio(self, audio: np.ndarray, thred: float = 0.03) -> np.ndarray:
-        """Reference signature (rmvpe.py:366-383): np.ndarray[N] -> np.ndarray[1 + N//160] (float64 Hz, 0 = unvoiced)."""
+    def infer_from_audio_begin(self, audio, thred: float = 0.03):
+        """First half of infer_from_audio: enqueue the network, the decode and the D2H of the cents track (into pinned memory)
+        on the CURRENT stream and return a handle without waiting — a caller that runs this on a side stream overlaps the F0
+        estimate (whose BiGRU occupies 16 SMs for tens of ms) with other work."""
         if isinstance(audio, torch.Tensor):
             a = audio.detach().to(self.device).float().contiguous()      # extension: device tensor in, no H2D
         else:
@@ -219,11 +221,25 @@ class RMVPEB200:
         pl = self._plan(int(a.numel()))
         pl.run(a)
         ops.rmvpe_decode(pl.sal, pl.f0, pl.n_frames, thred, cents=pl.cents)
-        cents_pred = pl.cents.cpu().numpy()
+        if getattr(pl, "cents_host", None) is None:
+            pl.cents_host = torch.empty(pl.cents.shape, dtype=pl.cents.dtype).pin_memory()
+        pl.cents_host.copy_(pl.cents, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record()
+        return pl, done, a
+
+    def infer_from_audio_end(self, handle) -> np.ndarray:
+        pl, done, _ = handle
+        done.synchronize()
+        cents_pred = pl.cents_host.numpy().copy()
         # the reference's own last two numpy lines (rmvpe.py:361-362), on the host so f0 is bit-identical
         f0 = 10 * (2 ** (cents_pred / 1200))
         f0[f0 == 10] = 0
         return f0
+
+    def infer_from_audio(self, audio: np.ndarray, thred: float = 0.03) -> np.ndarray:
+        """Reference signature (rmvpe.py:366-383): np.ndarray[N] -> np.ndarray[1 + N//160] (float64 Hz, 0 = unvoiced)."""
+        return self.infer_from_audio_end(self.infer_from_audio_begin(audio, thred))
 
 
 class _RmvpePlan:

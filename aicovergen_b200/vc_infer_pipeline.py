@@ -25,6 +25,10 @@ from scipy import signal
 from . import _ffi, ops
 from .index import IvfIndexB200, read_index
 
+# rmvpe F0 of the whole utterance on a side stream, overlapped with the HuBERT / index half of the segments (the synthesizer
+# half needs the F0).  B200VC_F0_OVERLAP=0: the reference's order (F0 first, then the segments one after the other).
+F0_OVERLAP = os.environ.get("B200VC_F0_OVERLAP", "0") == "1"
+
 # 5th-order Butterworth high-pass at 48 Hz for 16 kHz input (vc_infer_pipeline.py:22)
 bh, ah = signal.butter(N=5, Wn=48, btype="high", fs=16000)
 
@@ -110,6 +114,13 @@ class VC(object):
             raise NotImplementedError(
                 f"f0_method={f0_method!r}: 'rmvpe' and 'mangio-crepe' run on the B200 path (pm / harvest / dio / pyin are CPU "
                 "libraries outside the hot path; crepe-tiny and the hybrid methods are not built)")
+        return self._coarse_from_f0(f0, f0_up_key, inp_f0)
+
+    def _coarse_from_f0(self, f0, f0_up_key, inp_f0=None):
+        """Transposition, optional f0-file override and the mel quantisation to 1..255 (vc_infer_pipeline.py:322-370), host numpy."""
+        f0_min, f0_max = 50, 1100
+        f0_mel_min = 1127 * np.log(1 + f0_min / 700)
+        f0_mel_max = 1127 * np.log(1 + f0_max / 700)
         f0 *= pow(2, f0_up_key / 12)
         tf0 = self.sr // self.window
         if inp_f0 is not None:
@@ -129,6 +140,14 @@ class VC(object):
     def vc(self, model, net_g, sid, audio0, pitch, pitchf, times, index, big_npy, index_rate, version, protect):
         """Returns the converted segment as a float32 DEVICE tensor (the reference returns numpy; pipeline()
         keeps segments in HBM until the final concat)."""
+        has_f0 = pitch is not None and pitchf is not None
+        half = self._vc_features(model, audio0, times, index, big_npy, index_rate, version, protect < 0.5 and has_f0)
+        return self._vc_synth(net_g, sid, half, pitch, pitchf, times, protect)
+
+    def _vc_features(self, model, audio0, times, index, big_npy, index_rate, version, keep_raw, own=False):
+        """First half of VC.vc (vc_infer_pipeline.py:385-431): HuBERT features (+ final_proj for v1) and the index blend;
+        nothing here needs the F0.  own=True: the returned tensors do not alias per-shape plan buffers (the caller keeps the
+        halves of several segments alive at once)."""
         dev = self.device
         feats = torch.from_numpy(np.ascontiguousarray(audio0)).float() if isinstance(audio0, np.ndarray) else audio0.float()
         if feats.dim() == 2:
@@ -141,11 +160,20 @@ class VC(object):
         logits = model.extract_features(source=feats, padding_mask=padding_mask, output_layer=9 if version == "v1" else 12)
         feats = model.final_proj(logits[0]) if version == "v1" else logits[0]
         f2d = feats[0]                                             # [T, C]
-        has_f0 = pitch is not None and pitchf is not None
-        do_protect = protect < 0.5 and has_f0
-        feats0 = f2d.clone() if do_protect else None
+        feats0 = f2d.clone() if keep_raw else None
         if index is not None and big_npy is not None and index_rate != 0:
             f2d = index.search_blend(f2d, index_rate)
+        if own:
+            f2d = f2d.clone()
+        times[0] += ttime() - t0
+        return f2d, feats0, n_in
+
+    def _vc_synth(self, net_g, sid, half, pitch, pitchf, times, protect):
+        """Second half of VC.vc (vc_infer_pipeline.py:432-470): 2x feature upsampling with the protect blend, synthesizer."""
+        dev = self.device
+        f2d, feats0, n_in = half
+        has_f0 = pitch is not None and pitchf is not None
+        do_protect = protect < 0.5 and has_f0
         t1 = ttime()
         p_len = n_in // self.window
         if 2 * f2d.shape[0] < p_len:
@@ -162,9 +190,7 @@ class VC(object):
             audio1 = net_g.infer(up.unsqueeze(0), p_len_t, pitch, pitchf, sid, noise_z=nz, noise_src=ns)[0][0, 0]
         else:
             audio1 = net_g.infer(up.unsqueeze(0), p_len_t, sid, noise_z=nz)[0][0, 0]
-        t2 = ttime()
-        times[0] += t1 - t0
-        times[2] += t2 - t1
+        times[2] += ttime() - t1
         return audio1
 
     # ------------------------------------------------------------------ segment sharding (extension)
@@ -267,10 +293,40 @@ class VC(object):
         if self.group is not None:
             import torch.distributed as dist
             world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        # the padded utterance goes to HBM once; segments are device slices of it
+        pad_dev = audio_pad.float()
+        w = self.window
+        # segment list exactly as the reference walks it (:548-603): (sample range of the padded utterance, F0 frame range)
+        segs = []
+        for t in opt_ts:
+            t = t // w * w
+            segs.append((s, t + self.t_pad2 + w, s // w, (t + self.t_pad2) // w))
+            s = t
+        segs.append((t if t is not None else 0, None, t // w if t is not None else 0, None))
+        mine = [i for i in range(len(segs)) if i % world == rank]      # the others: another rank of the group converts them
+        overlap = (F0_OVERLAP and if_f0 == 1 and f0_method == "rmvpe" and hasattr(getattr(self, "model_rmvpe", None), "infer_from_audio_begin"))
+        halves = {}
+        pending = None
+        if overlap:
+            # F0 (rank 0) goes to a side stream; meanwhile the main stream runs the F0-independent half of every segment
+            main = torch.cuda.current_stream()
+            if rank == 0:
+                if getattr(self, "_f0_stream", None) is None:
+                    self._f0_stream = torch.cuda.Stream(device=self.device)
+                self._f0_stream.wait_stream(main)
+                with torch.cuda.stream(self._f0_stream):
+                    pending = self.model_rmvpe.infer_from_audio_begin(audio_pad, thred=0.03)
+            for i in mine:
+                a0, a1, _, _ = segs[i]
+                halves[i] = self._vc_features(model, pad_dev[a0:a1], times, index, big_npy, index_rate, version, protect < 0.5, own=True)
         if if_f0 == 1:
             if rank == 0:       # the F0 is one whole-utterance estimate (bidirectional GRU): group rank 0 computes it ...
-                pitch, pitchf = self.get_f0(input_audio_path, audio_pad, p_len, f0_up_key, f0_method, filter_radius,
-                                            crepe_hop_length, inp_f0)
+                if pending is not None:
+                    pitch, pitchf = self._coarse_from_f0(self.model_rmvpe.infer_from_audio_end(pending), f0_up_key, inp_f0)
+                    torch.cuda.current_stream().wait_stream(self._f0_stream)     # plan buffers of the F0 net are free again
+                else:
+                    pitch, pitchf = self.get_f0(input_audio_path, audio_pad, p_len, f0_up_key, f0_method, filter_radius,
+                                                crepe_hop_length, inp_f0)
                 pitch = torch.tensor(pitch[:p_len], device=self.device).unsqueeze(0).long()
                 pitchf = torch.tensor(pitchf[:p_len], device=self.device).unsqueeze(0).float()
             else:
@@ -282,28 +338,18 @@ class VC(object):
                 dist.broadcast(pitchf, src=src, group=self.group)
         t2 = ttime()
         times[1] += t2 - t1
-        # the padded utterance goes to HBM once; segments are device slices of it
-        pad_dev = audio_pad.float()
-        w = self.window
-        # segment list exactly as the reference walks it (:548-603): (sample range of the padded utterance, F0 frame range)
-        segs = []
-        for t in opt_ts:
-            t = t // w * w
-            segs.append((s, t + self.t_pad2 + w, s // w, (t + self.t_pad2) // w))
-            s = t
-        segs.append((t if t is not None else 0, None, t // w if t is not None else 0, None))
         audio_opt = [None] * len(segs)
         for i, (a0, a1, p0, p1) in enumerate(segs):
             seg = pad_dev[a0:a1]
-            if i % world != rank:          # another rank of the group converts this segment (independent after the global F0)
+            if i % world != rank:
                 if self._noise_gen is not None:
                     self._draw_noise(net_g, self._segment_frames(seg.shape[0]), upload=False)
                 continue
-            if if_f0 == 1:
-                out = self.vc(model, net_g, sid, seg, pitch[:, p0:p1], pitchf[:, p0:p1], times, index, big_npy, index_rate,
-                              version, protect)
+            pi, pfi = (pitch[:, p0:p1], pitchf[:, p0:p1]) if if_f0 == 1 else (None, None)
+            if i in halves:
+                out = self._vc_synth(net_g, sid, halves.pop(i), pi, pfi, times, protect)
             else:
-                out = self.vc(model, net_g, sid, seg, None, None, times, index, big_npy, index_rate, version, protect)
+                out = self.vc(model, net_g, sid, seg, pi, pfi, times, index, big_npy, index_rate, version, protect)
             audio_opt[i] = out[self.t_pad_tgt: -self.t_pad_tgt].clone()
         if world > 1:
             self._gather_segments(audio_opt, [pad_dev[a0:a1].shape[0] for (a0, a1, _, _) in segs], net_g, world, rank)

@@ -358,7 +358,7 @@ int b200vc_fx_finish(const float* reverb, const float* x, int16_t* out16, float*
                      void* stream);
 
 /* x [channels, n] float (a stem in HBM) -> out [n, channels] int16 as soundfile writes a float array to a PCM_16 WAV
- * (mdx.py:283-284; libsndfile: lrintf(x * 0x7FFF), the conversion to short wraps). */
+ * (mdx.py:273,280; libsndfile with clipping on: lrintf(x * 2^31) >> 16, saturated). */
 int b200vc_pcm16_from_planar(const float* x, int64_t n, int channels, int16_t* out, void* stream);
 
 /* One operand of the pydub mix: interleaved int16 frames as read from the WAV file. */

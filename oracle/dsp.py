@@ -72,3 +72,19 @@ def resample_sinc_mono(x, n_out, rate_in, rate_out, zero_crossings=16):
         v = mono[np.clip(k, 0, n_in - 1)]
         out[m] = (np.where(ok, v * sinc * win, 0.0)).sum(1) * scale
     return out.astype(np.float32)
+
+
+def pcm16_soundfile(x: np.ndarray) -> np.ndarray:
+    """`soundfile.write(path, float_array, sr)` to a .wav (default subtype PCM_16; mdx.py:273,280): python-soundfile enables
+    libsndfile's clipping for every file it opens (`sf_command(SFC_SET_CLIPPING, SF_TRUE)`), so floats are converted by
+    pcm.c f2s_clip_array: scaled = x * (8.0 * 0x10000000) in float; >= 0x7FFFFFFF -> 0x7FFF; <= -8.0 * 0x10000000 -> 0x8000;
+    else lrintf(scaled) >> 16.  soundfile / libsndfile are absent from /root/reference and from this image: restated from
+    their published sources, PARITY UNPINNED."""
+    s = np.asarray(x, dtype=np.float32) * np.float32(8.0 * 0x10000000)
+    out = np.empty(s.shape, dtype=np.int16)
+    flat, o = s.reshape(-1), out.reshape(-1)
+    hi, lo = flat >= np.float32(1.0 * 0x7FFFFFFF), flat <= np.float32(-8.0 * 0x10000000)
+    mid = ~(hi | lo)
+    o[hi], o[lo] = 0x7FFF, -0x8000
+    o[mid] = (np.rint(flat[mid]).astype(np.int64) >> 16).astype(np.int16)
+    return out

@@ -56,7 +56,7 @@ def combs(x, k):
     return total
 
 
-def allpass(x, D, M=40):
+def allpass(x, D, M=32):
     n = x.size
     pad = np.concatenate([np.zeros((M + 1) * D, f32), x])
     off = (M + 1) * D

@@ -226,7 +226,7 @@ def test_cover_engine_stage_handoffs_30s():
     print(f"[cover 30 s] effects       int16 differences: max {dfx.max()} LSB on {float((dfx > 0).mean()):.4f} of the samples")
     assert dfx.max() <= 1 and (dfx > 0).mean() < 0.02
     cover = eng.mix(fx16, torch.from_numpy(stems["backup"]).cuda(), torch.from_numpy(stems["instrumental"]).cuda()).cpu().numpy()
-    pcm = lambda x: np.rint(x * np.float32(32767.0)).astype(np.int16).T
+    pcm = lambda x: odsp.pcm16_soundfile(x).T
     ref_mix, rate = omix.combine_audio(fx16, 40000, pcm(stems["backup"]), 44100, pcm(stems["instrumental"]), 44100)
     print(f"[cover 30 s] mix           {cover.shape[0]} frames @ {eng.cover_rate}; bit-exact {np.array_equal(cover, ref_mix)}")
     assert rate == eng.cover_rate == 44100 and np.array_equal(cover, ref_mix)

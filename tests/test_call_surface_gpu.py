@@ -77,6 +77,7 @@ def _read(path):
 
 
 def test_file_level_call_surface(tmp_path, monkeypatch):
+    from oracle import dsp as odsp
     from aicovergen_b200 import main as bmain
     from aicovergen_b200 import mdx as bmdx
     from aicovergen_b200 import rvc as brvc
@@ -102,7 +103,7 @@ def test_file_level_call_surface(tmp_path, monkeypatch):
     assert np.isfinite(main_a).all() and np.isfinite(inv_a).all() and np.abs(main_a).max() > 1e-3
     for path, arr in ((voc_path, main_a), (inst_path, inv_a)):
         sr_f, d = _read(path)
-        want = np.rint(np.clip(arr.T, -1, 1) * 32767.0).astype(np.int16)
+        want = odsp.pcm16_soundfile(arr.T)
         assert sr_f == 44100 and d.shape == want.shape
         assert np.array_equal(d, want), path
     with pytest.raises(KeyError):                                    # unknown hash: the reference dies on model_params.get -> None

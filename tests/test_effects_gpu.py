@@ -68,9 +68,9 @@ def test_pydub_mix_full_size_and_refusals():
 
 
 def test_pcm16_from_planar():
+    from oracle import dsp as odsp
     rng = np.random.default_rng(3)
-    x = rng.uniform(-1.2, 1.2, (2, 100_003)).astype(np.float32)                # beyond +-1: libsndfile's conversion wraps
-    x[0, :5] = [0.5 / 32767, 1.5 / 32767, 2.5 / 32767, -0.5 / 32767, 1.0]       # ties round to even
+    x = rng.uniform(-1.2, 1.2, (2, 100_003)).astype(np.float32)                # beyond +-1: saturates
+    x[0, :8] = [0.5 / 32768, 0.99999 / 32768, 1.0 / 32768, -0.5 / 32768, 1.0, -1.0, 0.99999994, 65535.7 / 2 ** 31]
     got = fx.pcm16_from_planar(torch.from_numpy(x).cuda()).cpu().numpy()
-    want = np.rint(x * np.float32(32767.0)).astype(np.int64).astype(np.int16).T
-    assert np.array_equal(got, want)
+    assert np.array_equal(got, odsp.pcm16_soundfile(x).T)
