@@ -24,26 +24,56 @@ namespace b200vc {
 namespace {
 
 // ---- int16 -> float (JUCE reader: sample * 2^-15), first-order high-pass (TDF-II), peak ballistics filter, VCA gain ----
-__global__ void fx_hpf_comp_kernel(const int16_t* __restrict__ x, float* __restrict__ y, long long n, int chunk, int warm,
-                                   float b0, float b1, float a1, float cte_at, float cte_rl, float thr, float thr_inv,
-                                   float expo) {
-  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long lo = c * chunk;
-  if (lo >= n) return;
-  const long long hi = (lo + chunk < n) ? lo + chunk : n;
-  float lv1 = 0.f, yold = 0.f;
-  for (long long t = (lo > warm) ? lo - warm : 0; t < hi; ++t) {
-    const float in = (float)x[t] * (1.0f / 32768.0f);
+struct HpfComp {
+  float b0, b1, a1, cte_at, cte_rl, thr, thr_inv, expo;
+  float lv1, yold;
+  __device__ __forceinline__ float step(float in, bool emit, float& out_gain) {
     const float out = __fadd_rn(__fmul_rn(in, b0), lv1);
     lv1 = __fsub_rn(__fmul_rn(in, b1), __fmul_rn(out, a1));
     const float a = fabsf(out);
     const float cte = (a > yold) ? cte_at : cte_rl;
     const float env = __fadd_rn(a, __fmul_rn(cte, __fsub_rn(yold, a)));
     yold = env;
-    if (t >= lo) {
-      const float g = (env < thr) ? 1.0f : powf(__fmul_rn(env, thr_inv), expo);
-      y[t] = __fmul_rn(g, out);
+    if (emit) out_gain = (env < thr) ? 1.0f : powf(__fmul_rn(env, thr_inv), expo);
+    return out;
+  }
+};
+
+// One thread per chunk.  chunk and warm are multiples of 8 and x / y are 16-byte aligned, so a thread walks its stream in groups
+// of 8 samples: one 128-bit load (issued one group ahead of its use), two 128-bit stores.
+__global__ void fx_hpf_comp_kernel(const int16_t* __restrict__ x, float* __restrict__ y, long long n, int chunk, int warm,
+                                   HpfComp f) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long lo = c * chunk;
+  if (lo >= n) return;
+  const long long hi = (lo + chunk < n) ? lo + chunk : n;
+  long long t = (lo > warm) ? lo - warm : 0;
+  f.lv1 = 0.f;
+  f.yold = 0.f;
+  const float sc = 1.0f / 32768.0f;
+  float g = 1.f;
+  uint4 nxt = make_uint4(0, 0, 0, 0);
+  if (t + 8 <= hi) nxt = *reinterpret_cast<const uint4*>(x + t);
+  for (; t + 8 <= hi; t += 8) {
+    const uint4 cur = nxt;
+    if (t + 16 <= hi) nxt = *reinterpret_cast<const uint4*>(x + t + 8);
+    const uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
+    float o[8];
+    const bool emit = t >= lo;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int16_t sv = (int16_t)((i & 1) ? (w[i >> 1] >> 16) : (w[i >> 1] & 0xffffu));
+      const float out = f.step((float)sv * sc, emit, g);
+      o[i] = __fmul_rn(g, out);
     }
+    if (emit) {
+      *reinterpret_cast<float4*>(y + t) = make_float4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<float4*>(y + t + 4) = make_float4(o[4], o[5], o[6], o[7]);
+    }
+  }
+  for (; t < hi; ++t) {                                     // tail of the last chunk
+    const float out = f.step((float)x[t] * sc, t >= lo, g);
+    if (t >= lo) y[t] = __fmul_rn(g, out);
   }
 }
 
@@ -63,11 +93,22 @@ __global__ void __launch_bounds__(1024) fx_comb_kernel(const float* __restrict__
   float* Yj = Y + (long long)blockIdx.x * n;
   for (int i = threadIdx.x; i < ring_size; i += blockDim.x) ring[i] = 0.f;
   __syncthreads();
+  // each thread owns the samples i = threadIdx.x and threadIdx.x + 1024 of every block of D (D <= 2048); their inputs are
+  // loaded one block ahead so that the global-memory latency is off the block-to-block critical path
+  const int i0 = threadIdx.x, i1 = threadIdx.x + 1024;
+  float xa = (i0 < D && i0 < n) ? x[i0] : 0.f;
+  float xb = (i1 < D && i1 < n) ? x[i1] : 0.f;
   for (long long s = 0; s < n; s += D) {
-    for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    const float ca = xa, cb = xb;
+    const long long na = s + D + i0, nb = s + D + i1;
+    xa = (i0 < D && na < n) ? x[na] : 0.f;
+    xb = (i1 < D && nb < n) ? x[nb] : 0.f;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int i = h ? i1 : i0;
       const long long t = s + i;
-      if (t >= n) break;
-      const float xin = __fmul_rn(x[t], gain);
+      if (i >= D || t >= n) continue;
+      const float xin = __fmul_rn(h ? cb : ca, gain);
       float last = 0.f;
       const unsigned u0 = (unsigned)(t - D);               // ring index arithmetic is modulo 2^32, ring_size divides it
       for (int k = K - 1; k >= 0; --k) last = __fadd_rn(__fmul_rn(ring[(u0 - (unsigned)k) & mask], omd), __fmul_rn(last, damp));
@@ -192,9 +233,12 @@ int b200vc_fx_hpf_comp(const int16_t* x, float* y, int64_t n, int chunk, int war
                        float cte_rl, float thr, float thr_inv, float expo, void* stream) {
   B200VC_RECORD(b200vc_fx_hpf_comp(x, y, n, chunk, warm, b0, b1, a1, cte_at, cte_rl, thr, thr_inv, expo, stream));
   B200VC_REQUIRE(x && y && n > 0 && chunk > 0 && warm >= 0, "fx_hpf_comp: bad args");
+  B200VC_REQUIRE(chunk % 8 == 0 && warm % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(y) & 15) == 0,
+                 "fx_hpf_comp: chunk / warm must be multiples of 8 and x / y 16-byte aligned");
   const long long chunks = (n + chunk - 1) / chunk;
-  fx_hpf_comp_kernel<<<(unsigned)((chunks + 31) / 32), 32, 0, (cudaStream_t)stream>>>(x, y, n, chunk, warm, b0, b1, a1, cte_at,
-                                                                                    cte_rl, thr, thr_inv, expo);
+  HpfComp f{b0, b1, a1, cte_at, cte_rl, thr, thr_inv, expo, 0.f, 0.f};
+  fx_hpf_comp_kernel<<<(unsigned)((chunks + 31) / 32), 32, 0, (cudaStream_t)stream>>>(x, y, n, chunk, warm, f);
   count_launch();
   B200VC_LAUNCH_CHECK();
   return kOk;
@@ -210,6 +254,7 @@ int b200vc_fx_reverb_combs(const float* x, float* Y, float* comb_sum, int64_t n,
   }
   int dmax = 0;
   for (int j = 0; j < 8; ++j) dmax = dl.d[j] > dmax ? dl.d[j] : dmax;
+  B200VC_REQUIRE(dmax <= 2048, "fx_reverb_combs: comb delay %d > 2048 samples (sample rate above 55 kHz)", dmax);
   B200VC_REQUIRE(terms <= 256, "fx_reverb_combs: %d low-pass terms (damping too close to 1)", terms);
   int ring = 1024;
   while (ring < 2 * dmax + terms) ring *= 2;

@@ -114,7 +114,7 @@ def _effects_on_current_device(x, n, k, return_float):
     dev = x.device
     lib, s = _ffi.lib(), _stream()
     comp = torch.empty(n, device=dev)
-    warm = min(k.warm, n)
+    warm = min(k.warm, ((n + 7) // 8) * 8)               # both multiples of 8: the kernel walks 8-sample groups
     chunk = max(4096, warm)
     _ffi.check(lib.b200vc_fx_hpf_comp(x.data_ptr(), comp.data_ptr(), n, chunk, warm, k.b0, k.b1, k.a1, k.cte_at, k.cte_rl, k.thr,
                                       k.thr_inv, k.expo, s), "fx_hpf_comp")

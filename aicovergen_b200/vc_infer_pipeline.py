@@ -27,7 +27,7 @@ from .index import IvfIndexB200, read_index
 
 # rmvpe F0 of the whole utterance on a side stream, overlapped with the HuBERT / index half of the segments (the synthesizer
 # half needs the F0).  B200VC_F0_OVERLAP=0: the reference's order (F0 first, then the segments one after the other).
-F0_OVERLAP = os.environ.get("B200VC_F0_OVERLAP", "0") == "1"
+F0_OVERLAP = os.environ.get("B200VC_F0_OVERLAP", "1") == "1"
 
 # 5th-order Butterworth high-pass at 48 Hz for 16 kHz input (vc_infer_pipeline.py:22)
 bh, ah = signal.butter(N=5, Wn=48, btype="high", fs=16000)
