@@ -5,11 +5,12 @@
 // 8 combs + 4 all-passes); pydub's sample arithmetic is CPython's audioop (mul, ratecv, tostereo, add).  All of it is
 // sequential recursive code on the CPU; here each recursion is restructured so that a GPU can run it:
 //   * high-pass + envelope follower: both forget their state geometrically -> the signal is cut into chunks, each chunk is
-//     recomputed from `warm` samples earlier with zero state (error < 1e-10 of full scale) by its own thread;
+//     recomputed from `warm` samples earlier with zero state (error < 1e-10 of full scale) by its own thread; the compressor
+//     gain (a pow per sample) is an element-wise pass over the stored envelope;
 //   * comb filter j (delay D_j): y[t] = g x[t] + fb * last[t], last[t] = (1-damp) y[t-D] + damp last[t-1].  Inside one block
-//     of D samples every y[t-D-k] is already known, and `last` forgets like damp^k: each sample evaluates the K-term Horner
-//     form of the one-pole low-pass (the same operation order as the sequential loop, started K samples earlier), one thread
-//     block per comb walks the signal in steps of D samples;
+//     of D samples every y[t-D-k] is already known, and `last` forgets like damp^k: each run of 8 consecutive samples starts
+//     `last` with the K-term Horner form of the one-pole low-pass (the same operation order as the sequential loop, started
+//     K samples earlier) and then advances it sequentially; one thread block per comb walks the signal in steps of D samples;
 //   * all-pass (delay D, gain 0.5): w[t] = x[t] + 0.5 w[t-D] = sum_m 0.5^m x[t-mD] — 32 terms, fully parallel;
 //   * the mix is integer arithmetic per output sample; audioop.ratecv (linear interpolation on an integer phase accumulator)
 //     has the closed form written at src_sample() below — bit-exact against CPython's audioop (tests/test_effects_cpu.py pins
@@ -23,26 +24,27 @@
 namespace b200vc {
 namespace {
 
-// ---- int16 -> float (JUCE reader: sample * 2^-15), first-order high-pass (TDF-II), peak ballistics filter, VCA gain ----
-struct HpfComp {
-  float b0, b1, a1, cte_at, cte_rl, thr, thr_inv, expo;
+// ---- int16 -> float (JUCE reader: sample * 2^-15), first-order high-pass (TDF-II), peak ballistics filter ----
+struct HpfEnv {
+  float b0, b1, a1, cte_at, cte_rl;
   float lv1, yold;
-  __device__ __forceinline__ float step(float in, bool emit, float& out_gain) {
+  __device__ __forceinline__ float step(float in, float& env_out) {
     const float out = __fadd_rn(__fmul_rn(in, b0), lv1);
     lv1 = __fsub_rn(__fmul_rn(in, b1), __fmul_rn(out, a1));
     const float a = fabsf(out);
     const float cte = (a > yold) ? cte_at : cte_rl;
     const float env = __fadd_rn(a, __fmul_rn(cte, __fsub_rn(yold, a)));
     yold = env;
-    if (emit) out_gain = (env < thr) ? 1.0f : powf(__fmul_rn(env, thr_inv), expo);
+    env_out = env;
     return out;
   }
 };
 
-// One thread per chunk.  chunk and warm are multiples of 8 and x / y are 16-byte aligned, so a thread walks its stream in groups
-// of 8 samples: one 128-bit load (issued one group ahead of its use), two 128-bit stores.
-__global__ void fx_hpf_comp_kernel(const int16_t* __restrict__ x, float* __restrict__ y, long long n, int chunk, int warm,
-                                   HpfComp f) {
+// One thread per chunk (the two recurrences only: ~25 dependent cycles per sample).  chunk and warm are multiples of 8 and
+// x / y / env are 16-byte aligned, so a thread walks its stream in groups of 8 samples: one 128-bit load (issued one group ahead
+// of its use), 128-bit stores.  y = high-pass output, env = envelope; the VCA gain is applied by fx_gain_kernel.
+__global__ void fx_hpf_env_kernel(const int16_t* __restrict__ x, float* __restrict__ y, float* __restrict__ envo, long long n,
+                                  int chunk, int warm, HpfEnv f) {
   const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long lo = c * chunk;
   if (lo >= n) return;
@@ -51,30 +53,43 @@ __global__ void fx_hpf_comp_kernel(const int16_t* __restrict__ x, float* __restr
   f.lv1 = 0.f;
   f.yold = 0.f;
   const float sc = 1.0f / 32768.0f;
-  float g = 1.f;
   uint4 nxt = make_uint4(0, 0, 0, 0);
   if (t + 8 <= hi) nxt = *reinterpret_cast<const uint4*>(x + t);
   for (; t + 8 <= hi; t += 8) {
     const uint4 cur = nxt;
     if (t + 16 <= hi) nxt = *reinterpret_cast<const uint4*>(x + t + 8);
     const uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
-    float o[8];
-    const bool emit = t >= lo;
+    float o[8], e[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int16_t sv = (int16_t)((i & 1) ? (w[i >> 1] >> 16) : (w[i >> 1] & 0xffffu));
-      const float out = f.step((float)sv * sc, emit, g);
-      o[i] = __fmul_rn(g, out);
+      o[i] = f.step((float)sv * sc, e[i]);
     }
-    if (emit) {
+    if (t >= lo) {
       *reinterpret_cast<float4*>(y + t) = make_float4(o[0], o[1], o[2], o[3]);
       *reinterpret_cast<float4*>(y + t + 4) = make_float4(o[4], o[5], o[6], o[7]);
+      *reinterpret_cast<float4*>(envo + t) = make_float4(e[0], e[1], e[2], e[3]);
+      *reinterpret_cast<float4*>(envo + t + 4) = make_float4(e[4], e[5], e[6], e[7]);
     }
   }
   for (; t < hi; ++t) {                                     // tail of the last chunk
-    const float out = f.step((float)x[t] * sc, t >= lo, g);
-    if (t >= lo) y[t] = __fmul_rn(g, out);
+    float e;
+    const float out = f.step((float)x[t] * sc, e);
+    if (t >= lo) {
+      y[t] = out;
+      envo[t] = e;
+    }
   }
+}
+
+// Compressor VCA: y *= env < thr ? 1 : (env / thr) ^ (1/ratio - 1)
+__global__ void fx_gain_kernel(float* __restrict__ y, const float* __restrict__ env, long long n, float thr, float thr_inv,
+                               float expo) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const float e = env[t];
+  const float g = (e < thr) ? 1.0f : powf(__fmul_rn(e, thr_inv), expo);
+  y[t] = __fmul_rn(g, y[t]);
 }
 
 struct CombDelays {
@@ -82,39 +97,53 @@ struct CombDelays {
 };
 
 // One thread block per comb filter; Y[j][t] = the value the comb writes into its delay line at time t.  The last R samples of
-// the delay line live in a shared-memory ring (R = power of two >= 2 D + K, zero-initialised = the empty delay line): a block of
-// D samples reads y[t-D-K+1 .. t-D] from it and writes y[t]; one barrier per block of D samples.
-__global__ void __launch_bounds__(1024) fx_comb_kernel(const float* __restrict__ x, float* __restrict__ Y, long long n,
-                                                       CombDelays dl, int ring_size, float gain, float damp, float omd, float fb,
-                                                       int K) {
+// the delay line live in a shared-memory ring (R = power of two >= 2 D + K, zero-initialised = the empty delay line; one pad
+// word per 32 so that the stride-8 accesses below are conflict-free).  The block walks the signal in steps of D samples with
+// one barrier per step; inside a step thread j owns the 8 CONSECUTIVE samples t = s + 8j .. s + 8j + 7: the damping low-pass
+// `last` is started with the K-term Horner form at the first of them and then advanced sequentially, exactly like the
+// reference loop.  Inputs are loaded one step ahead.
+constexpr int kCombRun = 8;
+__device__ __forceinline__ unsigned ring_at(unsigned u, unsigned mask) {
+  const unsigned r = u & mask;
+  return r + (r >> 5);
+}
+
+__global__ void __launch_bounds__(256) fx_comb_kernel(const float* __restrict__ x, float* __restrict__ Y, long long n,
+                                                      CombDelays dl, int ring_size, float gain, float damp, float omd, float fb,
+                                                      int K) {
   extern __shared__ float ring[];
   const int D = dl.d[blockIdx.x];
   const unsigned mask = (unsigned)ring_size - 1u;
   float* Yj = Y + (long long)blockIdx.x * n;
-  for (int i = threadIdx.x; i < ring_size; i += blockDim.x) ring[i] = 0.f;
+  for (int i = threadIdx.x; i < ring_size + (ring_size >> 5); i += blockDim.x) ring[i] = 0.f;
   __syncthreads();
-  // each thread owns the samples i = threadIdx.x and threadIdx.x + 1024 of every block of D (D <= 2048); their inputs are
-  // loaded one block ahead so that the global-memory latency is off the block-to-block critical path
-  const int i0 = threadIdx.x, i1 = threadIdx.x + 1024;
-  float xa = (i0 < D && i0 < n) ? x[i0] : 0.f;
-  float xb = (i1 < D && i1 < n) ? x[i1] : 0.f;
-  for (long long s = 0; s < n; s += D) {
-    const float ca = xa, cb = xb;
-    const long long na = s + D + i0, nb = s + D + i1;
-    xa = (i0 < D && na < n) ? x[na] : 0.f;
-    xb = (i1 < D && nb < n) ? x[nb] : 0.f;
+  const int i0 = threadIdx.x * kCombRun;                    // first sample of this thread inside a step
+  float xn[kCombRun];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int i = h ? i1 : i0;
-      const long long t = s + i;
-      if (i >= D || t >= n) continue;
-      const float xin = __fmul_rn(h ? cb : ca, gain);
+  for (int r = 0; r < kCombRun; ++r) xn[r] = (i0 + r < D && i0 + r < n) ? x[i0 + r] : 0.f;
+  for (long long s = 0; s < n; s += D) {
+    float xc[kCombRun];
+#pragma unroll
+    for (int r = 0; r < kCombRun; ++r) {
+      xc[r] = xn[r];
+      const long long nx = s + D + i0 + r;
+      xn[r] = (i0 + r < D && nx < n) ? x[nx] : 0.f;
+    }
+    if (i0 < D && s + i0 < n) {
+      const long long t0 = s + i0;
+      const unsigned u0 = (unsigned)(t0 - D);               // ring arithmetic is modulo 2^32, ring_size divides it
       float last = 0.f;
-      const unsigned u0 = (unsigned)(t - D);               // ring index arithmetic is modulo 2^32, ring_size divides it
-      for (int k = K - 1; k >= 0; --k) last = __fadd_rn(__fmul_rn(ring[(u0 - (unsigned)k) & mask], omd), __fmul_rn(last, damp));
-      const float y = __fadd_rn(xin, __fmul_rn(last, fb));
-      ring[(unsigned)t & mask] = y;
-      Yj[t] = y;
+      for (int k = K - 1; k >= 1; --k) last = __fadd_rn(__fmul_rn(ring[ring_at(u0 - (unsigned)k, mask)], omd), __fmul_rn(last, damp));
+#pragma unroll
+      for (int r = 0; r < kCombRun; ++r) {
+        const long long t = t0 + r;
+        if (i0 + r < D && t < n) {
+          last = __fadd_rn(__fmul_rn(ring[ring_at(u0 + (unsigned)r, mask)], omd), __fmul_rn(last, damp));
+          const float y = __fadd_rn(__fmul_rn(xc[r], gain), __fmul_rn(last, fb));
+          ring[ring_at((unsigned)t, mask)] = y;
+          Yj[t] = y;
+        }
+      }
     }
     __syncthreads();
   }
@@ -229,17 +258,18 @@ using namespace b200vc;
 
 extern "C" {
 
-int b200vc_fx_hpf_comp(const int16_t* x, float* y, int64_t n, int chunk, int warm, float b0, float b1, float a1, float cte_at,
-                       float cte_rl, float thr, float thr_inv, float expo, void* stream) {
-  B200VC_RECORD(b200vc_fx_hpf_comp(x, y, n, chunk, warm, b0, b1, a1, cte_at, cte_rl, thr, thr_inv, expo, stream));
-  B200VC_REQUIRE(x && y && n > 0 && chunk > 0 && warm >= 0, "fx_hpf_comp: bad args");
+int b200vc_fx_hpf_comp(const int16_t* x, float* y, float* env_scratch, int64_t n, int chunk, int warm, float b0, float b1, float a1,
+                       float cte_at, float cte_rl, float thr, float thr_inv, float expo, void* stream) {
+  B200VC_RECORD(b200vc_fx_hpf_comp(x, y, env_scratch, n, chunk, warm, b0, b1, a1, cte_at, cte_rl, thr, thr_inv, expo, stream));
+  B200VC_REQUIRE(x && y && env_scratch && n > 0 && chunk > 0 && warm >= 0, "fx_hpf_comp: bad args");
   B200VC_REQUIRE(chunk % 8 == 0 && warm % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
-                     (reinterpret_cast<uintptr_t>(y) & 15) == 0,
+                     (reinterpret_cast<uintptr_t>(y) & 15) == 0 && (reinterpret_cast<uintptr_t>(env_scratch) & 15) == 0,
                  "fx_hpf_comp: chunk / warm must be multiples of 8 and x / y 16-byte aligned");
   const long long chunks = (n + chunk - 1) / chunk;
-  HpfComp f{b0, b1, a1, cte_at, cte_rl, thr, thr_inv, expo, 0.f, 0.f};
-  fx_hpf_comp_kernel<<<(unsigned)((chunks + 31) / 32), 32, 0, (cudaStream_t)stream>>>(x, y, n, chunk, warm, f);
-  count_launch();
+  HpfEnv f{b0, b1, a1, cte_at, cte_rl, 0.f, 0.f};
+  fx_hpf_env_kernel<<<(unsigned)((chunks + 31) / 32), 32, 0, (cudaStream_t)stream>>>(x, y, env_scratch, n, chunk, warm, f);
+  fx_gain_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(y, env_scratch, n, thr, thr_inv, expo);
+  count_launch(2);
   B200VC_LAUNCH_CHECK();
   return kOk;
 }
@@ -254,16 +284,16 @@ int b200vc_fx_reverb_combs(const float* x, float* Y, float* comb_sum, int64_t n,
   }
   int dmax = 0;
   for (int j = 0; j < 8; ++j) dmax = dl.d[j] > dmax ? dl.d[j] : dmax;
-  B200VC_REQUIRE(dmax <= 2048, "fx_reverb_combs: comb delay %d > 2048 samples (sample rate above 55 kHz)", dmax);
+  B200VC_REQUIRE(dmax <= 256 * kCombRun, "fx_reverb_combs: comb delay %d > 2048 samples (sample rate above 55 kHz)", dmax);
   B200VC_REQUIRE(terms <= 256, "fx_reverb_combs: %d low-pass terms (damping too close to 1)", terms);
   int ring = 1024;
   while (ring < 2 * dmax + terms) ring *= 2;
   B200VC_REQUIRE(ring * sizeof(float) <= 200 * 1024, "fx_reverb_combs: delay lines of %d samples do not fit shared memory", dmax);
-  const size_t smem = ring * sizeof(float);
+  const size_t smem = (ring + ring / 32) * sizeof(float);
   if (smem > 48 * 1024)
     B200VC_CHECK_CUDA(cudaFuncSetAttribute(fx_comb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   auto launch = [=](cudaStream_t st) {
-    fx_comb_kernel<<<8, 1024, smem, st>>>(x, Y, n, dl, ring, gain, damp, 1.0f - damp, feedback, terms);
+    fx_comb_kernel<<<8, 256, smem, st>>>(x, Y, n, dl, ring, gain, damp, 1.0f - damp, feedback, terms);
     fx_comb_sum_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(Y, n, dl, comb_sum);
     count_launch(2);
   };

@@ -30,7 +30,7 @@ class MixSource(C.Structure):
                 ("out_rate", C.c_int32), ("pad_", C.c_int32), ("gain1", C.c_double), ("gain2", C.c_double)]
 
 
-_ffi.declare("b200vc_fx_hpf_comp", [_P, _P, _i64, _i32, _i32, _f32, _f32, _f32, _f32, _f32, _f32, _f32, _f32, _P])
+_ffi.declare("b200vc_fx_hpf_comp", [_P, _P, _P, _i64, _i32, _i32, _f32, _f32, _f32, _f32, _f32, _f32, _f32, _f32, _P])
 _ffi.declare("b200vc_fx_reverb_combs", [_P, _P, _P, _i64, C.POINTER(C.c_int), _f32, _f32, _f32, _i32, _P])
 _ffi.declare("b200vc_fx_allpass", [_P, _P, _i64, _i32, _i32, _P])
 _ffi.declare("b200vc_fx_finish", [_P, _P, _P, _P, _i64, _f32, _f32, _P])
@@ -114,12 +114,12 @@ def _effects_on_current_device(x, n, k, return_float):
     dev = x.device
     lib, s = _ffi.lib(), _stream()
     comp = torch.empty(n, device=dev)
+    a, b = torch.empty(n, device=dev), torch.empty(n, device=dev)
     warm = min(k.warm, ((n + 7) // 8) * 8)               # both multiples of 8: the kernel walks 8-sample groups
-    chunk = max(4096, warm)
-    _ffi.check(lib.b200vc_fx_hpf_comp(x.data_ptr(), comp.data_ptr(), n, chunk, warm, k.b0, k.b1, k.a1, k.cte_at, k.cte_rl, k.thr,
+    chunk = max(2048, (warm // 4 + 7) // 8 * 8)          # one thread per chunk, each walks warm + chunk samples
+    _ffi.check(lib.b200vc_fx_hpf_comp(x.data_ptr(), comp.data_ptr(), b.data_ptr(), n, chunk, warm, k.b0, k.b1, k.a1, k.cte_at, k.cte_rl, k.thr,
                                       k.thr_inv, k.expo, s), "fx_hpf_comp")
     lines = torch.empty(8, n, device=dev)
-    a, b = torch.empty(n, device=dev), torch.empty(n, device=dev)
     delays = (C.c_int * 8)(*k.comb_delays)
     _ffi.check(lib.b200vc_fx_reverb_combs(comp.data_ptr(), lines.data_ptr(), a.data_ptr(), n, delays, k.gain, k.damp, k.feedback,
                                           k.comb_terms, s), "fx_reverb_combs")

@@ -339,9 +339,10 @@ int b200vc_resample_sinc_mono(const float* x, int64_t n_in, int channels, float*
 /* pedalboard HighpassFilter (JUCE dsp::IIR first-order high-pass, TDF-II: y = b0 x + s; s = b1 x - a1 y) followed by
  * pedalboard Compressor (JUCE dsp::Compressor: peak BallisticsFilter env += cte (env - |y|) with cte = cte_at when rising else
  * cte_rl; gain = env < thr ? 1 : (env * thr_inv) ^ expo).  x: the int16 WAV samples (mono), read as x * 2^-15; y: float out.
- * The signal is processed in chunks of `chunk` samples, each recomputed from `warm` samples earlier with zero state. */
-int b200vc_fx_hpf_comp(const int16_t* x, float* y, int64_t n, int chunk, int warm, float b0, float b1, float a1, float cte_at,
-                       float cte_rl, float thr, float thr_inv, float expo, void* stream);
+ * The signal is processed in chunks of `chunk` samples, each recomputed from `warm` samples earlier with zero state (chunk, warm:
+ * multiples of 8; x, y, env_scratch [n]: 16-byte aligned); env_scratch receives the envelope. */
+int b200vc_fx_hpf_comp(const int16_t* x, float* y, float* env_scratch, int64_t n, int chunk, int warm, float b0, float b1, float a1,
+                       float cte_at, float cte_rl, float thr, float thr_inv, float expo, void* stream);
 
 /* juce::Reverb, mono: the eight parallel comb filters (delays8: HOST array; input x * gain, damping low-pass `damp`, feedback)
  * written as their delay-line contents Y [8, n] (scratch) and summed into comb_sum [n].  terms = Horner terms of the damping

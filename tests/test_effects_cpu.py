@@ -48,7 +48,8 @@ def test_restructured_effects_match_sequential_oracle(sr, params):
     room, wet, dry, damping = params
     want16, stages = oe.add_audio_effects(x, sr, room, wet, dry, damping, return_stages=True)
     k = fx.effect_constants(sr, room, wet, dry, damping)
-    got16, gotf, comp = emu.effects(x, k, chunk=max(4096, min(k.warm, x.size)), warm=min(k.warm, x.size))
+    warm = min(k.warm, (x.size + 7) // 8 * 8)
+    got16, gotf, comp = emu.effects(x, k, chunk=max(2048, (warm // 4 + 7) // 8 * 8), warm=warm)       # as effects.py sizes them
     assert np.abs(comp - stages[1]).max() < 2e-6                    # high-pass + compressor
     assert np.abs(gotf - stages[2]).max() < 5e-6                    # + reverb, wet/dry
     d = np.abs(got16.astype(np.int32) - want16.astype(np.int32))
