@@ -304,7 +304,9 @@ class VC(object):
             s = t
         segs.append((t if t is not None else 0, None, t // w if t is not None else 0, None))
         mine = [i for i in range(len(segs)) if i % world == rank]      # the others: another rank of the group converts them
-        overlap = (F0_OVERLAP and if_f0 == 1 and f0_method == "rmvpe" and hasattr(getattr(self, "model_rmvpe", None), "infer_from_audio_begin"))
+        # (single-GPU schedule; in a sharded run the ranks keep the validated order: F0 on rank 0 -> broadcast -> segments)
+        overlap = (F0_OVERLAP and world == 1 and if_f0 == 1 and f0_method == "rmvpe"
+                   and hasattr(getattr(self, "model_rmvpe", None), "infer_from_audio_begin"))
         halves = {}
         pending = None
         if overlap:
