@@ -100,6 +100,8 @@ def add_audio_effects_device(x_i16: torch.Tensor, sample_rate: int, reverb_rm_si
     if x_i16.dim() != 1 or x_i16.dtype != torch.int16:
         raise NotImplementedError("add_audio_effects: mono int16 input (the RVC output) only")
     x = x_i16.contiguous()
+    if x.data_ptr() % 16:
+        x = x.clone()                    # a view into a larger buffer: the kernel walks 128-bit groups
     n, dev = x.numel(), x.device
     if n == 0:
         return (x.clone(), torch.empty(0, device=dev)) if return_float else x.clone()

@@ -61,3 +61,38 @@ def test_effect_constants_delay_lines():
     assert k.comb_delays == (1012, 1077, 1158, 1229, 1289, 1352, 1412, 1466) and k.allpass_delays == (504, 400, 309, 204)
     assert abs(k.feedback - 0.742) < 1e-6 and abs(k.damp - 0.28) < 1e-6 and abs(k.wet1 - 0.6) < 1e-6 and abs(k.dry - 1.6) < 1e-6
     assert k.warm % 1024 == 0 and 0.9984 ** k.warm < 1e-9
+
+
+def test_mix_ragged_and_tiny_inputs():
+    """Edge cases of the overlay geometry: one-frame operands, vocals shorter / longer than the stems, all four RVC rates, mono
+    and stereo stems — closed form == CPython's audioop through the restated pydub glue, for 60 random cases."""
+    rng = np.random.default_rng(11)
+    for case in range(60):
+        sr_main = int(rng.choice([32000, 40000, 44100, 48000]))
+        n_main = int(rng.choice([1, 2, 3, 7, 45, 441, 1000, 4411, 20011]))
+        n_b = int(rng.choice([1, 2, 44, 999, 4410, 30000]))
+        n_i = int(rng.choice([1, 5, 441, 4409, 50000]))
+        ch_b = int(rng.choice([1, 2]))
+        mk = lambda n, ch: rng.integers(-32768, 32768, (n, ch) if ch > 1 else n).astype(np.int16)
+        main, backup, inst = mk(n_main, 1), mk(n_b, ch_b), mk(n_i, 2)
+        gains = tuple(float(g) for g in rng.choice([0, -3, 2.5, 6], 3))
+        want, rate = om.combine_audio(main, sr_main, backup, 44100, inst, 44100, *gains)
+        r, used, n_out = fx.mix_geometry([n_main, n_b, n_i], [sr_main, 44100, 44100])
+        assert (r, n_out) == (rate, want.shape[0]), (case, sr_main, n_main, n_b, n_i)
+        if n_out == 0:
+            continue
+        g = [(fx.db_to_float(b), fx.db_to_float(x)) for b, x in zip((-4, -6, -7), gains)]
+        got = emu.pydub_mix([main, backup, inst], [sr_main, 44100, 44100], g, r, used, n_out)
+        assert np.array_equal(got, want.reshape(n_out, -1)), (case, sr_main, n_main, n_b, n_i)
+
+
+@pytest.mark.parametrize("n", [1, 7, 8, 9, 1013, 4099, 15361])
+def test_restructured_effects_short_and_unaligned_lengths(n):
+    """Lengths below one comb delay, below the warm-up, and not multiples of the 8-sample group the kernel walks."""
+    x = _vocal(40000, 1.0, seed=n)[20000:20000 + n]
+    want16, stages = oe.add_audio_effects(x, 40000, 0.15, 0.2, 0.8, 0.7, return_stages=True)
+    k = fx.effect_constants(40000, 0.15, 0.2, 0.8, 0.7)
+    warm = min(k.warm, (n + 7) // 8 * 8)
+    got16, gotf, comp = emu.effects(x, k, chunk=max(2048, (warm // 4 + 7) // 8 * 8), warm=warm)
+    assert np.abs(comp - stages[1]).max() < 1e-6 and np.abs(gotf - stages[2]).max() < 2e-6
+    assert np.abs(got16.astype(np.int32) - want16.astype(np.int32)).max() <= 1
