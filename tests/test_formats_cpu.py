@@ -114,3 +114,66 @@ def test_onnx_convtdfnet_round_trip(tmp_path, fold_bn):
         for k_ in sd:
             if k_ != "_meta":
                 assert torch.equal(sd[k_].float(), sd2[k_].float()), k_
+
+
+def test_onnx_hand_assembled_protobuf_bytes(tmp_path):
+    """A ModelProto assembled BY HAND from the protobuf wire format and onnx.proto's field numbers — not through
+    write_convtdfnet_onnx — with what exporter-written files carry and this package's writer does not: ir_version /
+    producer / opset_import / doc_string fields to skip, graph inputs / outputs / value_info, unpacked (proto2-style) and packed
+    `dims`, `raw_data` and packed `float_data` initialisers, an int64 initialiser, float / int / ints / string / tensor
+    attributes, a negative int attribute (10-byte varint)."""
+    import struct
+
+    from aicovergen_b200.onnx_io import read_onnx
+
+    def vi(v):                       # varint
+        v &= (1 << 64) - 1
+        out = bytearray()
+        while True:
+            b = v & 0x7F
+            v >>= 7
+            out.append(b | (0x80 if v else 0))
+            if not v:
+                return bytes(out)
+
+    key = lambda fno, wt: vi((fno << 3) | wt)
+    ld = lambda fno, payload: key(fno, 2) + vi(len(payload)) + payload
+    w = np.arange(24, dtype=np.float32).reshape(2, 3, 4) - 7.5
+    # TensorProto: dims (1) unpacked varints, data_type (2) = 1 FLOAT, name (8), raw_data (9), doc_string (12, skipped)
+    t_raw = b"".join(key(1, 0) + vi(d) for d in w.shape) + key(2, 0) + vi(1) + ld(8, b"conv.weight") + ld(9, w.tobytes()) + ld(12, b"doc")
+    # TensorProto with packed dims and packed float_data (4)
+    b = np.array([0.5, -1.25, 3.0], dtype=np.float32)
+    t_flt = ld(1, vi(3)) + key(2, 0) + vi(1) + ld(4, struct.pack("<3f", *b)) + ld(8, b"conv.bias")
+    # int64 initialiser (a Reshape target), data_type 7, raw_data
+    shp = np.array([1, -1, 4], dtype=np.int64)
+    t_i64 = ld(1, vi(3)) + key(2, 0) + vi(7) + ld(8, b"shape") + ld(9, shp.tobytes())
+    # AttributeProto: name (1), f (2, fixed32), i (3), s (4), t (5), ints (8), type (20)
+    a_ints_packed = ld(1, b"kernel_shape") + ld(8, vi(3) + vi(3)) + key(20, 0) + vi(7)
+    a_ints_unpacked = ld(1, b"pads") + b"".join(key(8, 0) + vi(p) for p in (1, 1, 1, 1)) + key(20, 0) + vi(7)
+    a_int = ld(1, b"axis") + key(3, 0) + vi(-1) + key(20, 0) + vi(2)
+    a_flt = ld(1, b"epsilon") + key(2, 5) + struct.pack("<f", 1e-5) + key(20, 0) + vi(1)
+    a_str = ld(1, b"auto_pad") + ld(4, b"NOTSET") + key(20, 0) + vi(3)
+    a_tensor = ld(1, b"value") + ld(5, t_i64) + key(20, 0) + vi(4)
+    n_conv = ld(1, b"x") + ld(1, b"conv.weight") + ld(1, b"conv.bias") + ld(2, b"y") + ld(3, b"Conv_0") + ld(4, b"Conv") + \
+        ld(5, a_ints_packed) + ld(5, a_ints_unpacked) + ld(5, a_str) + ld(7, b"")          # domain (7) = ""
+    n_bn = ld(1, b"y") + ld(2, b"z") + ld(4, b"BatchNormalization") + ld(5, a_flt)
+    n_cat = ld(1, b"z") + ld(1, b"z") + ld(2, b"c") + ld(4, b"Concat") + ld(5, a_int)
+    n_const = ld(2, b"k") + ld(4, b"Constant") + ld(5, a_tensor)
+    value_info = ld(1, b"x") + ld(2, ld(1, key(1, 0) + vi(1)))                             # ValueInfoProto{name, type{tensor_type{elem_type}}}
+    graph = ld(1, n_conv) + ld(1, n_bn) + ld(1, n_cat) + ld(1, n_const) + ld(2, b"torch_jit") + ld(5, t_raw) + ld(5, t_flt) + \
+        ld(5, t_i64) + ld(10, b"graph doc") + ld(11, value_info) + ld(12, value_info) + ld(13, value_info)
+    opset = ld(1, b"") + key(2, 0) + vi(11)
+    model = key(1, 0) + vi(6) + ld(2, b"pytorch") + ld(3, b"1.10") + ld(7, graph) + ld(8, opset) + key(5, 0) + vi(0)
+    path = tmp_path / "hand.onnx"
+    path.write_bytes(model)
+
+    inits, nodes = read_onnx(str(path))
+    assert set(inits) == {"conv.weight", "conv.bias", "shape"}
+    assert inits["conv.weight"].dtype == np.float32 and np.array_equal(inits["conv.weight"], w)
+    assert np.array_equal(inits["conv.bias"], b) and inits["conv.bias"].shape == (3,)
+    assert inits["shape"].dtype == np.int64 and inits["shape"].tolist() == [1, -1, 4]
+    assert [n.op_type for n in nodes] == ["Conv", "BatchNormalization", "Concat", "Constant"]
+    conv = nodes[0]
+    assert conv.inputs == ["x", "conv.weight", "conv.bias"] and conv.outputs == ["y"] and conv.name == "Conv_0"
+    assert conv.attrs["kernel_shape"] == [3, 3] and conv.attrs["pads"] == [1, 1, 1, 1]
+    assert abs(nodes[1].attrs["epsilon"] - 1e-5) < 1e-12 and nodes[2].attrs["axis"] == -1
